@@ -1,0 +1,154 @@
+/* SPDX-License-Identifier: MIT
+ *
+ * markov_b200.h — C ABI of libmarkov_b200.so: the B200-native (sm_100a) drop-in for
+ * MarkovModels.jl's batched semiring inference path.
+ *
+ * The reference has no FFI: its "operator API" is Julia method dispatch from
+ * src/inference.jl onto the GPU methods of src/linalg.jl (mul!, blockdiag, vcat,
+ * broadcast!).  This boundary sits one level higher so that the per-frame host
+ * loop (src/inference.jl:69-72,105-108) moves into the kernels.  Each entry point
+ * names the reference interface it replaces.  A Julia shim binds these with
+ * ccall; tests/bench bind them with ctypes.
+ *
+ * Conventions
+ *   - every call returns an int status (MK_OK == 0); mk_last_error() gives the
+ *     message of the calling thread's last failure.  No exceptions cross the ABI.
+ *   - DimensionMismatch (src/linalg.jl:166-167,242-244) maps to MK_EINVAL.
+ *   - handles are immutable after creation except for their private workspace:
+ *     one in-flight call per mk_batch at a time; distinct batches may run
+ *     concurrently on distinct streams.
+ *   - "device" pointers are CUDA device pointers on the graph's device; the call
+ *     is asynchronous on `stream` (a cudaStream_t passed as void*), like CUDA.jl
+ *     launches on the task-local stream.  `_host` variants take host pointers,
+ *     do the H2D/D2H copies themselves and return after synchronising.
+ *   - payload floats only: Matrix{LogSemiring{Float32}} is bit-identical to
+ *     Matrix{Float32}, so buffers are passed as float* / double*.
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry
+ *     point fails with MK_ECUDA.
+ */
+#ifndef MARKOV_B200_H
+#define MARKOV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MK_ABI_VERSION 1
+
+enum mk_status {
+    MK_OK = 0,
+    MK_EINVAL = 22,   /* dimension mismatch / bad argument  (DimensionMismatch) */
+    MK_ENOMEM = 12,   /* host or device allocation failed */
+    MK_ENOTSUP = 95,  /* valid request the library does not implement */
+    MK_ECUDA = 1000   /* CUDA runtime error; text in mk_last_error() */
+};
+
+/* Semirings.jl types the path is instantiated with (src/MarkovModels.jl:12). */
+enum mk_semiring { MK_LOG = 0, MK_TROPICAL = 1 };
+enum mk_dtype { MK_F32 = 0, MK_F64 = 1 };
+
+typedef struct mk_graph mk_graph; /* one compiled FSM resident on one GPU */
+typedef struct mk_batch mk_batch; /* ragged batch of graphs (virtual rawunion) */
+
+int mk_abi_version(void);
+const char* mk_last_error(void);
+
+/* Number of CUDA devices visible (0 when none / no driver). */
+int mk_device_count(void);
+
+/* FSM + compile + adapt(CuArray, ·)   — src/fsm.jl:7-28,42-48, src/inference.jl:3-26.
+ *
+ * The graph is the reference's extended matrix T̂ = [T ω; 0̄ 1̄] (phony final state
+ * last, src/fsm.jl:22-27) exactly as the CPU FSM stores it, a
+ * SparseMatrixCSC{K,Int64}: colptr (n_states_hat+1), rowval (nnz_hat), nzval
+ * (nnz_hat) — column = destination state, rowval = source state.  α̂ is the
+ * SparseVector nzind/nzval pair.  index_base is 1 for Julia arrays, 0 for C.
+ * state2pdf[s] (same base) replaces Ĉ/Ĉᵀ: Ĉ has exactly one 1̄ per row
+ * (examples/prepare-lfmmi-graphs.jl:15-23); the phony state must map to the phony
+ * pdf n_pdf_hat (1-based) / n_pdf_hat-1 (0-based).  Inputs are copied; the caller
+ * keeps ownership.  The library builds both orientations (T̂ and T̂ᵀ, the
+ * copy(T̂') of src/inference.jl:12) on the device `device` (-1 = current). */
+int mk_graph_create(mk_graph** out, int semiring, int dtype, int64_t n_states_hat,
+                    int64_t nnz_hat, const int64_t* colptr, const int64_t* rowval,
+                    const void* nzval, int64_t n_init, const int64_t* init_idx,
+                    const void* init_w, const int32_t* state2pdf, int64_t n_pdf_hat,
+                    int index_base, int device);
+int mk_graph_destroy(mk_graph* g);
+int mk_graph_info(const mk_graph* g, int64_t* n_states_hat, int64_t* nnz_hat,
+                  int64_t* n_pdf_hat, int* semiring, int* dtype);
+
+/* rawunion / batch   — src/fsmops.jl:28-36, src/inference.jl:28-36 (+ GPU blockdiag/vcat,
+ * src/linalg.jl:73-157).  No block-diagonal matrix is materialised: the batch is a
+ * descriptor; identical handles are stored once (the replicated denominator).  State
+ * numbering of the virtual union is concatenation order: utterance b owns rows
+ * [off_b, off_b + Ŝ_b).  All graphs must share semiring, dtype, device, n_pdf_hat. */
+int mk_batch_create(mk_batch** out, mk_graph* const* graphs, int64_t B);
+int mk_batch_destroy(mk_batch* b);
+int mk_batch_info(const mk_batch* b, int64_t* B, int64_t* total_states_hat);
+
+/* Emission argument shared by the calls below.
+ * `ll` points at payload floats; element (b, d, n) (0-based utterance, pdf, frame)
+ * lives at ll[b*stride_b + d*stride_d + n*stride_n] (strides in elements).
+ *   expanded == 0: ll holds the un-padded D x T likelihoods; `expand`
+ *       (src/inference.jl:54-60) is applied inside using seqlens (host int32[B] or
+ *       NULL = all T): D̂ = D+1 must equal the graphs' n_pdf_hat, N̂ = T+1.
+ *   expanded == 1: ll already holds the D̂ x N̂ matrices V̂ the reference's callers
+ *       pass (examples/test_cuda.jl:124-128); then D == n_pdf_hat, T == N̂, seqlens
+ *       must be NULL.
+ */
+
+/* αrecursion / βrecursion   — src/inference.jl:62-74, :99-110.
+ * out: (ΣŜ_b) x N̂ column-major payload array on the device (state fastest). */
+int mk_alpha(mk_batch* b, const void* ll, int64_t stride_b, int64_t stride_d, int64_t stride_n,
+             int64_t D, int64_t T, int expanded, const int32_t* seqlens, void* out_A,
+             void* stream);
+int mk_beta(mk_batch* b, const void* ll, int64_t stride_b, int64_t stride_d, int64_t stride_n,
+            int64_t D, int64_t T, int expanded, const int32_t* seqlens, void* out_B,
+            void* stream);
+
+/* pdfposteriors   — src/inference.jl:145-161 (and pdfposteriors2 :164-180).
+ * out_post: the reference's (B, D, N) column-major array (b fastest), exp-domain,
+ * real pdfs and real frames only (Ẑ[:, 1:end-1, 1:end-1], :160).  out_logz: B
+ * totals (the reference's `ttl`, minimum over frames of the per-frame sums, :159).
+ * Unreachable final state: posteriors 0, logz -Inf (the pdfposteriors3 convention,
+ * src/inference.jl:198-200). */
+int mk_pdfposteriors(mk_batch* b, const void* ll, int64_t stride_b, int64_t stride_d,
+                     int64_t stride_n, int64_t D, int64_t T, int expanded,
+                     const int32_t* seqlens, void* out_post, void* out_logz, void* stream);
+
+/* bestpath   — absent from the 0.10.0 sources (src/MarkovModels.jl:56-57 are commented
+ * exports); historical signature test/test_algorithms.jl:279-281.  Tropical graphs only,
+ * expanded must be 0.  out_path: int32 [B][T] (utterance-major), 1-based state ids local
+ * to each utterance's graph for frames < seqlens[b], 0 after; ties resolve to the
+ * smallest predecessor index.  out_score: B path scores (-Inf and an all-zero path
+ * when the final state is unreachable). */
+int mk_bestpath(mk_batch* b, const void* ll, int64_t stride_b, int64_t stride_d,
+                int64_t stride_n, int64_t D, int64_t T, int expanded, const int32_t* seqlens,
+                int32_t* out_path, void* out_score, void* stream);
+
+/* Host-buffer variants: what a caller holding CPU arrays (the reference's CPU
+ * FSM path) calls.  ll/out_* are HOST pointers (pinned gives full PCIe rate);
+ * copies in, computes, copies out, synchronises. */
+int mk_pdfposteriors_host(mk_batch* b, const void* ll, int64_t stride_b, int64_t stride_d,
+                          int64_t stride_n, int64_t D, int64_t T, int expanded,
+                          const int32_t* seqlens, void* out_post, void* out_logz);
+int mk_bestpath_host(mk_batch* b, const void* ll, int64_t stride_b, int64_t stride_d,
+                     int64_t stride_n, int64_t D, int64_t T, int expanded,
+                     const int32_t* seqlens, int32_t* out_path, void* out_score);
+
+/* Instrumentation: number of kernels this library launched on the calling thread since
+ * the last reset (bench.py's gpu_launches), and workspace bytes held by a batch. */
+int64_t mk_launch_count(int reset);
+int64_t mk_batch_workspace_bytes(const mk_batch* b);
+/* When enabled, CUDA events are recorded (on the call's stream) around the dominant kernel of
+ * the next calls — the shared-graph forward-backward kernel; mk_batch_last_kernel_ms waits for
+ * the last recorded pair and returns its duration (of the batch's last shared-graph group). */
+int mk_batch_profile(mk_batch* b, int enable);
+int mk_batch_last_kernel_ms(mk_batch* b, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARKOV_B200_H */

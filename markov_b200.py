@@ -1,0 +1,13 @@
+# SPDX-License-Identifier: MIT
+"""Import alias: the package directory is ``markovmodels.jl_b200`` (not a valid identifier);
+``import markov_b200`` loads it under this name."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "markovmodels.jl_b200")
+_spec = importlib.util.spec_from_file_location(
+    "markov_b200", os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["markov_b200"] = _mod
+_spec.loader.exec_module(_mod)

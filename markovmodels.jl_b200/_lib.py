@@ -1,0 +1,113 @@
+# SPDX-License-Identifier: MIT
+"""ctypes binding of ``libmarkov_b200.so`` (the C ABI of ``include/markov_b200.h``).
+
+The library is built in-tree (``csrc/libmarkov_b200.so``) by :func:`build`.  There is no CPU
+fallback: if the shared object is missing, loading raises; if no CUDA device is usable, every
+compute entry point returns ``MK_ECUDA`` and the wrappers raise :class:`MarkovError`.
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libmarkov_b200.so")
+INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "markov_b200.h")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+MK_OK, MK_EINVAL, MK_ENOMEM, MK_ENOTSUP, MK_ECUDA = 0, 22, 12, 95, 1000
+
+
+class MarkovError(RuntimeError):
+    """A failed libmarkov_b200 call.  ``code == MK_EINVAL`` is the reference's
+    ``DimensionMismatch`` (src/linalg.jl:166-167)."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"libmarkov_b200 error {code}: {msg}")
+        self.code = code
+
+
+class DimensionMismatch(MarkovError, ValueError):
+    pass
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))] + [INCLUDE]
+    return any(os.path.getmtime(s) > t for s in srcs)
+
+
+def build(force=False, verbose=False):
+    """Compile ``csrc/*.cu`` for sm_100a into ``csrc/libmarkov_b200.so`` (nvcc cross-compiles
+    without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "markov_b200.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+_i64, _i32, _vp = C.c_int64, C.c_int32, C.c_void_p
+_EMIS = [_vp, _i64, _i64, _i64, _i64, _i64, C.c_int, C.POINTER(_i32)]  # ll, sb, sd, sn, D, T, expanded, seqlens
+
+SIGNATURES = {
+    "mk_abi_version": (C.c_int, []),
+    "mk_last_error": (C.c_char_p, []),
+    "mk_device_count": (C.c_int, []),
+    "mk_graph_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp,
+                                  _vp, _i64, C.c_int, C.c_int]),
+    "mk_graph_destroy": (C.c_int, [_vp]),
+    "mk_graph_info": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(C.c_int),
+                                C.POINTER(C.c_int)]),
+    "mk_batch_create": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), _i64]),
+    "mk_batch_destroy": (C.c_int, [_vp]),
+    "mk_batch_info": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    "mk_alpha": (C.c_int, [_vp] + _EMIS + [_vp, _vp]),
+    "mk_beta": (C.c_int, [_vp] + _EMIS + [_vp, _vp]),
+    "mk_pdfposteriors": (C.c_int, [_vp] + _EMIS + [_vp, _vp, _vp]),
+    "mk_bestpath": (C.c_int, [_vp] + _EMIS + [_vp, _vp, _vp]),
+    "mk_pdfposteriors_host": (C.c_int, [_vp] + _EMIS + [_vp, _vp]),
+    "mk_bestpath_host": (C.c_int, [_vp] + _EMIS + [_vp, _vp]),
+    "mk_launch_count": (_i64, [C.c_int]),
+    "mk_batch_workspace_bytes": (_i64, [_vp]),
+    "mk_batch_profile": (C.c_int, [_vp, C.c_int]),
+    "mk_batch_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+}
+
+
+def lib():
+    """The loaded library.  Raises if it has not been built — there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(libmarkov_b200 has no CPU fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        if l.mk_abi_version() != 1:
+            raise RuntimeError("libmarkov_b200.so ABI version mismatch; rebuild")
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != MK_OK:
+        msg = lib().mk_last_error().decode("utf-8", "replace")
+        raise (DimensionMismatch if rc == MK_EINVAL else MarkovError)(rc, msg)

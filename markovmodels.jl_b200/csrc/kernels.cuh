@@ -1,0 +1,649 @@
+// SPDX-License-Identifier: MIT
+//
+// kernels.cuh — sm_100a device code of libmarkov_b200.so.
+//
+// Two kernel families implement the reference's time recursions
+// (src/inference.jl:62-74 αrecursion, :99-110 βrecursion, :145-161 pdfposteriors)
+// with the host-side frame loop moved on to the device:
+//
+//  * shared_fb_kernel  — a group of U utterances that share ONE graph (the replicated
+//    LF-MMI denominator).  Persistent cooperative grid, one CTA per SM.  State vectors
+//    live in global memory as [state][utterance] so that one arc (src -> dst, w) is
+//    loaded once and applied to 128 utterances: lane l owns utterances 4l..4l+3 and
+//    fetches them with one 16-byte load, a warp therefore gathers one contiguous 512 B
+//    segment per arc (L2-resident: two frames of state are 2*Ŝ*U*4 B ≈ 31 MB ≪ 126 MB).
+//    No cross-lane reduction is needed; the ⊕ over a row's arcs runs per lane.  Rows are
+//    split over warps by arc count.  One grid barrier per frame.
+//    Replaces K1 (SpMV per frame), K2 (Ĉ·V̂ gather, Ĉᵀ scatter-reduce), K3 (α̂ ⊙ e₁), K4
+//    (per-frame broadcasts, γ, exp, sums) of SURVEY.md §2.2.
+//
+//  * small_fb_kernel — one CTA per utterance for graphs that fit shared memory (LF-MMI
+//    numerators: a few hundred states each, all distinct).  α/β vectors ping-pong in
+//    shared memory, arcs come through L1, one __syncthreads per frame.
+//
+// Semiring arithmetic (Semirings.jl): Log ⊕ = log-sum-exp evaluated as
+// max + log(Σ exp(x - max)) over a register-cached chunk of arcs (one ex2 per arc, one
+// rescale ex2 per further 8-arc chunk, one lg2 per row); Tropical ⊕ = max.  ⊗ = +.  -Inf is
+// the semiring zero and never produces NaN (the max of an all--Inf row is replaced by 0
+// before subtracting).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mk {
+
+enum { SR_LOG = 0, SR_TROP = 1 };
+
+constexpr int kSharedThreads = 512;  // 16 warps / CTA, 1 CTA / SM
+constexpr int kSharedWarps = kSharedThreads / 32;
+constexpr int kChunk = 8;       // arcs cached in registers per ⊕ chunk
+constexpr int kTileUtts = 128;  // utterances covered by one warp pass (32 lanes x 4)
+
+template <typename T> struct Arc {
+    int idx;  // source state (in-arcs, forward) or destination state (out-arcs, backward)
+    T w;
+};
+static_assert(sizeof(Arc<float>) == 8, "arc f32 = 8 B");
+static_assert(sizeof(Arc<double>) == 16, "arc f64 = 16 B");
+
+template <typename T> __device__ __forceinline__ T neg_inf();
+template <> __device__ __forceinline__ float neg_inf<float>() { return __int_as_float(0xff800000); }
+template <> __device__ __forceinline__ double neg_inf<double>() {
+    return __longlong_as_double(0xfff0000000000000LL);
+}
+
+// ---- scalar math ---------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float exp_(float x) { return ex2_approx(x * 1.4426950408889634f); }
+__device__ __forceinline__ double exp_(double x) { return exp(x); }
+__device__ __forceinline__ float log_(float x) { return lg2_approx(x) * 0.6931471805599453f; }
+__device__ __forceinline__ double log_(double x) { return log(x); }
+__device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
+
+// ---- arc and 4-wide vector access --------------------------------------------------------------
+__device__ __forceinline__ Arc<float> ld_arc(const Arc<float>* p) {
+    int2 t = __ldg(reinterpret_cast<const int2*>(p));
+    Arc<float> a; a.idx = t.x; a.w = __int_as_float(t.y); return a;
+}
+__device__ __forceinline__ Arc<double> ld_arc(const Arc<double>* p) {
+    int4 t = __ldg(reinterpret_cast<const int4*>(p));
+    Arc<double> a; a.idx = t.x; a.w = __hiloint2double(t.w, t.z); return a;
+}
+
+template <typename T> struct V4 { T v[4]; };
+
+// L2-coherent (L1-bypassing) accesses: the state vectors are rewritten by other SMs each frame.
+__device__ __forceinline__ V4<float> ld4_cg(const float* p) {
+    float4 t = __ldcg(reinterpret_cast<const float4*>(p));
+    V4<float> r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
+}
+__device__ __forceinline__ V4<double> ld4_cg(const double* p) {
+    double2 a = __ldcg(reinterpret_cast<const double2*>(p));
+    double2 b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+    V4<double> r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; return r;
+}
+// streaming (read-once) loads: the α store on the backward sweep, emissions
+__device__ __forceinline__ V4<float> ld4_cs(const float* p) {
+    float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+    V4<float> r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
+}
+__device__ __forceinline__ V4<double> ld4_cs(const double* p) {
+    double2 a = __ldcs(reinterpret_cast<const double2*>(p));
+    double2 b = __ldcs(reinterpret_cast<const double2*>(p) + 1);
+    V4<double> r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; return r;
+}
+__device__ __forceinline__ void st4_cg(float* p, const V4<float>& x) {
+    __stcg(reinterpret_cast<float4*>(p), make_float4(x.v[0], x.v[1], x.v[2], x.v[3]));
+}
+__device__ __forceinline__ void st4_cg(double* p, const V4<double>& x) {
+    __stcg(reinterpret_cast<double2*>(p), make_double2(x.v[0], x.v[1]));
+    __stcg(reinterpret_cast<double2*>(p) + 1, make_double2(x.v[2], x.v[3]));
+}
+
+// posterior accumulation into the (B, D, N) output: Log -> add, Tropical -> max
+__device__ __forceinline__ void red_add4(float* p, const V4<float>& x) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x.v[0]),
+                 "f"(x.v[1]), "f"(x.v[2]), "f"(x.v[3])
+                 : "memory");
+}
+__device__ __forceinline__ void red_add4(double* p, const V4<double>& x) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(p + j, x.v[j]);
+}
+// values are >= 0 so the IEEE bit patterns order like signed integers
+__device__ __forceinline__ void red_max1(float* p, float x) {
+    atomicMax(reinterpret_cast<int*>(p), __float_as_int(x));
+}
+__device__ __forceinline__ void red_max1(double* p, double x) {
+    atomicMax(reinterpret_cast<long long*>(p), __double_as_longlong(x));
+}
+template <int SR, typename T> __device__ __forceinline__ void red1(T* p, T x) {
+    if (SR == SR_LOG) atomicAdd(p, x);
+    else red_max1(p, x);
+}
+template <int SR, typename T> __device__ __forceinline__ T lin_add(T a, T b) {
+    return SR == SR_LOG ? a + b : max_(a, b);
+}
+
+// ---- grid barrier ------------------------------------------------------------------------------
+// Monotonic counter; the kernel is launched cooperatively (all CTAs co-resident).  Writers'
+// stores are ordered by bar.sync + fence + the atomic; the waiting thread uses an acquire load
+// and every consumer then reads other CTAs' data with L1-bypassing loads only (ld4_cg).
+__device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
+// ---- per-lane ⊕ over one row's arcs for 4 utterances -------------------------------------------
+// One chunk of CNT arcs: gather CNT x 16 B, then fold into the running (m, s) pair (Log) or
+// into m (Tropical).
+template <typename T, int SR, int CNT>
+__device__ __forceinline__ void chunk_fold(const Arc<T>* __restrict__ arcs, const T* vec, int U4,
+                                           int uoff, bool first, T (&m)[4], T (&s)[4]) {
+    T x[CNT][4];
+#pragma unroll
+    for (int k = 0; k < CNT; ++k) {
+        Arc<T> a = ld_arc(arcs + k);
+        V4<T> v = ld4_cg(vec + size_t(a.idx) * U4 + uoff);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[k][j] = v.v[j] + a.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        T mc = x[0][j];
+#pragma unroll
+        for (int k = 1; k < CNT; ++k) mc = max_(mc, x[k][j]);
+        if (SR == SR_TROP) {
+            m[j] = max_(m[j], mc);
+        } else {
+            T mn = first ? mc : max_(m[j], mc);
+            T ms = (mn == neg_inf<T>()) ? T(0) : mn;
+            T acc = first ? T(0) : s[j] * exp_(m[j] - ms);
+#pragma unroll
+            for (int k = 0; k < CNT; ++k) acc += exp_(x[k][j] - ms);
+            s[j] = acc;
+            m[j] = mn;
+        }
+    }
+}
+
+// vec: [state][U4] payload; uoff: this lane's utterance offset (multiple of 4).
+template <typename T, int SR>
+__device__ __forceinline__ V4<T> row_reduce(const Arc<T>* __restrict__ arcs, int beg, int end,
+                                            const T* vec, int U4, int uoff) {
+    T m[4], s[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { m[j] = neg_inf<T>(); s[j] = T(0); }
+    int a = beg;
+    bool first = true;
+    for (; a + kChunk <= end; a += kChunk) {
+        chunk_fold<T, SR, kChunk>(arcs + a, vec, U4, uoff, first, m, s);
+        first = false;
+    }
+    switch (end - a) {  // warp-uniform
+        case 1: chunk_fold<T, SR, 1>(arcs + a, vec, U4, uoff, first, m, s); break;
+        case 2: chunk_fold<T, SR, 2>(arcs + a, vec, U4, uoff, first, m, s); break;
+        case 3: chunk_fold<T, SR, 3>(arcs + a, vec, U4, uoff, first, m, s); break;
+        case 4: chunk_fold<T, SR, 4>(arcs + a, vec, U4, uoff, first, m, s); break;
+        case 5: chunk_fold<T, SR, 5>(arcs + a, vec, U4, uoff, first, m, s); break;
+        case 6: chunk_fold<T, SR, 6>(arcs + a, vec, U4, uoff, first, m, s); break;
+        case 7: chunk_fold<T, SR, 7>(arcs + a, vec, U4, uoff, first, m, s); break;
+        default: break;
+    }
+    V4<T> out;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (SR == SR_TROP) out.v[j] = m[j];
+        else out.v[j] = (s[j] > T(0)) ? m[j] + log_(s[j]) : neg_inf<T>();
+    }
+    return out;
+}
+
+// ================================================================================================
+// Shared-graph kernel
+// ================================================================================================
+template <typename T> struct SharedParams {
+    int S;       // Ŝ states incl. phony final (last)
+    int Dh;      // D̂ pdfs incl. phony (last)
+    int N1;      // N̂ frames incl. phony (last)
+    int U4;      // utterances in the group, padded to a multiple of 4
+    int ntiles;  // ceil(U4 / 128)
+    const int* in_ptr;  const Arc<T>* in_arcs;    // T̂ᵀ rows (by destination)
+    const int* out_ptr; const Arc<T>* out_arcs;   // T̂ rows (by source)
+    const int* pdf;                               // state -> pdf (0-based)
+    const T* init_dense;                          // α̂ as a dense vector [S]
+    const int* fwd_rows;                          // [grid*warps + 1] row ranges per warp
+    const int* bwd_rows;
+    const T* E;      // expanded, transposed emissions [N1][Dh][U4]
+    T* alpha;        // [N1][S][U4]
+    T* bt;           // [2][S][U4]   β_{n+1} ⊗ e_{n+1} ping-pong
+    T* beta_out;     // optional [N1][S][U4]
+    // posterior output, the reference's (B, D, N) b-fastest array
+    T* post; int B; int D; int Tn;
+    const int* utt_b;  // [U4] global utterance index per group lane (-1 = padding)
+    int post_vec4;     // 1: the 4 utterances of every lane are b0..b0+3, 16 B aligned
+    T* zsum;           // [N1][B] per-frame normalisers (linear, relative to lz)
+    T* lz;             // [B] forward total log-likelihood (reference for γ)
+    unsigned* barrier;
+    int do_fwd, do_bwd, do_post;
+};
+
+template <typename T, int SR>
+__global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(SharedParams<T> p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* s_lz = reinterpret_cast<T*>(smem_raw);  // [U4]
+    T* s_z = s_lz + p.U4;                      // [U4]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * kSharedWarps + warp;
+    const int S = p.S, U4 = p.U4;
+    const size_t frame = size_t(S) * U4;
+    unsigned bar_target = 0;
+
+    // ---------------------------------------------------------------- forward (αrecursion)
+    if (p.do_fwd) {
+        const int r0 = p.fwd_rows[gw], r1 = p.fwd_rows[gw + 1];
+        for (int n = 0; n < p.N1; ++n) {
+            const T* prev = p.alpha + size_t(n > 0 ? n - 1 : 0) * frame;
+            T* cur = p.alpha + size_t(n) * frame;
+            const T* En = p.E + size_t(n) * p.Dh * U4;
+            for (int tile = 0; tile < p.ntiles; ++tile) {
+                const int uoff = tile * kTileUtts + lane * 4;
+                if (uoff >= U4) continue;
+                for (int r = r0; r < r1; ++r) {
+                    V4<T> acc;
+                    if (n == 0) {
+                        T a0 = __ldg(p.init_dense + r);  // A[:,1] = α̂ ⊗ e₁  (:68)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc.v[j] = a0;
+                    } else {
+                        acc = row_reduce<T, SR>(p.in_arcs, __ldg(p.in_ptr + r), __ldg(p.in_ptr + r + 1),
+                                                prev, U4, uoff);  // T̂ᵀ A[:,n-1]  (:70)
+                    }
+                    V4<T> e = ld4_cs(En + size_t(__ldg(p.pdf + r)) * U4 + uoff);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc.v[j] += e.v[j];  // ⊗ e_n  (:71)
+                    st4_cg(cur + size_t(r) * U4 + uoff, acc);
+                }
+            }
+            grid_sync(p.barrier, bar_target);
+        }
+        // total log-likelihood = α_{N̂}[phony final]
+        const T* last = p.alpha + size_t(p.N1 - 1) * frame + size_t(S - 1) * U4;
+        if (blockIdx.x == 0)
+            for (int u = threadIdx.x; u < U4; u += blockDim.x) {
+                int b = p.utt_b[u];
+                if (b >= 0) p.lz[b] = __ldcg(last + u);
+            }
+    }
+    if (!p.do_bwd) return;
+
+    // ---------------------------------------------------------------- backward (βrecursion + γ)
+    if (p.do_post) {
+        const T* last = p.alpha + size_t(p.N1 - 1) * frame + size_t(S - 1) * U4;
+        for (int u = threadIdx.x; u < U4; u += blockDim.x) {
+            s_lz[u] = __ldcg(last + u);
+            s_z[u] = T(0);
+        }
+        __syncthreads();
+    }
+    const int r0 = p.bwd_rows[gw], r1 = p.bwd_rows[gw + 1];
+    for (int n = p.N1 - 1; n >= 0; --n) {
+        const T* bt_next = p.bt + size_t((n + 1) & 1) * frame;
+        T* bt_cur = p.bt + size_t(n & 1) * frame;
+        const T* En = p.E + size_t(n) * p.Dh * U4;
+        const T* An = p.alpha + size_t(n) * frame;
+        for (int tile = 0; tile < p.ntiles; ++tile) {
+            const int uoff = tile * kTileUtts + lane * 4;
+            if (uoff >= U4) continue;
+            T zs[4] = {T(0), T(0), T(0), T(0)};
+            V4<T> lz;
+            if (p.do_post) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    T v = s_lz[uoff + j];
+                    lz.v[j] = (v == neg_inf<T>()) ? T(0) : v;
+                }
+            }
+            for (int i = r0; i < r1; ++i) {
+                V4<T> beta;
+                if (n == p.N1 - 1) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) beta.v[j] = T(0);  // B[:,end] = 1̄  (:104)
+                } else {
+                    beta = row_reduce<T, SR>(p.out_arcs, __ldg(p.out_ptr + i), __ldg(p.out_ptr + i + 1),
+                                             bt_next, U4, uoff);  // T̂ (B[:,n+1] ⊗ e_{n+1})  (:106-107)
+                }
+                const int pdf = __ldg(p.pdf + i);
+                if (p.beta_out) st4_cg(p.beta_out + size_t(n) * frame + size_t(i) * U4 + uoff, beta);
+                if (p.do_post) {
+                    // γ = α ⊗ β ⊘ logZ, exp, per-pdf ⊕  (:154-160)
+                    V4<T> a = ld4_cs(An + size_t(i) * U4 + uoff);
+                    V4<T> pg;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        pg.v[j] = exp_(a.v[j] + beta.v[j] - lz.v[j]);
+                        zs[j] = lin_add<SR>(zs[j], pg.v[j]);
+                    }
+                    if (n < p.Tn && pdf < p.D) {
+                        T* dst = p.post + (size_t(n) * p.D + pdf) * p.B;
+                        if (p.post_vec4 && SR == SR_LOG) {
+                            red_add4(dst + p.utt_b[uoff], pg);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                int b = p.utt_b[uoff + j];
+                                if (b >= 0) red1<SR>(dst + b, pg.v[j]);
+                            }
+                        }
+                    }
+                }
+                if (n > 0) {
+                    V4<T> e = ld4_cs(En + size_t(pdf) * U4 + uoff);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) beta.v[j] += e.v[j];
+                    st4_cg(bt_cur + size_t(i) * U4 + uoff, beta);
+                }
+            }
+            if (p.do_post) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (SR == SR_LOG) atomicAdd(&s_z[uoff + j], zs[j]);
+                    else red_max1(&s_z[uoff + j], zs[j]);
+                }
+            }
+        }
+        if (p.do_post) {
+            __syncthreads();
+            for (int u = threadIdx.x; u < U4; u += blockDim.x) {
+                int b = p.utt_b[u];
+                T v = s_z[u];
+                if (b >= 0 && v > T(0)) red1<SR>(p.zsum + size_t(n) * p.B + b, v);
+                s_z[u] = T(0);
+            }
+        }
+        grid_sync(p.barrier, bar_target);
+    }
+}
+
+// ================================================================================================
+// Emission transpose + expand  (src/inference.jl:54-60 expand, :146-150 vcat / Ĉ·V̂ — the pdf
+// gather itself happens in the recursion kernels through state->pdf)
+//   E[n][d][u] for the utterances of one shared-graph group.
+// ================================================================================================
+template <typename T> struct EmisParams {
+    const T* ll; long long sb, sd, sn;
+    int D, Tn, expanded;       // as passed by the caller
+    int Dh, N1;                // D̂, N̂
+    const int* seqlens;        // device [B] or null
+    const int* utt_b;          // [U4]
+    int U4;
+    T* E;
+};
+
+template <typename T>
+__device__ __forceinline__ T emission(const T* ll, long long sb, long long sd, long long sn, int D,
+                                      int expanded, int L, int b, int d, int n) {
+    if (expanded) return ll[b * sb + d * sd + n * sn];
+    if (d < D) return n < L ? ll[b * sb + d * sd + n * sn] : neg_inf<T>();
+    return n < L ? neg_inf<T>() : T(0);
+}
+
+// grid: (ceil(Dh/32), ceil(U4/32), N1), block (32, 8)
+template <typename T> __global__ void expand_transpose_kernel(EmisParams<T> p) {
+    __shared__ T tile[32][33];
+    const int n = blockIdx.z;
+    const int d0 = blockIdx.x * 32, u0 = blockIdx.y * 32;
+    for (int k = threadIdx.y; k < 32; k += 8) {
+        int u = u0 + k, d = d0 + threadIdx.x;
+        T v = neg_inf<T>();
+        if (u < p.U4 && d < p.Dh) {
+            int b = p.utt_b[u];
+            if (b >= 0) {
+                int L = p.seqlens ? p.seqlens[b] : p.Tn;
+                v = emission<T>(p.ll, p.sb, p.sd, p.sn, p.D, p.expanded, L, b, d, n);
+            }
+        }
+        tile[k][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += 8) {
+        int d = d0 + k, u = u0 + threadIdx.x;
+        if (d < p.Dh && u < p.U4) p.E[(size_t(n) * p.Dh + d) * p.U4 + u] = tile[threadIdx.x][k];
+    }
+}
+
+// ================================================================================================
+// Small-graph kernel: one CTA per utterance
+// ================================================================================================
+template <typename T> struct UttDesc {
+    const int* in_ptr;  const Arc<T>* in_arcs;
+    const int* out_ptr; const Arc<T>* out_arcs;
+    const int* pdf;
+    const T* init_dense;
+    int S;        // Ŝ
+    int b;        // global utterance index
+    long long ws_off;   // offset of this utterance's [N1][S] block in the α workspace
+    long long out_off;  // state offset off_b in the virtual union (for user-layout outputs)
+};
+
+template <typename T> struct SmallParams {
+    const UttDesc<T>* utts;
+    const T* ll; long long sb, sd, sn;
+    int D, Tn, expanded, Dh, N1;
+    const int* seqlens;
+    // α destination: element (n, s) of utterance u at alpha + base + n*alpha_sn + s, with
+    // base = ws_off (workspace, alpha_sn = -1 meaning S) or out_off (user layout, alpha_sn = ΣŜ)
+    T* alpha; long long alpha_sn; int alpha_user;
+    T* beta_out; long long beta_sn;  // user layout only
+    T* post; int B;
+    T* zsum; T* lz;
+    int do_fwd, do_bwd, do_post;
+};
+
+template <typename T, int SR>
+__device__ __forceinline__ T small_row(const Arc<T>* __restrict__ arcs, int beg, int end, const T* vec) {
+    if (SR == SR_TROP) {
+        T m = neg_inf<T>();
+        for (int a = beg; a < end; ++a) {
+            Arc<T> arc = ld_arc(arcs + a);
+            m = max_(m, arc.w + vec[arc.idx]);
+        }
+        return m;
+    }
+    T m = neg_inf<T>();
+    for (int a = beg; a < end; ++a) {
+        Arc<T> arc = ld_arc(arcs + a);
+        m = max_(m, arc.w + vec[arc.idx]);
+    }
+    if (m == neg_inf<T>()) return m;
+    T s = T(0);
+    for (int a = beg; a < end; ++a) {
+        Arc<T> arc = ld_arc(arcs + a);
+        s += exp_(arc.w + vec[arc.idx] - m);
+    }
+    return m + log_(s);
+}
+
+template <typename T, int SR> __global__ void small_fb_kernel(SmallParams<T> p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const UttDesc<T> u = p.utts[blockIdx.x];
+    const int S = u.S;
+    T* v0 = reinterpret_cast<T*>(smem_raw);
+    T* v1 = v0 + S;
+    T* s_red = v1 + S;  // [32]
+    const int b = u.b;
+    const int L = p.seqlens ? p.seqlens[b] : p.Tn;
+    const long long a_sn = p.alpha_user ? p.alpha_sn : S;
+    T* A = p.alpha + (p.alpha_user ? u.out_off : u.ws_off);
+
+    if (p.do_fwd) {
+        for (int n = 0; n < p.N1; ++n) {
+            const T* prev = (n & 1) ? v0 : v1;
+            T* cur = (n & 1) ? v1 : v0;
+            for (int s = threadIdx.x; s < S; s += blockDim.x) {
+                T e = emission<T>(p.ll, p.sb, p.sd, p.sn, p.D, p.expanded, L, b, u.pdf[s], n);
+                T acc = (n == 0) ? u.init_dense[s]
+                                 : small_row<T, SR>(u.in_arcs, u.in_ptr[s], u.in_ptr[s + 1], prev);
+                acc += e;
+                cur[s] = acc;
+                A[size_t(n) * a_sn + s] = acc;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) p.lz[b] = A[size_t(p.N1 - 1) * a_sn + (S - 1)];
+    }
+    if (!p.do_bwd) return;
+    __syncthreads();  // make A (global, written by this CTA) visible to the whole CTA
+
+    T lzv = T(0);
+    if (p.do_post) {
+        lzv = A[size_t(p.N1 - 1) * a_sn + (S - 1)];
+        if (lzv == neg_inf<T>()) lzv = T(0);
+    }
+    T* Bo = p.beta_out ? p.beta_out + u.out_off : nullptr;
+    for (int n = p.N1 - 1; n >= 0; --n) {
+        const T* nxt = (n & 1) ? v0 : v1;  // β_{n+1} ⊗ e_{n+1}
+        T* cur = (n & 1) ? v1 : v0;
+        T zs = T(0);
+        for (int i = threadIdx.x; i < S; i += blockDim.x) {
+            const int pdf = u.pdf[i];
+            T e = (n > 0) ? emission<T>(p.ll, p.sb, p.sd, p.sn, p.D, p.expanded, L, b, pdf, n) : T(0);
+            T beta = (n == p.N1 - 1) ? T(0)
+                                     : small_row<T, SR>(u.out_arcs, u.out_ptr[i], u.out_ptr[i + 1], nxt);
+            if (Bo) Bo[size_t(n) * p.beta_sn + i] = beta;
+            if (p.do_post) {
+                T pg = exp_(A[size_t(n) * a_sn + i] + beta - lzv);
+                zs = lin_add<SR>(zs, pg);
+                if (n < p.Tn && pdf < p.D && pg > T(0))
+                    red1<SR>(p.post + (size_t(n) * p.D + pdf) * p.B + b, pg);
+            }
+            cur[i] = beta + e;
+        }
+        if (p.do_post) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) zs = lin_add<SR>(zs, __shfl_xor_sync(0xffffffffu, zs, o));
+            if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = zs;
+        }
+        __syncthreads();
+        if (p.do_post && threadIdx.x == 0) {
+            T z = T(0);
+            for (int w = 0; w < (blockDim.x + 31) / 32; ++w) z = lin_add<SR>(z, s_red[w]);
+            p.zsum[size_t(n) * p.B + b] = z;
+        }
+    }
+}
+
+// ================================================================================================
+// Normalisation: Ẑ ./ sums, ttl = minimum(sums)   (src/inference.jl:157-160)
+// ================================================================================================
+// post[n][d][b] /= zsum[n][b];   grid-stride over n*D*B elements
+template <typename T> __global__ void normalize_post_kernel(T* post, const T* zsum, int B, int D, int Tn) {
+    const size_t total = size_t(Tn) * D * B;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total;
+         i += size_t(gridDim.x) * blockDim.x) {
+        int b = int(i % B);
+        size_t n = i / (size_t(D) * B);
+        T z = zsum[n * B + b];
+        T v = post[i];
+        post[i] = z > T(0) ? v / z : T(0);
+    }
+}
+// logz[b] = lz[b] + log(min_n zsum[n][b])
+template <typename T> __global__ void total_kernel(const T* zsum, const T* lz, T* logz, int B, int N1) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    T l = lz[b];
+    if (l == neg_inf<T>()) { logz[b] = l; return; }
+    T mn = zsum[b];
+    for (int n = 1; n < N1; ++n) mn = fmin(mn, zsum[size_t(n) * B + b]);
+    logz[b] = mn > T(0) ? l + T(log(double(mn))) : neg_inf<T>();
+}
+
+// ================================================================================================
+// Layout conversion for the αrecursion / βrecursion entry points:
+//   src [N1][S][U4] (shared-graph layout) -> dst[(off_b + s) + total*n]  (reference layout)
+// grid (ceil(S/32), ceil(U4/32), N1), block (32, 8)
+// ================================================================================================
+template <typename T>
+__global__ void unpack_states_kernel(const T* src, int S, int U4, const int* utt_b,
+                                     const long long* utt_off, T* dst, long long total) {
+    __shared__ T tile[32][33];
+    const int n = blockIdx.z, s0 = blockIdx.x * 32, u0 = blockIdx.y * 32;
+    for (int k = threadIdx.y; k < 32; k += 8) {
+        int s = s0 + k, u = u0 + threadIdx.x;
+        if (s < S && u < U4) tile[k][threadIdx.x] = src[(size_t(n) * S + s) * U4 + u];
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += 8) {
+        int u = u0 + k, s = s0 + threadIdx.x;
+        if (s < S && u < U4 && utt_b[u] >= 0) dst[utt_off[u] + s + total * n] = tile[threadIdx.x][k];
+    }
+}
+
+// ================================================================================================
+// Viterbi back-trace (bestpath).  One warp per utterance walks N̂-1 steps
+// back from the phony final state; at each step the lanes scan the in-arcs of the current
+// state and pick the first maximum in ascending predecessor order.
+//   α(n, s) of utterance k lives at alpha + base[k] + n*sn[k] + s*ss[k].
+// ================================================================================================
+template <typename T> struct TraceDesc {
+    const int* in_ptr; const Arc<T>* in_arcs;
+    long long base, sn, ss;
+    int S, b;
+};
+template <typename T>
+__global__ void backtrace_kernel(const TraceDesc<T>* descs, int nutts, const T* alpha, int N1, int Tn,
+                                 const int* seqlens, int* path, T* score) {
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (k >= nutts) return;
+    const TraceDesc<T> d = descs[k];
+    const int L = seqlens ? seqlens[d.b] : Tn;
+    int* out = path + size_t(d.b) * Tn;
+    for (int t = lane; t < Tn; t += 32) out[t] = 0;
+    __syncwarp();
+    const T* A = alpha + d.base;
+    T sc = A[size_t(N1 - 1) * d.sn + size_t(d.S - 1) * d.ss];
+    if (lane == 0) score[d.b] = sc;
+    if (sc == neg_inf<T>()) return;
+    int cur = d.S - 1;
+    for (int n = N1 - 1; n >= 1; --n) {
+        const T* prev = A + size_t(n - 1) * d.sn;
+        const int beg = d.in_ptr[cur], end = d.in_ptr[cur + 1];
+        T best = neg_inf<T>();
+        int arg = 0x7fffffff;
+        for (int a = beg + lane; a < end; a += 32) {  // ascending within a lane
+            Arc<T> arc = ld_arc(d.in_arcs + a);
+            T v = arc.w + prev[size_t(arc.idx) * d.ss];
+            if (v > best) { best = v; arg = arc.idx; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            T ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        }
+        cur = arg;
+        if (lane == 0 && n - 1 < L) out[n - 1] = cur + 1;
+    }
+}
+
+}  // namespace mk

@@ -1,0 +1,765 @@
+// SPDX-License-Identifier: MIT
+//
+// markov_b200.cu — host side of libmarkov_b200.so: graph compilation (FSM + compile + adapt,
+// src/fsm.jl:7-48, src/inference.jl:3-26), the ragged batch descriptor (rawunion / batch,
+// src/fsmops.jl:28-36, src/inference.jl:28-36), kernel dispatch, and the C ABI declared in
+// include/markov_b200.h.  No CPU compute path exists here: every entry point either runs the
+// CUDA kernels of kernels.cuh or fails.
+#include "../../include/markov_b200.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace mk;
+
+// ------------------------------------------------------------------------------------------------
+// errors, instrumentation
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static thread_local int64_t g_launches = 0;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(MK_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                                 \
+    } while (0)
+#define TRY(call)                   \
+    do {                            \
+        int rc_ = (call);           \
+        if (rc_ != MK_OK) return rc_; \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return MK_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 16 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            cudaGetLastError();
+            return fail(MK_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return MK_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+template <typename T> static int upload(const std::vector<T>& h, void** d) {
+    size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+    CK(cudaMalloc(d, bytes));
+    if (!h.empty()) CK(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return MK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mk_graph
+// ------------------------------------------------------------------------------------------------
+struct mk_graph {
+    int semiring = 0, dtype = 0, device = 0, n_sms = 0;
+    int64_t S = 0, nnz = 0, Dh = 0;
+    int max_in_deg = 0, max_out_deg = 0;
+    int *d_in_ptr = nullptr, *d_out_ptr = nullptr, *d_pdf = nullptr;
+    int *d_fwd_rows = nullptr, *d_bwd_rows = nullptr;
+    void *d_in_arcs = nullptr, *d_out_arcs = nullptr, *d_init_dense = nullptr;
+    size_t bytes = 0;
+    ~mk_graph() {
+        cudaFree(d_in_ptr); cudaFree(d_out_ptr); cudaFree(d_pdf);
+        cudaFree(d_fwd_rows); cudaFree(d_bwd_rows);
+        cudaFree(d_in_arcs); cudaFree(d_out_arcs); cudaFree(d_init_dense);
+    }
+};
+
+// contiguous row ranges per warp, balanced by (arcs + 2) per row
+static std::vector<int> partition_rows(const std::vector<int>& ptr, int S, int n_warps) {
+    std::vector<int> b(n_warps + 1, S);
+    const double total = double(ptr[S]) + 2.0 * S;
+    double acc = 0;
+    int r = 0;
+    b[0] = 0;
+    for (int k = 1; k < n_warps; ++k) {
+        const double target = total * k / n_warps;
+        while (r < S) {
+            double c = double(ptr[r + 1] - ptr[r]) + 2.0;
+            if (acc + 0.5 * c > target) break;
+            acc += c;
+            ++r;
+        }
+        b[k] = r;
+    }
+    b[n_warps] = S;
+    return b;
+}
+
+template <typename T>
+static int build_graph(mk_graph* g, const int64_t* colptr, const int64_t* rowval, const void* nzval_,
+                       int64_t n_init, const int64_t* init_idx, const void* init_w_,
+                       const int32_t* state2pdf, int base) {
+    const T* nzval = static_cast<const T*>(nzval_);
+    const T* init_w = static_cast<const T*>(init_w_);
+    const int S = int(g->S);
+    const int64_t nnz = g->nnz;
+    const T ninf = -std::numeric_limits<T>::infinity();
+
+    std::vector<int> in_ptr(S + 1), out_ptr(S + 1, 0);
+    std::vector<Arc<T>> in_arcs(nnz), out_arcs(nnz);
+    for (int j = 0; j <= S; ++j) {
+        int64_t v = colptr[j] - base;
+        if (v < 0 || v > nnz || (j > 0 && v < in_ptr[j - 1]))
+            return fail(MK_EINVAL, "colptr is not a valid CSC pointer array at column %d", j);
+        in_ptr[j] = int(v);
+    }
+    if (in_ptr[0] != 0 || in_ptr[S] != nnz) return fail(MK_EINVAL, "colptr does not span nnz");
+    for (int64_t a = 0; a < nnz; ++a) {
+        int64_t s = rowval[a] - base;
+        if (s < 0 || s >= S) return fail(MK_EINVAL, "rowval[%lld] out of range", (long long)a);
+        std::memset(&in_arcs[a], 0, sizeof(Arc<T>));
+        in_arcs[a].idx = int(s);
+        in_arcs[a].w = nzval[a];
+    }
+    // Julia's CSC keeps row indices ascending inside a column; enforce it (defines the tie rule)
+    for (int j = 0; j < S; ++j) {
+        auto b = in_arcs.begin() + in_ptr[j], e = in_arcs.begin() + in_ptr[j + 1];
+        if (!std::is_sorted(b, e, [](const Arc<T>& x, const Arc<T>& y) { return x.idx < y.idx; }))
+            std::stable_sort(b, e, [](const Arc<T>& x, const Arc<T>& y) { return x.idx < y.idx; });
+        g->max_in_deg = std::max(g->max_in_deg, in_ptr[j + 1] - in_ptr[j]);
+    }
+    // T̂ rows (by source): the transpose, destinations ascending inside a row
+    for (int64_t a = 0; a < nnz; ++a) out_ptr[in_arcs[a].idx + 1]++;
+    for (int i = 0; i < S; ++i) {
+        g->max_out_deg = std::max(g->max_out_deg, out_ptr[i + 1]);
+        out_ptr[i + 1] += out_ptr[i];
+    }
+    {
+        std::vector<int> fill(out_ptr.begin(), out_ptr.end() - 1);
+        for (int j = 0; j < S; ++j)
+            for (int a = in_ptr[j]; a < in_ptr[j + 1]; ++a) {
+                int pos = fill[in_arcs[a].idx]++;
+                std::memset(&out_arcs[pos], 0, sizeof(Arc<T>));
+                out_arcs[pos].idx = j;
+                out_arcs[pos].w = in_arcs[a].w;
+            }
+    }
+    std::vector<int> pdf(S);
+    for (int s = 0; s < S; ++s) {
+        int64_t d = int64_t(state2pdf[s]) - base;
+        if (d < 0 || d >= g->Dh) return fail(MK_EINVAL, "state2pdf[%d] out of range", s);
+        pdf[s] = int(d);
+    }
+    if (pdf[S - 1] != g->Dh - 1)
+        return fail(MK_EINVAL, "the phony final state must map to the phony pdf (n_pdf_hat)");
+    for (int s = 0; s + 1 < S; ++s)
+        if (pdf[s] == g->Dh - 1)
+            return fail(MK_EINVAL, "state %d maps to the phony pdf; only the phony final state may", s);
+    std::vector<T> init(S, ninf);
+    for (int64_t k = 0; k < n_init; ++k) {
+        int64_t s = init_idx[k] - base;
+        if (s < 0 || s >= S) return fail(MK_EINVAL, "init_idx[%lld] out of range", (long long)k);
+        init[s] = init_w[k];
+    }
+    const int n_warps = g->n_sms * kSharedWarps;
+    std::vector<int> fwd = partition_rows(in_ptr, S, n_warps), bwd = partition_rows(out_ptr, S, n_warps);
+
+    TRY(upload(in_ptr, (void**)&g->d_in_ptr));
+    TRY(upload(out_ptr, (void**)&g->d_out_ptr));
+    TRY(upload(in_arcs, &g->d_in_arcs));
+    TRY(upload(out_arcs, &g->d_out_arcs));
+    TRY(upload(pdf, (void**)&g->d_pdf));
+    TRY(upload(init, &g->d_init_dense));
+    TRY(upload(fwd, (void**)&g->d_fwd_rows));
+    TRY(upload(bwd, (void**)&g->d_bwd_rows));
+    g->bytes = 2 * (S + 1) * sizeof(int) + 2 * nnz * sizeof(Arc<T>) + S * (sizeof(int) + sizeof(T)) +
+               2 * (n_warps + 1) * sizeof(int);
+    return MK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mk_batch
+// ------------------------------------------------------------------------------------------------
+struct Group {  // utterances sharing one graph, run by shared_fb_kernel
+    mk_graph* g = nullptr;
+    std::vector<int> utts;
+    int U4 = 0;
+    bool vec4 = false;
+    int* d_utt_b = nullptr;
+    long long* d_utt_off = nullptr;
+    DevBuf E, alpha, bt;
+};
+
+struct mk_batch {
+    int64_t B = 0, total = 0;
+    int semiring = 0, dtype = 0, device = 0, n_sms = 0;
+    int64_t Dh = 0;
+    std::vector<mk_graph*> graphs;
+    std::vector<int64_t> off;
+    std::vector<Group> groups;
+    std::vector<int> small;  // utterances run by small_fb_kernel
+    int small_smax = 0;
+    int64_t small_cached_n1 = -1;
+    DevBuf small_descs, small_alpha, zsum, lz, seqlens, barrier, trace, h_ll, h_post, h_logz, h_path;
+    cudaStream_t own_stream = nullptr;
+    size_t max_smem_optin = 0;
+    // optional timing of the dominant kernel (bench.py roofline): events around the last
+    // shared_fb_kernel launch, on the stream it was launched on
+    bool profile = false;
+    bool prof_valid = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ~mk_batch() {
+        for (auto& gr : groups) {
+            cudaFree(gr.d_utt_b); cudaFree(gr.d_utt_off);
+            gr.E.release(); gr.alpha.release(); gr.bt.release();
+        }
+        DevBuf* all[] = {&small_descs, &small_alpha, &zsum, &lz, &seqlens, &barrier, &trace,
+                         &h_ll, &h_post, &h_logz, &h_path};
+        for (DevBuf* d : all) d->release();
+        if (own_stream) cudaStreamDestroy(own_stream);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+    }
+    size_t ws_bytes() const {
+        size_t t = small_descs.cap + small_alpha.cap + zsum.cap + lz.cap + seqlens.cap + barrier.cap +
+                   trace.cap + h_ll.cap + h_post.cap + h_logz.cap + h_path.cap;
+        for (auto& gr : groups) t += gr.E.cap + gr.alpha.cap + gr.bt.cap;
+        return t;
+    }
+};
+
+static size_t tsize(int dtype) { return dtype == MK_F32 ? 4 : 8; }
+static size_t small_smem_bytes(int S, int dtype) { return (2 * size_t(S) + 32) * tsize(dtype); }
+
+// ------------------------------------------------------------------------------------------------
+// run
+// ------------------------------------------------------------------------------------------------
+enum Mode { MODE_ALPHA, MODE_BETA, MODE_POST, MODE_BEST };
+
+struct CallArgs {
+    const void* ll; int64_t sb, sd, sn, D, T; int expanded; const int32_t* seqlens;
+    void* out0;  // A / B / post / path
+    void* out1;  // logz / score
+    cudaStream_t stream;
+};
+
+template <typename T, int SR>
+static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, int Dh, int N1,
+                         int Dout, int Tout, const int* d_seqlens) {
+    mk_graph* g = gr.g;
+    const int S = int(g->S), U4 = gr.U4;
+    const size_t frame = size_t(S) * U4 * sizeof(T);
+    if (size_t(S) * U4 >= (size_t(1) << 31)) return fail(MK_ENOTSUP, "Ŝ*U exceeds 2^31 in one group");
+    TRY(gr.E.ensure(size_t(N1) * Dh * U4 * sizeof(T)));
+    TRY(gr.alpha.ensure(size_t(N1) * frame));
+    if (mode == MODE_POST || mode == MODE_BETA) TRY(gr.bt.ensure(2 * frame));
+
+    EmisParams<T> ep;
+    ep.ll = static_cast<const T*>(c.ll); ep.sb = c.sb; ep.sd = c.sd; ep.sn = c.sn;
+    ep.D = int(c.D); ep.Tn = int(c.T); ep.expanded = c.expanded; ep.Dh = Dh; ep.N1 = N1;
+    ep.seqlens = d_seqlens; ep.utt_b = gr.d_utt_b; ep.U4 = U4; ep.E = static_cast<T*>(gr.E.p);
+    dim3 eg((Dh + 31) / 32, (U4 + 31) / 32, N1), eb(32, 8);
+    expand_transpose_kernel<T><<<eg, eb, 0, c.stream>>>(ep);
+    CK(cudaGetLastError());
+    ++g_launches;
+
+    SharedParams<T> p;
+    p.S = S; p.Dh = Dh; p.N1 = N1; p.U4 = U4; p.ntiles = (U4 + kTileUtts - 1) / kTileUtts;
+    p.in_ptr = g->d_in_ptr; p.in_arcs = static_cast<const Arc<T>*>(g->d_in_arcs);
+    p.out_ptr = g->d_out_ptr; p.out_arcs = static_cast<const Arc<T>*>(g->d_out_arcs);
+    p.pdf = g->d_pdf; p.init_dense = static_cast<const T*>(g->d_init_dense);
+    p.fwd_rows = g->d_fwd_rows; p.bwd_rows = g->d_bwd_rows;
+    p.E = static_cast<const T*>(gr.E.p);
+    p.alpha = static_cast<T*>(gr.alpha.p);
+    p.bt = static_cast<T*>(gr.bt.p);
+    p.beta_out = nullptr;
+    p.post = nullptr; p.B = int(bt->B); p.D = Dout; p.Tn = Tout;
+    p.utt_b = gr.d_utt_b; p.post_vec4 = 0;
+    p.zsum = static_cast<T*>(bt->zsum.p); p.lz = static_cast<T*>(bt->lz.p);
+    p.barrier = static_cast<unsigned*>(bt->barrier.p);
+    p.do_fwd = p.do_bwd = p.do_post = 0;
+    switch (mode) {
+        case MODE_ALPHA: case MODE_BEST: p.do_fwd = 1; break;
+        case MODE_BETA: p.do_bwd = 1; p.beta_out = static_cast<T*>(gr.alpha.p); break;
+        case MODE_POST:
+            p.do_fwd = p.do_bwd = p.do_post = 1;
+            p.post = static_cast<T*>(c.out0);
+            p.post_vec4 = (gr.vec4 && bt->B % 4 == 0 && (reinterpret_cast<uintptr_t>(c.out0) & 15) == 0) ? 1 : 0;
+            break;
+    }
+    CK(cudaMemsetAsync(bt->barrier.p, 0, sizeof(unsigned), c.stream));
+    void* args[] = {&p};
+    size_t smem = 2 * size_t(U4) * sizeof(T);
+    auto kern = shared_fb_kernel<T, SR>;
+    if (bt->profile) CK(cudaEventRecord(bt->ev0, c.stream));
+    CK(cudaLaunchCooperativeKernel((void*)kern, dim3(g->n_sms), dim3(kSharedThreads), args, smem, c.stream));
+    ++g_launches;
+    if (bt->profile) { CK(cudaEventRecord(bt->ev1, c.stream)); bt->prof_valid = true; }
+
+    if (mode == MODE_ALPHA || mode == MODE_BETA) {
+        dim3 ug((S + 31) / 32, (U4 + 31) / 32, N1), ub(32, 8);
+        unpack_states_kernel<T><<<ug, ub, 0, c.stream>>>(static_cast<const T*>(gr.alpha.p), S, U4, gr.d_utt_b,
+                                                        gr.d_utt_off, static_cast<T*>(c.out0), bt->total);
+        CK(cudaGetLastError());
+        ++g_launches;
+    }
+    return MK_OK;
+}
+
+template <typename T, int SR>
+static int launch_small(mk_batch* bt, Mode mode, const CallArgs& c, int Dh, int N1, int Dout, int Tout,
+                        const int* d_seqlens) {
+    const int n = int(bt->small.size());
+    if (n == 0) return MK_OK;
+    // descriptors (ws_off depends on N̂)
+    if (bt->small_cached_n1 != N1) {
+        std::vector<UttDesc<T>> descs(n);
+        long long off = 0;
+        for (int k = 0; k < n; ++k) {
+            int b = bt->small[k];
+            mk_graph* g = bt->graphs[b];
+            UttDesc<T>& d = descs[k];
+            d.in_ptr = g->d_in_ptr; d.in_arcs = static_cast<const Arc<T>*>(g->d_in_arcs);
+            d.out_ptr = g->d_out_ptr; d.out_arcs = static_cast<const Arc<T>*>(g->d_out_arcs);
+            d.pdf = g->d_pdf; d.init_dense = static_cast<const T*>(g->d_init_dense);
+            d.S = int(g->S); d.b = b; d.ws_off = off; d.out_off = bt->off[b];
+            off += (long long)N1 * g->S;
+        }
+        TRY(bt->small_descs.ensure(n * sizeof(UttDesc<T>)));
+        TRY(bt->small_alpha.ensure(size_t(off) * sizeof(T)));
+        CK(cudaMemcpyAsync(bt->small_descs.p, descs.data(), n * sizeof(UttDesc<T>), cudaMemcpyHostToDevice,
+                           c.stream));
+        CK(cudaStreamSynchronize(c.stream));  // descs is a stack-lifetime host buffer
+        bt->small_cached_n1 = N1;
+    }
+    SmallParams<T> p;
+    p.utts = static_cast<const UttDesc<T>*>(bt->small_descs.p);
+    p.ll = static_cast<const T*>(c.ll); p.sb = c.sb; p.sd = c.sd; p.sn = c.sn;
+    p.D = Dout; p.Tn = Tout; p.expanded = c.expanded; p.Dh = Dh; p.N1 = N1;
+    p.seqlens = d_seqlens;
+    p.alpha = static_cast<T*>(bt->small_alpha.p); p.alpha_sn = 0; p.alpha_user = 0;
+    p.beta_out = nullptr; p.beta_sn = 0;
+    p.post = nullptr; p.B = int(bt->B);
+    p.zsum = static_cast<T*>(bt->zsum.p); p.lz = static_cast<T*>(bt->lz.p);
+    p.do_fwd = p.do_bwd = p.do_post = 0;
+    switch (mode) {
+        case MODE_ALPHA: p.do_fwd = 1; p.alpha = static_cast<T*>(c.out0); p.alpha_sn = bt->total; p.alpha_user = 1; break;
+        case MODE_BEST: p.do_fwd = 1; break;
+        case MODE_BETA: p.do_bwd = 1; p.beta_out = static_cast<T*>(c.out0); p.beta_sn = bt->total; break;
+        case MODE_POST: p.do_fwd = p.do_bwd = p.do_post = 1; p.post = static_cast<T*>(c.out0); break;
+    }
+    const int smax = bt->small_smax;
+    int threads = std::min(1024, std::max(64, ((smax + 31) / 32) * 32));
+    size_t smem = small_smem_bytes(smax, bt->dtype);
+    auto kern = small_fb_kernel<T, SR>;
+    if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    kern<<<n, threads, smem, c.stream>>>(p);
+    CK(cudaGetLastError());
+    ++g_launches;
+    return MK_OK;
+}
+
+template <typename T, int SR> static int run(mk_batch* bt, Mode mode, const CallArgs& c) {
+    DeviceGuard guard(bt->device);
+    if (!guard.ok) return fail(MK_ECUDA, "cannot select CUDA device %d", bt->device);
+    const int B = int(bt->B);
+    if (c.D <= 0 || c.T <= 0) return fail(MK_EINVAL, "D and T must be positive");
+    const int Dh = c.expanded ? int(c.D) : int(c.D) + 1;
+    const int N1 = c.expanded ? int(c.T) : int(c.T) + 1;
+    const int Dout = Dh - 1, Tout = N1 - 1;
+    if (Dh != bt->Dh)
+        return fail(MK_EINVAL, "DimensionMismatch: emissions have %d pdfs (incl. phony), graphs expect %lld",
+                    Dh, (long long)bt->Dh);
+    if (c.expanded && c.seqlens) return fail(MK_EINVAL, "seqlens must be NULL with expanded emissions");
+    if (N1 < 2) return fail(MK_EINVAL, "need at least one real frame");
+    if (!c.ll || !c.out0) return fail(MK_EINVAL, "null buffer");
+    const int* d_seqlens = nullptr;
+    if (c.seqlens) {
+        for (int b = 0; b < B; ++b)
+            if (c.seqlens[b] < 0 || c.seqlens[b] > c.T)
+                return fail(MK_EINVAL, "seqlens[%d] = %d outside [0, T]", b, c.seqlens[b]);
+        TRY(bt->seqlens.ensure(B * sizeof(int)));
+        CK(cudaMemcpyAsync(bt->seqlens.p, c.seqlens, B * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+        d_seqlens = static_cast<const int*>(bt->seqlens.p);
+    }
+    TRY(bt->barrier.ensure(256));
+    TRY(bt->lz.ensure(B * sizeof(T)));
+    TRY(bt->zsum.ensure(size_t(N1) * B * sizeof(T)));
+    if (mode == MODE_POST) {
+        if (!c.out1) return fail(MK_EINVAL, "null logz buffer");
+        CK(cudaMemsetAsync(c.out0, 0, size_t(Tout) * Dout * B * sizeof(T), c.stream));
+        CK(cudaMemsetAsync(bt->zsum.p, 0, size_t(N1) * B * sizeof(T), c.stream));
+    }
+    for (auto& gr : bt->groups) TRY((launch_shared<T, SR>(bt, gr, mode, c, Dh, N1, Dout, Tout, d_seqlens)));
+    TRY((launch_small<T, SR>(bt, mode, c, Dh, N1, Dout, Tout, d_seqlens)));
+
+    if (mode == MODE_POST) {
+        size_t total = size_t(Tout) * Dout * B;
+        int blocks = int(std::min<size_t>((total + 255) / 256, size_t(bt->n_sms) * 16));
+        normalize_post_kernel<T><<<blocks, 256, 0, c.stream>>>(static_cast<T*>(c.out0),
+                                                             static_cast<const T*>(bt->zsum.p), B, Dout, Tout);
+        CK(cudaGetLastError());
+        total_kernel<T><<<(B + 127) / 128, 128, 0, c.stream>>>(static_cast<const T*>(bt->zsum.p),
+                                                             static_cast<const T*>(bt->lz.p),
+                                                             static_cast<T*>(c.out1), B, N1);
+        CK(cudaGetLastError());
+        g_launches += 2;
+    }
+    if (mode == MODE_BEST) {
+        if (!c.out1) return fail(MK_EINVAL, "null score buffer");
+        std::vector<TraceDesc<T>> descs;
+        descs.reserve(B);
+        // every utterance's α lives in one of the workspaces; describe them relative to one base
+        // pointer per launch: two launches (shared groups use per-group buffers).
+        for (auto& gr : bt->groups) {
+            descs.clear();
+            for (size_t k = 0; k < gr.utts.size(); ++k) {
+                TraceDesc<T> d;
+                d.in_ptr = gr.g->d_in_ptr; d.in_arcs = static_cast<const Arc<T>*>(gr.g->d_in_arcs);
+                d.base = (long long)k; d.sn = (long long)gr.g->S * gr.U4; d.ss = gr.U4;
+                d.S = int(gr.g->S); d.b = gr.utts[k];
+                descs.push_back(d);
+            }
+            size_t bytes = descs.size() * sizeof(TraceDesc<T>);
+            TRY(bt->trace.ensure(bytes));
+            CK(cudaMemcpyAsync(bt->trace.p, descs.data(), bytes, cudaMemcpyHostToDevice, c.stream));
+            CK(cudaStreamSynchronize(c.stream));
+            int n = int(descs.size());
+            backtrace_kernel<T><<<(n * 32 + 127) / 128, 128, 0, c.stream>>>(
+                static_cast<const TraceDesc<T>*>(bt->trace.p), n, static_cast<const T*>(gr.alpha.p), N1, Tout,
+                d_seqlens, static_cast<int*>(c.out0), static_cast<T*>(c.out1));
+            CK(cudaGetLastError());
+            ++g_launches;
+            CK(cudaStreamSynchronize(c.stream));  // bt->trace is reused by the next group
+        }
+        if (!bt->small.empty()) {
+            descs.clear();
+            long long off = 0;
+            for (int b : bt->small) {
+                mk_graph* g = bt->graphs[b];
+                TraceDesc<T> d;
+                d.in_ptr = g->d_in_ptr; d.in_arcs = static_cast<const Arc<T>*>(g->d_in_arcs);
+                d.base = off; d.sn = g->S; d.ss = 1; d.S = int(g->S); d.b = b;
+                off += (long long)N1 * g->S;
+                descs.push_back(d);
+            }
+            size_t bytes = descs.size() * sizeof(TraceDesc<T>);
+            TRY(bt->trace.ensure(bytes));
+            CK(cudaMemcpyAsync(bt->trace.p, descs.data(), bytes, cudaMemcpyHostToDevice, c.stream));
+            CK(cudaStreamSynchronize(c.stream));
+            int n = int(descs.size());
+            backtrace_kernel<T><<<(n * 32 + 127) / 128, 128, 0, c.stream>>>(
+                static_cast<const TraceDesc<T>*>(bt->trace.p), n, static_cast<const T*>(bt->small_alpha.p), N1,
+                Tout, d_seqlens, static_cast<int*>(c.out0), static_cast<T*>(c.out1));
+            CK(cudaGetLastError());
+            ++g_launches;
+        }
+    }
+    return MK_OK;
+}
+
+static int dispatch(mk_batch* bt, Mode mode, const CallArgs& c) {
+    if (!bt) return fail(MK_EINVAL, "null batch");
+    if (mode == MODE_BEST && bt->semiring != MK_TROPICAL)
+        return fail(MK_EINVAL, "bestpath needs TropicalSemiring graphs");
+    if (mode == MODE_BEST && c.expanded) return fail(MK_EINVAL, "bestpath takes un-expanded emissions");
+    if (bt->dtype == MK_F32)
+        return bt->semiring == MK_LOG ? run<float, SR_LOG>(bt, mode, c) : run<float, SR_TROP>(bt, mode, c);
+    return bt->semiring == MK_LOG ? run<double, SR_LOG>(bt, mode, c) : run<double, SR_TROP>(bt, mode, c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int mk_abi_version(void) { return MK_ABI_VERSION; }
+const char* mk_last_error(void) { return g_err.c_str(); }
+int64_t mk_launch_count(int reset) {
+    int64_t v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+int mk_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int mk_graph_create(mk_graph** out, int semiring, int dtype, int64_t n_states_hat, int64_t nnz_hat,
+                    const int64_t* colptr, const int64_t* rowval, const void* nzval, int64_t n_init,
+                    const int64_t* init_idx, const void* init_w, const int32_t* state2pdf,
+                    int64_t n_pdf_hat, int index_base, int device) {
+    if (!out) return fail(MK_EINVAL, "null out");
+    *out = nullptr;
+    if (semiring != MK_LOG && semiring != MK_TROPICAL) return fail(MK_EINVAL, "unknown semiring %d", semiring);
+    if (dtype != MK_F32 && dtype != MK_F64) return fail(MK_EINVAL, "unknown dtype %d", dtype);
+    if (index_base != 0 && index_base != 1) return fail(MK_EINVAL, "index_base must be 0 or 1");
+    if (n_states_hat < 2 || n_states_hat > (int64_t(1) << 30)) return fail(MK_EINVAL, "bad n_states_hat");
+    if (nnz_hat < 0 || nnz_hat > (int64_t(1) << 31) - 2) return fail(MK_EINVAL, "bad nnz_hat");
+    if (n_pdf_hat < 2 || n_pdf_hat > (int64_t(1) << 30)) return fail(MK_EINVAL, "bad n_pdf_hat");
+    if (!colptr || (nnz_hat && (!rowval || !nzval)) || !state2pdf || (n_init && (!init_idx || !init_w)))
+        return fail(MK_EINVAL, "null array");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(MK_ECUDA, "no CUDA device available (libmarkov_b200 has no CPU fallback)");
+    }
+    if (device < 0) CK(cudaGetDevice(&device));
+    if (device >= ndev) return fail(MK_EINVAL, "device %d out of range", device);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(MK_ECUDA, "cannot select CUDA device %d", device);
+    mk_graph* g = new (std::nothrow) mk_graph;
+    if (!g) return fail(MK_ENOMEM, "out of host memory");
+    g->semiring = semiring; g->dtype = dtype; g->device = device;
+    g->S = n_states_hat; g->nnz = nnz_hat; g->Dh = n_pdf_hat;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { delete g; return fail(MK_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+    g->n_sms = prop.multiProcessorCount;
+    int rc = dtype == MK_F32
+                 ? build_graph<float>(g, colptr, rowval, nzval, n_init, init_idx, init_w, state2pdf, index_base)
+                 : build_graph<double>(g, colptr, rowval, nzval, n_init, init_idx, init_w, state2pdf, index_base);
+    if (rc != MK_OK) { delete g; return rc; }
+    *out = g;
+    return MK_OK;
+}
+
+int mk_graph_destroy(mk_graph* g) {
+    if (!g) return MK_OK;
+    DeviceGuard guard(g->device);
+    delete g;
+    return MK_OK;
+}
+
+int mk_graph_info(const mk_graph* g, int64_t* n_states_hat, int64_t* nnz_hat, int64_t* n_pdf_hat,
+                  int* semiring, int* dtype) {
+    if (!g) return fail(MK_EINVAL, "null graph");
+    if (n_states_hat) *n_states_hat = g->S;
+    if (nnz_hat) *nnz_hat = g->nnz;
+    if (n_pdf_hat) *n_pdf_hat = g->Dh;
+    if (semiring) *semiring = g->semiring;
+    if (dtype) *dtype = g->dtype;
+    return MK_OK;
+}
+
+int mk_batch_create(mk_batch** out, mk_graph* const* graphs, int64_t B) {
+    if (!out) return fail(MK_EINVAL, "null out");
+    *out = nullptr;
+    if (!graphs || B <= 0 || B > (1 << 24)) return fail(MK_EINVAL, "bad batch size");
+    for (int64_t b = 0; b < B; ++b)
+        if (!graphs[b]) return fail(MK_EINVAL, "graphs[%lld] is null", (long long)b);
+    mk_graph* g0 = graphs[0];
+    for (int64_t b = 1; b < B; ++b) {
+        mk_graph* g = graphs[b];
+        if (g->semiring != g0->semiring || g->dtype != g0->dtype || g->device != g0->device || g->Dh != g0->Dh)
+            return fail(MK_EINVAL, "graphs[%lld] differs in semiring/dtype/device/n_pdf_hat", (long long)b);
+    }
+    DeviceGuard guard(g0->device);
+    if (!guard.ok) return fail(MK_ECUDA, "cannot select CUDA device %d", g0->device);
+    mk_batch* bt = new (std::nothrow) mk_batch;
+    if (!bt) return fail(MK_ENOMEM, "out of host memory");
+    bt->B = B; bt->semiring = g0->semiring; bt->dtype = g0->dtype; bt->device = g0->device;
+    bt->n_sms = g0->n_sms; bt->Dh = g0->Dh;
+    bt->graphs.assign(graphs, graphs + B);
+    bt->off.resize(B);
+    for (int64_t b = 0; b < B; ++b) { bt->off[b] = bt->total; bt->total += graphs[b]->S; }
+    int optin = 0;
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, bt->device);
+    bt->max_smem_optin = size_t(optin);
+
+    // Route every distinct graph: the replicated large graph goes to the shared-graph kernel,
+    // graphs that fit shared memory to the per-utterance kernel.  MK_FORCE_KERNEL=shared|small
+    // overrides (tests exercise both on the same inputs).
+    const char* force = getenv("MK_FORCE_KERNEL");
+    std::map<mk_graph*, std::vector<int>> by_graph;
+    std::vector<mk_graph*> order;
+    for (int64_t b = 0; b < B; ++b) {
+        auto it = by_graph.find(graphs[b]);
+        if (it == by_graph.end()) { order.push_back(graphs[b]); by_graph[graphs[b]] = {int(b)}; }
+        else it->second.push_back(int(b));
+    }
+    for (mk_graph* g : order) {
+        std::vector<int>& utts = by_graph[g];
+        bool fits_small = small_smem_bytes(int(g->S), g->dtype) <= bt->max_smem_optin;
+        bool shared = !fits_small || (utts.size() >= 8 && g->S >= 2048);
+        if (force && !strcmp(force, "shared")) shared = true;
+        if (force && !strcmp(force, "small") && fits_small) shared = false;
+        if (!shared) {
+            for (int b : utts) { bt->small.push_back(b); bt->small_smax = std::max(bt->small_smax, int(g->S)); }
+            continue;
+        }
+        bt->groups.emplace_back();
+        Group& gr = bt->groups.back();
+        gr.g = g; gr.utts = utts;
+        gr.U4 = int((utts.size() + 3) / 4 * 4);
+        std::vector<int> ub(gr.U4, -1);
+        std::vector<long long> uo(gr.U4, 0);
+        bool vec4 = utts.size() % 4 == 0;
+        for (size_t k = 0; k < utts.size(); ++k) {
+            ub[k] = utts[k]; uo[k] = bt->off[utts[k]];
+            if (k % 4 == 0) vec4 = vec4 && utts[k] % 4 == 0;
+            else vec4 = vec4 && utts[k] == utts[k - 1] + 1;
+        }
+        gr.vec4 = vec4;
+        int rc = upload(ub, (void**)&gr.d_utt_b);
+        if (rc == MK_OK) rc = upload(uo, (void**)&gr.d_utt_off);
+        if (rc != MK_OK) { delete bt; return rc; }
+    }
+    std::sort(bt->small.begin(), bt->small.end());
+    cudaError_t e = cudaStreamCreateWithFlags(&bt->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete bt; return fail(MK_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    *out = bt;
+    return MK_OK;
+}
+
+int mk_batch_destroy(mk_batch* b) {
+    if (!b) return MK_OK;
+    DeviceGuard guard(b->device);
+    delete b;
+    return MK_OK;
+}
+
+int mk_batch_info(const mk_batch* b, int64_t* B, int64_t* total_states_hat) {
+    if (!b) return fail(MK_EINVAL, "null batch");
+    if (B) *B = b->B;
+    if (total_states_hat) *total_states_hat = b->total;
+    return MK_OK;
+}
+
+int64_t mk_batch_workspace_bytes(const mk_batch* b) { return b ? int64_t(b->ws_bytes()) : 0; }
+
+int mk_batch_profile(mk_batch* b, int enable) {
+    if (!b) return fail(MK_EINVAL, "null batch");
+    DeviceGuard guard(b->device);
+    if (enable && !b->ev0) {
+        CK(cudaEventCreate(&b->ev0));
+        CK(cudaEventCreate(&b->ev1));
+    }
+    b->profile = enable != 0;
+    b->prof_valid = false;
+    return MK_OK;
+}
+
+int mk_batch_last_kernel_ms(mk_batch* b, float* ms) {
+    if (!b || !ms) return fail(MK_EINVAL, "null argument");
+    if (!b->prof_valid) return fail(MK_EINVAL, "no profiled launch recorded");
+    DeviceGuard guard(b->device);
+    CK(cudaEventSynchronize(b->ev1));
+    CK(cudaEventElapsedTime(ms, b->ev0, b->ev1));
+    return MK_OK;
+}
+
+static CallArgs mkargs(const void* ll, int64_t sb, int64_t sd, int64_t sn, int64_t D, int64_t T, int expanded,
+                       const int32_t* seqlens, void* o0, void* o1, void* stream) {
+    CallArgs c;
+    c.ll = ll; c.sb = sb; c.sd = sd; c.sn = sn; c.D = D; c.T = T; c.expanded = expanded; c.seqlens = seqlens;
+    c.out0 = o0; c.out1 = o1; c.stream = static_cast<cudaStream_t>(stream);
+    return c;
+}
+
+int mk_alpha(mk_batch* b, const void* ll, int64_t sb, int64_t sd, int64_t sn, int64_t D, int64_t T,
+             int expanded, const int32_t* seqlens, void* out_A, void* stream) {
+    return dispatch(b, MODE_ALPHA, mkargs(ll, sb, sd, sn, D, T, expanded, seqlens, out_A, nullptr, stream));
+}
+int mk_beta(mk_batch* b, const void* ll, int64_t sb, int64_t sd, int64_t sn, int64_t D, int64_t T,
+            int expanded, const int32_t* seqlens, void* out_B, void* stream) {
+    return dispatch(b, MODE_BETA, mkargs(ll, sb, sd, sn, D, T, expanded, seqlens, out_B, nullptr, stream));
+}
+int mk_pdfposteriors(mk_batch* b, const void* ll, int64_t sb, int64_t sd, int64_t sn, int64_t D, int64_t T,
+                     int expanded, const int32_t* seqlens, void* out_post, void* out_logz, void* stream) {
+    return dispatch(b, MODE_POST, mkargs(ll, sb, sd, sn, D, T, expanded, seqlens, out_post, out_logz, stream));
+}
+int mk_bestpath(mk_batch* b, const void* ll, int64_t sb, int64_t sd, int64_t sn, int64_t D, int64_t T,
+                int expanded, const int32_t* seqlens, int32_t* out_path, void* out_score, void* stream) {
+    return dispatch(b, MODE_BEST, mkargs(ll, sb, sd, sn, D, T, expanded, seqlens, out_path, out_score, stream));
+}
+
+static int64_t extent(int64_t B, int64_t D, int64_t T, int64_t sb, int64_t sd, int64_t sn) {
+    return (B - 1) * sb + (D - 1) * sd + (T - 1) * sn + 1;
+}
+
+int mk_pdfposteriors_host(mk_batch* b, const void* ll, int64_t sb, int64_t sd, int64_t sn, int64_t D,
+                          int64_t T, int expanded, const int32_t* seqlens, void* out_post, void* out_logz) {
+    if (!b) return fail(MK_EINVAL, "null batch");
+    if (!ll || !out_post || !out_logz) return fail(MK_EINVAL, "null buffer");
+    if (sb < 0 || sd < 0 || sn < 0 || D <= 0 || T <= 0) return fail(MK_EINVAL, "bad strides/dims");
+    DeviceGuard guard(b->device);
+    if (!guard.ok) return fail(MK_ECUDA, "cannot select CUDA device %d", b->device);
+    const size_t ts = tsize(b->dtype);
+    const int64_t Dout = expanded ? D - 1 : D, Tout = expanded ? T - 1 : T;
+    const size_t in_bytes = size_t(extent(b->B, D, T, sb, sd, sn)) * ts;
+    const size_t post_bytes = size_t(b->B) * Dout * Tout * ts;
+    TRY(b->h_ll.ensure(in_bytes));
+    TRY(b->h_post.ensure(post_bytes));
+    TRY(b->h_logz.ensure(b->B * ts));
+    cudaStream_t st = b->own_stream;
+    CK(cudaMemcpyAsync(b->h_ll.p, ll, in_bytes, cudaMemcpyHostToDevice, st));
+    TRY(dispatch(b, MODE_POST, mkargs(b->h_ll.p, sb, sd, sn, D, T, expanded, seqlens, b->h_post.p, b->h_logz.p, st)));
+    CK(cudaMemcpyAsync(out_post, b->h_post.p, post_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_logz, b->h_logz.p, b->B * ts, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return MK_OK;
+}
+
+int mk_bestpath_host(mk_batch* b, const void* ll, int64_t sb, int64_t sd, int64_t sn, int64_t D, int64_t T,
+                     int expanded, const int32_t* seqlens, int32_t* out_path, void* out_score) {
+    if (!b) return fail(MK_EINVAL, "null batch");
+    if (!ll || !out_path || !out_score) return fail(MK_EINVAL, "null buffer");
+    if (sb < 0 || sd < 0 || sn < 0 || D <= 0 || T <= 0) return fail(MK_EINVAL, "bad strides/dims");
+    DeviceGuard guard(b->device);
+    if (!guard.ok) return fail(MK_ECUDA, "cannot select CUDA device %d", b->device);
+    const size_t ts = tsize(b->dtype);
+    const size_t in_bytes = size_t(extent(b->B, D, T, sb, sd, sn)) * ts;
+    const size_t path_bytes = size_t(b->B) * T * sizeof(int32_t);
+    TRY(b->h_ll.ensure(in_bytes));
+    TRY(b->h_path.ensure(path_bytes));
+    TRY(b->h_logz.ensure(b->B * ts));
+    cudaStream_t st = b->own_stream;
+    CK(cudaMemcpyAsync(b->h_ll.p, ll, in_bytes, cudaMemcpyHostToDevice, st));
+    TRY(dispatch(b, MODE_BEST, mkargs(b->h_ll.p, sb, sd, sn, D, T, expanded, seqlens, b->h_path.p, b->h_logz.p, st)));
+    CK(cudaMemcpyAsync(out_path, b->h_path.p, path_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_score, b->h_logz.p, b->B * ts, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return MK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,414 @@
+# SPDX-License-Identifier: MIT
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): log-likelihoods and pdf posteriors within 1e-4 relative
+in Float32 and 1e-9 in Float64; best-path state sequences bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_golden_fsm
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float32: dict(rtol=1e-4, atol=1e-6), np.float64: dict(rtol=1e-9, atol=1e-12)}
+# α/β are log-domain values of magnitude 10..1000: relative 1e-4 (f32) / 1e-9 (f64), with an
+# absolute floor for entries near 0
+TOL_STATE = {np.float32: dict(rtol=1e-4, atol=1e-4), np.float64: dict(rtol=1e-9, atol=1e-9)}
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.cuda.set_device(0)
+    return torch
+
+
+class forced:
+    """MK_FORCE_KERNEL is read when the batch is created."""
+
+    def __init__(self, which):
+        self.which = which
+
+    def __enter__(self):
+        self.old = os.environ.get("MK_FORCE_KERNEL")
+        if self.which:
+            os.environ["MK_FORCE_KERNEL"] = self.which
+        else:
+            os.environ.pop("MK_FORCE_KERNEL", None)
+
+    def __exit__(self, *a):
+        if self.old is None:
+            os.environ.pop("MK_FORCE_KERNEL", None)
+        else:
+            os.environ["MK_FORCE_KERNEL"] = self.old
+
+
+def gpu_batch(mm, graphs, D, force=None):
+    """graphs: list of (fsm, pdfids); identical objects are compiled once."""
+    cache = {}
+    cs = []
+    for f, p in graphs:
+        if id(f) not in cache:
+            cache[id(f)] = mm.compile(f, mm.statemap(f, D, p))
+        cs.append(cache[id(f)])
+    with forced(force):
+        return mm.batch(*cs)
+
+
+def orc_graphs(orc, graphs, D):
+    cache = {}
+    out = []
+    for f, p in graphs:
+        if id(f) not in cache:
+            cache[id(f)] = orc.OracleGraph(f, p, D)
+        out.append(cache[id(f)])
+    return out
+
+
+def dev(torch, V_btd):
+    """(B, T, D) host array -> the (B, D, T) strided device view a network output gives."""
+    return torch.from_numpy(np.ascontiguousarray(V_btd)).cuda().permute(0, 2, 1)
+
+
+def assert_states_close(got, want, dtype):
+    got, want = np.asarray(got), np.asarray(want)
+    inf_w = np.isneginf(want)
+    np.testing.assert_array_equal(np.isneginf(got), inf_w)
+    np.testing.assert_allclose(got[~inf_w], want[~inf_w], **TOL_STATE[dtype])
+
+
+# ---------------------------------------------------------------------------------------------
+# known answers straight from the reference tree
+# ---------------------------------------------------------------------------------------------
+GAMMA_DEMO = np.array([[1, .5, 1 / 6, 0, 0], [0, .5, 2 / 3, .5, 0], [0, 0, 1 / 6, .5, 1]])
+
+
+@pytest.mark.parametrize("force", ["small", "shared"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_demo_posteriors(torch, mm, dtype, force):
+    """examples/demo.ipynb cell 13."""
+    K = mm.LogSemiring[dtype]
+    g = mm.graphs.hmm3(K)
+    b = gpu_batch(mm, [g], 3, force)
+    post, ttl = mm.pdfposteriors(b, torch.zeros((1, 3, 5), dtype=torch.float32 if dtype == np.float32 else torch.float64,
+                                             device="cuda"))
+    np.testing.assert_allclose(post[0].cpu().numpy(), GAMMA_DEMO, atol=2e-6 if dtype == np.float32 else 1e-12)
+    assert float(ttl[0]) == pytest.approx(np.log(6 / 32), rel=1e-5 if dtype == np.float32 else 1e-12)
+
+
+@pytest.mark.parametrize("force", ["small", "shared"])
+def test_ragged_batch_kat(torch, mm, orc, force):
+    """test/test_algorithms.jl:218-248: lhs = ones(3,7,2), seqlengths = [5,7]."""
+    K = mm.LogSemiring[np.float32]
+    g = mm.graphs.hmm3(K)
+    b = gpu_batch(mm, [g, g], 3, force)
+    V = np.ones((2, 7, 3), np.float32)
+    post, ttl = mm.pdfposteriors(b, dev(torch, V), seqlengths=[5, 7])
+    post, ttl = post.cpu().numpy(), ttl.cpu().numpy()
+    opost, ottl = orc.pdfposteriors(orc_graphs(orc, [g, g], 3), V, [5, 7])
+    np.testing.assert_allclose(post, opost, **TOL[np.float32])
+    np.testing.assert_allclose(ttl, ottl, rtol=1e-4)
+    assert np.all(post[0, :, 5:] == 0.0)
+
+
+@pytest.mark.parametrize("force", ["small", "shared"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_bestpath_chain(torch, mm, dtype, force):
+    """test/test_algorithms.jl:262-283 => "a b c d"."""
+    K = mm.TropicalSemiring[dtype]
+    g = mm.graphs.chain(K)
+    b = gpu_batch(mm, [g, g], 4, force)
+    path, score = mm.bestpath(b, dev(torch, np.ones((2, 6, 4), dtype)), seqlengths=[4, 3])
+    np.testing.assert_array_equal(path[0].cpu().numpy(), [1, 2, 3, 4, 0, 0])
+    assert float(score[0]) == 4.0
+    assert float(score[1]) == -np.inf and np.all(path[1].cpu().numpy() == 0)
+
+
+@pytest.mark.parametrize("dtype,rel", [(np.float32, 1e-4), (np.float64, 1e-9)])
+@pytest.mark.parametrize("force", ["small", "shared"])
+def test_den_fsm_wsj_logz(torch, mm, dtype, rel, force):
+    """the reference's benchmark graph, lhs = ones(84, N)."""
+    K = mm.LogSemiring[dtype]
+    g = load_golden_fsm("den_fsm_wsj", K)
+    b = gpu_batch(mm, [g] * 4, 84, force)
+    for N, want in ((20, 12.578496038935), (100, 92.531024082122)):
+        V = np.ones((4, N, 84), dtype)
+        post, ttl = mm.pdfposteriors(b, dev(torch, V))
+        np.testing.assert_allclose(ttl.cpu().numpy(), want, rtol=rel)
+        np.testing.assert_allclose(post.cpu().numpy().sum(axis=1), 1.0, atol=1e-5 if dtype == np.float32 else 1e-10)
+
+
+def test_num_fsm_wsj_unreachable(torch, mm):
+    """Appendix B item 7: final state unreachable in < 166 frames -> posteriors 0, logZ -Inf."""
+    K = mm.LogSemiring[np.float32]
+    g = load_golden_fsm("num_fsm_wsj", K)
+    b = gpu_batch(mm, [g, g], 84)
+    post, ttl = mm.pdfposteriors(b, dev(torch, np.zeros((2, 166, 84), np.float32)), seqlengths=[165, 166])
+    post, ttl = post.cpu().numpy(), ttl.cpu().numpy()
+    assert ttl[0] == -np.inf and np.all(post[0] == 0.0) and not np.isnan(post).any()
+    assert np.isfinite(ttl[1])
+    np.testing.assert_allclose(post[1].sum(axis=0), 1.0, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# seeded random inputs vs the oracle
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_numerator_batch_vs_oracle(torch, mm, orc, dtype):
+    """cfg 2 shape (distinct per-utterance graphs, ragged lengths), reduced batch."""
+    K = mm.LogSemiring[dtype]
+    rng = np.random.default_rng(202)
+    B, T, D = 12, 60, 200
+    graphs = [mm.graphs.numerator(K, np.random.default_rng(202 + k), D, n_phones=int(rng.integers(8, 20))) for k in range(B)]
+    V = (rng.standard_normal((B, T, D)) * 2).astype(dtype)
+    lens = rng.integers(T // 2, T + 1, B).astype(np.int32)
+    lens[0] = T
+    b = gpu_batch(mm, graphs, D)
+    post, ttl = mm.pdfposteriors(b, dev(torch, V), seqlengths=lens)
+    opost, ottl = orc.pdfposteriors(orc_graphs(orc, graphs, D), V, lens)
+    assert np.isfinite(ottl).all()
+    np.testing.assert_allclose(ttl.cpu().numpy(), ottl, rtol=TOL[dtype]["rtol"])
+    np.testing.assert_allclose(post.cpu().numpy(), opost, **TOL[dtype])
+    for k in range(B):
+        assert np.all(post[k, :, int(lens[k]):].cpu().numpy() == 0.0)
+
+
+@pytest.mark.parametrize("dtype,force", [(np.float32, None), (np.float32, "small"), (np.float64, None)])
+def test_denominator_vs_oracle(torch, mm, orc, dtype, force):
+    """cfg 3 shape, reduced: replicated denominator through the shared-graph kernel (U not a
+    multiple of 4, ragged lengths) and, forced, through the per-utterance kernel."""
+    K = mm.LogSemiring[dtype]
+    rng = np.random.default_rng(303)
+    B, T, D = 10, 40, 300
+    g = mm.graphs.denominator(K, n_tokens=1500, n_pdf=D, seed=303)
+    V = (rng.standard_normal((B, T, D)) * 2).astype(dtype)
+    lens = rng.integers(T // 2, T + 1, B).astype(np.int32)
+    b = gpu_batch(mm, [g] * B, D, force)
+    post, ttl = mm.pdfposteriors(b, dev(torch, V), seqlengths=lens)
+    opost, ottl = orc.pdfposteriors(orc_graphs(orc, [g] * B, D), V, lens)
+    np.testing.assert_allclose(ttl.cpu().numpy(), ottl, rtol=TOL[dtype]["rtol"])
+    np.testing.assert_allclose(post.cpu().numpy(), opost, **TOL[dtype])
+
+
+def test_mixed_batch_vs_oracle(torch, mm, orc):
+    """One batch holding the replicated denominator (shared-graph kernel, interleaved utterance
+    indices) and distinct small graphs (per-utterance kernel)."""
+    K = mm.LogSemiring[np.float32]
+    rng = np.random.default_rng(11)
+    T, D = 30, 120
+    den = mm.graphs.denominator(K, n_tokens=1100, n_pdf=D, seed=5)
+    nums = [mm.graphs.numerator(K, np.random.default_rng(50 + k), D, n_phones=6) for k in range(5)]
+    graphs = []
+    for k in range(9):
+        graphs.append(den)
+        if k < 5:
+            graphs.append(nums[k])
+    B = len(graphs)
+    V = (rng.standard_normal((B, T, D)) * 2).astype(np.float32)
+    lens = rng.integers(T // 2, T + 1, B).astype(np.int32)
+    b = gpu_batch(mm, graphs, D)
+    post, ttl = mm.pdfposteriors(b, dev(torch, V), seqlengths=lens)
+    opost, ottl = orc.pdfposteriors(orc_graphs(orc, graphs, D), V, lens)
+    np.testing.assert_allclose(ttl.cpu().numpy(), ottl, rtol=1e-4)
+    np.testing.assert_allclose(post.cpu().numpy(), opost, **TOL[np.float32])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("semiring", ["log", "tropical"])
+@pytest.mark.parametrize("force", ["small", "shared"])
+def test_alpha_beta_recursions(torch, mm, orc, dtype, semiring, force):
+    """αrecursion / βrecursion outputs in the reference's (ΣŜ x N̂) layout."""
+    K = (mm.LogSemiring if semiring == "log" else mm.TropicalSemiring)[dtype]
+    rng = np.random.default_rng(21)
+    T, D = 25, 60
+    g1 = mm.graphs.denominator(K, n_tokens=150, n_pdf=D, seed=9)
+    g2 = mm.graphs.numerator(K, rng, D, n_phones=7)
+    graphs = [g1, g2, g1, g1, g2]
+    B = len(graphs)
+    V = (rng.standard_normal((B, T, D)) * 2).astype(dtype)
+    lens = np.array([T, T - 3, T - 10, T, 12], np.int32)
+    b = gpu_batch(mm, graphs, D, force)
+    A = mm.αrecursion(b, dev(torch, V), seqlengths=lens).cpu().numpy()
+    Bm = mm.βrecursion(b, dev(torch, V), seqlengths=lens).cpu().numpy()
+    assert A.shape == (b.total_states_hat, T + 1) == Bm.shape
+    og = orc_graphs(orc, graphs, D)
+    for k in range(B):
+        oA, oB = orc.alpha_beta(og[k], V[k], lens[k])
+        lo, hi = b.offsets[k], b.offsets[k + 1]
+        assert_states_close(A[lo:hi], oA, dtype)
+        assert_states_close(Bm[lo:hi], oB, dtype)
+
+
+def test_tropical_alpha_bit_exact(torch, mm, orc):
+    """max / + are exact in floating point: tropical α must match the oracle bit for bit."""
+    K = mm.TropicalSemiring[np.float32]
+    rng = np.random.default_rng(3)
+    T, D = 30, 80
+    g = mm.graphs.denominator(K, n_tokens=400, n_pdf=D, seed=4)
+    V = (rng.standard_normal((3, T, D)) * 2).astype(np.float32)
+    for force in ("small", "shared"):
+        b = gpu_batch(mm, [g] * 3, D, force)
+        A = mm.αrecursion(b, dev(torch, V)).cpu().numpy()
+        for k in range(3):
+            oA, _ = orc.alpha_beta(orc_graphs(orc, [g], D)[0], V[k], want_beta=False)
+            np.testing.assert_array_equal(A[b.offsets[k]:b.offsets[k + 1]], oA)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("force", ["small", "shared"])
+def test_bestpath_vs_oracle(torch, mm, orc, dtype, force):
+    K = mm.TropicalSemiring[dtype]
+    rng = np.random.default_rng(505)
+    T, D = 50, 100
+    den = mm.graphs.denominator(K, n_tokens=500, n_pdf=D, seed=6)
+    loop = mm.graphs.phone_loop(K, n_phones=11)
+    loop = (loop[0], loop[1] % D)
+    graphs = [den] * 6 + [loop] * 3
+    B = len(graphs)
+    V = (rng.standard_normal((B, T, D)) * 2).astype(dtype)
+    lens = rng.integers(T // 2, T + 1, B).astype(np.int32)
+    b = gpu_batch(mm, graphs, D, force)
+    path, score = mm.bestpath(b, dev(torch, V), seqlengths=lens)
+    opath, oscore = orc.bestpath(orc_graphs(orc, graphs, D), V, lens)
+    np.testing.assert_array_equal(path.cpu().numpy(), opath)
+    np.testing.assert_array_equal(score.cpu().numpy(), oscore)
+    for k in range(B):
+        assert np.all(opath[k, :lens[k]] > 0) and np.all(opath[k, lens[k]:] == 0)
+
+
+def test_bestpath_ties_take_smallest_predecessor(torch, mm, orc):
+    """Two exactly tied branches 1->2->4 and 1->3->4: the path goes through state 2."""
+    K = mm.TropicalSemiring[np.float32]
+    fsm = mm.FSM.from_arrays(K, 4, [0, 0, 1, 2], [1, 2, 3, 3], [0.0] * 4, [0], [0.0], [3], [0.0])
+    pdf = np.zeros(4, np.int64)
+    V = np.zeros((1, 3, 1), np.float32)
+    for force in ("small", "shared"):
+        b = gpu_batch(mm, [(fsm, pdf)], 1, force)
+        path, score = mm.bestpath(b, dev(torch, V))
+        np.testing.assert_array_equal(path.cpu().numpy(), [[1, 2, 4]])
+    opath, _ = orc.bestpath(orc_graphs(orc, [(fsm, pdf)], 1), V)
+    np.testing.assert_array_equal(opath, [[1, 2, 4]])
+
+
+def test_expanded_inputs_and_reference_call_shape(torch, mm, orc):
+    """The reference's call: pdfposteriors(rawunion(fsms...), V̂s, Ĉs) with expanded D̂ x N̂
+    matrices (examples/test_cuda.jl:124-128) gives the same result as the un-expanded call."""
+    K = mm.LogSemiring[np.float32]
+    rng = np.random.default_rng(8)
+    T, D = 20, 40
+    fsms = [mm.graphs.numerator(K, rng, D, n_phones=5) for _ in range(3)]
+    lens = [20, 14, 17]
+    V = (rng.standard_normal((3, T, D)) * 2).astype(np.float32)
+    Vhats = [torch.from_numpy(mm.expand(V[k].T, lens[k])).cuda() for k in range(3)]
+    Cs = [mm.statemap(f, D, p) for f, p in fsms]
+    post, ttl = mm.pdfposteriors(mm.rawunion(*[f for f, _ in fsms]), Vhats, Cs)
+    opost, ottl = orc.pdfposteriors(orc_graphs(orc, fsms, D), V, lens)
+    assert tuple(post.shape) == (3, D, T)
+    np.testing.assert_allclose(ttl.cpu().numpy(), ottl, rtol=1e-4)
+    np.testing.assert_allclose(post.cpu().numpy(), opost, **TOL[np.float32])
+
+
+def test_host_buffer_entry_point(torch, mm, orc):
+    """numpy in -> numpy out through mk_pdfposteriors_host / mk_bestpath_host."""
+    K = mm.LogSemiring[np.float32]
+    rng = np.random.default_rng(12)
+    B, T, D = 9, 30, 100
+    g = mm.graphs.denominator(K, n_tokens=1100, n_pdf=D, seed=2)
+    V = (rng.standard_normal((B, T, D)) * 2).astype(np.float32)
+    b = gpu_batch(mm, [g] * B, D)
+    post, ttl = mm.pdfposteriors(b, V.transpose(0, 2, 1))
+    assert isinstance(post, np.ndarray)
+    opost, ottl = orc.pdfposteriors(orc_graphs(orc, [g] * B, D), V)
+    np.testing.assert_allclose(ttl, ottl, rtol=1e-4)
+    np.testing.assert_allclose(post, opost, **TOL[np.float32])
+    Kt = mm.TropicalSemiring[np.float32]
+    gt = mm.graphs.denominator(Kt, n_tokens=1100, n_pdf=D, seed=2)
+    path, score = mm.bestpath(gpu_batch(mm, [gt] * B, D), V.transpose(0, 2, 1))
+    opath, oscore = orc.bestpath(orc_graphs(orc, [gt] * B, D), V)
+    np.testing.assert_array_equal(path, opath)
+    np.testing.assert_array_equal(score, oscore)
+
+
+def test_dimension_mismatch(torch, mm):
+    """@boundscheck ... throw(DimensionMismatch()) (src/linalg.jl:166-167)."""
+    K = mm.LogSemiring[np.float32]
+    g = mm.graphs.hmm3(K)
+    b = gpu_batch(mm, [g, g], 3)
+    with pytest.raises(mm.DimensionMismatch):
+        mm.pdfposteriors(b, torch.zeros((2, 7, 5), device="cuda"))  # 7 pdfs for a 3-pdf graph
+    with pytest.raises(mm.DimensionMismatch):
+        mm.pdfposteriors(b, torch.zeros((3, 3, 5), device="cuda"))  # 3 utterances for 2 FSMs
+    with pytest.raises(mm.DimensionMismatch):
+        mm.pdfposteriors(b, torch.zeros((2, 3, 5), device="cuda"), seqlengths=[5, 6])
+    with pytest.raises(mm.DimensionMismatch):
+        mm.bestpath(b, torch.zeros((2, 3, 5), device="cuda"))  # Log graphs
+    Kd = mm.LogSemiring[np.float64]
+    with pytest.raises(mm.DimensionMismatch):
+        mm.batch(mm.compile(g[0], mm.statemap(g[0], 3, g[1])),
+                 mm.compile(*(lambda f, p: (f, mm.statemap(f, 3, p)))(*mm.graphs.hmm3(Kd))))
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: size-independent properties + a sampled oracle comparison
+# ---------------------------------------------------------------------------------------------
+def test_cfg3_full_size_properties(torch, mm, orc):
+    """cfg 3: S=30 000, ~520k arcs, D=3 000, B=128, T=150, Float32."""
+    K = mm.LogSemiring[np.float32]
+    B, T, D = 128, 150, 3000
+    g = mm.graphs.denominator(K)
+    gen = torch.Generator(device="cuda").manual_seed(303)
+    V = torch.randn((B, T, D), generator=gen, device="cuda") * 2
+    b = gpu_batch(mm, [g] * B, D)
+    post, ttl = mm.pdfposteriors(b, V.permute(0, 2, 1))
+    torch.cuda.synchronize()
+    assert tuple(post.shape) == (B, D, T) and post.stride() == (1, B, B * D)
+    assert bool(torch.isfinite(ttl).all()) and bool(torch.isfinite(post).all()) and float(post.min()) >= 0.0
+    # every frame's pdf posteriors sum to 1 (the reference normalises per frame, :157-158)
+    torch.testing.assert_close(post.sum(dim=1), torch.ones((B, T), device="cuda"), rtol=0, atol=2e-4)
+    # linearity in a per-utterance constant: adding c to every log-likelihood adds T*c to logZ
+    # and leaves the posteriors unchanged
+    post2, ttl2 = mm.pdfposteriors(b, (V + 0.5).permute(0, 2, 1))
+    torch.testing.assert_close(ttl2, ttl + 0.5 * T, rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(post2, post, rtol=1e-3, atol=1e-6)
+    # sampled oracle comparison: 3 utterances of the 128
+    idx = [0, 77, 127]
+    Vh = V[idx].cpu().numpy()
+    opost, ottl = orc.pdfposteriors(orc_graphs(orc, [g] * len(idx), D), Vh)
+    np.testing.assert_allclose(ttl[idx].cpu().numpy(), ottl, rtol=1e-4)
+    np.testing.assert_allclose(post[idx].cpu().numpy(), opost, **TOL[np.float32])
+
+
+def test_cfg5_bestpath_full_graph(torch, mm, orc):
+    """cfg 5 graph (tropical denominator) at a reduced batch: path is a valid arc sequence whose
+    score equals the reported one, and matches the oracle on sampled utterances."""
+    K = mm.TropicalSemiring[np.float32]
+    B, T, D = 32, 100, 3000
+    g = mm.graphs.denominator(K)
+    fsm, pdfids = g
+    rng = np.random.default_rng(505)
+    V = (rng.standard_normal((B, T, D)) * 2).astype(np.float32)
+    b = gpu_batch(mm, [g] * B, D)
+    path, score = mm.bestpath(b, dev(torch, V))
+    path, score = path.cpu().numpy(), score.cpu().numpy()
+    Tm = fsm.T if fsm.nstates <= 4000 else None
+    assert Tm is None
+    import scipy.sparse as sp
+    src, dst, w = fsm.arcs_hat()
+    M = sp.csr_matrix((w.astype(np.float64) + 1e3, (src, dst)), shape=(fsm.nstates_hat,) * 2)  # shift: keep zeros explicit
+    for k in (0, 13, 31):
+        p = path[k] - 1
+        tot = float(fsm.α[p[0]]) + float(V[k, 0, pdfids[p[0]]])
+        for n in range(1, T):
+            a = M[p[n - 1], p[n]]
+            assert a != 0, "path uses a non-existent arc"
+            tot += (a - 1e3) + float(V[k, n, pdfids[p[n]]])
+        tot += float(fsm.ω[p[-1]])
+        assert tot == pytest.approx(float(score[k]), rel=1e-5)
+    idx = [0, 13]
+    opath, oscore = orc.bestpath(orc_graphs(orc, [g] * 2, D), V[idx])
+    np.testing.assert_array_equal(path[idx], opath)
+    np.testing.assert_array_equal(score[idx], oscore)
