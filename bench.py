@@ -1,0 +1,299 @@
+# SPDX-License-Identifier: MIT
+"""bench.py — LF-MMI denominator forward-backward throughput (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm
+                                                             # (oracle port) on the host cores
+
+A step is one `pdfposteriors` (forward + backward + pdf posteriors, src/inference.jl:145-161)
+over one batch of synthetic input.  Workload per GPU = BASELINE.json configs[2]: the synthetic
+Kaldi-chain denominator graph (S = 30 000 states, ~520k arcs, D = 3 000 pdfs; SURVEY.md §8d cfg 3),
+B = 128 utterances x T = 150 frames, LogSemiring{Float32}.  With N GPUs every rank runs its own
+128 utterances on a replicated graph (weak scaling; N = 8 is configs[3]'s 1 024 utterances) and
+the ranks exchange only [Σ logZ, #frames, pdf occupancy[D]] with one NCCL all-reduce per step.
+
+Prints ONE JSON line (rank 0).  `value`: device-resident inputs; `e2e`: the same call on HOST
+(pinned) buffers, H2D + D2H inside the timed region; `roofline`: the shared-graph kernel's
+algorithmic HBM bytes / its CUDA-event time against MEASURED_PEAKS.json; `cpu_baseline`: the
+oracle port timed on this box's cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "LF-MMI denominator forward-backward frames/sec (batch x T)"
+UNIT = "frames/s"
+B_PER_GPU, T_FRAMES, N_PDF, N_TOKENS, SEED = 128, 150, 3000, 15000, 303
+HBM_FALLBACK_GBS = 6650.0
+
+
+def workload_config(n_gpus, b_per_gpu, frames):
+    return {"workload": "BASELINE.json configs[2]: synthetic Kaldi-chain denominator graph (30000 states, "
+                        "3000 pdfs, SURVEY.md 8d cfg 3), LogSemiring{Float32}, forward-backward (pdfposteriors)",
+            "batch_per_gpu": b_per_gpu, "global_batch": b_per_gpu * n_gpus, "frames": frames,
+            "graph": "replicated per GPU", "parallelism": f"utterance-sharded x{n_gpus}",
+            "l2": "inputs larger than L2 (alpha store 2.3 GB, emissions 230 MB per step)"}
+
+
+class ClockSampler(threading.Thread):
+    """NVML sampler: SM clock + throttle reasons while the timed region runs."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.mask, self.stop_flag, self.max_mhz, self.err = index, [], 0, False, None, None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    self.mask |= pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    self.mask |= pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                time.sleep(0.005)
+        except Exception as e:  # no NVML: report it rather than invent numbers
+            self.err = repr(e)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        if self.err or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "error": self.err or "no samples"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": [n for bit, n in self.REASONS.items() if self.mask & bit], "samples": len(self.samples)}
+
+
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback"
+
+
+def build_graph(mm):
+    K = mm.LogSemiring[np.float32]
+    return K, mm.graphs.denominator(K, n_tokens=N_TOKENS, n_pdf=N_PDF, seed=SEED)
+
+
+def cpu_sample(fsm, pdfids, n_utts, frames, threads, seed=SEED):
+    """Time the oracle port on `n_utts` utterances x `frames` frames of the workload."""
+    import oracle
+    og = oracle.OracleGraph(fsm, pdfids, N_PDF)
+    rng = np.random.default_rng(seed)
+    V = (rng.standard_normal((n_utts, frames, N_PDF)) * 2).astype(np.float32)
+    t0 = time.perf_counter()
+    oracle.pdfposteriors([og] * n_utts, V, threads=threads)
+    return n_utts * frames / (time.perf_counter() - t0)
+
+
+def run_reference(args):
+    """The reference's own CPU algorithm for the path (oracle port: the reference is Julia and
+    cannot run here) on all host cores; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import markov_b200 as mm
+    import oracle
+    K, (fsm, pdfids) = build_graph(mm)
+    threads = oracle.num_threads()
+    # bounded sample: one utterance per thread; frames chosen so that warmup+steps end in ~2-3 min
+    # (one 150-frame utterance takes ~6.5 s on one core)
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    frames = int(min(T_FRAMES, max(10, T_FRAMES * budget / 8.0)))
+    og = oracle.OracleGraph(fsm, pdfids, N_PDF)
+    rng = np.random.default_rng(SEED)
+    V = (rng.standard_normal((threads, frames, N_PDF)) * 2).astype(np.float32)
+    for _ in range(args.warmup):
+        oracle.pdfposteriors([og] * threads, V, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.pdfposteriors([og] * threads, V, threads=threads)
+    dt = time.perf_counter() - t0
+    value = args.steps * threads * frames / dt
+    sample = f"{threads} utterances x {frames} frames of the workload per step (one utterance per thread)"
+    cfg = workload_config(args.gpus, B_PER_GPU, T_FRAMES)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "oracle port (C++ restatement of src/inference.jl, OpenMP over utterances); the Julia "
+                "reference cannot run in this image"}))
+
+
+def run_ours(args):
+    import torch
+    import markov_b200 as mm
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (libmarkov_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B, T, D = args.batch, args.frames, N_PDF
+    K, (fsm, pdfids) = build_graph(mm)
+    cfsm = mm.compile(fsm, mm.statemap(fsm, D, pdfids))
+    bfsm = mm.batch(*[cfsm] * B)
+    gen = torch.Generator(device="cuda").manual_seed(SEED + rank)
+    V = torch.randn((B, T, D), generator=gen, device="cuda") * 2  # the network's (B, T, D) output
+    Vd = V.permute(0, 2, 1)                                        # (B, D, T) view the API takes
+    post = torch.empty((T, D, B), device="cuda")
+    ttl = torch.empty((B,), device="cuda")
+    stats = torch.zeros((D + 2,), device="cuda")
+    lib = mm.lib()
+
+    def step():
+        mm.pdfposteriors(bfsm, Vd, out=(post, ttl))
+        # the data-parallel exchange: Σ logZ, #frames, per-pdf occupancy (12 KB)
+        stats[0] = ttl.sum()
+        stats[1] = float(B * T)
+        stats[2:] = post.sum(dim=(0, 2))
+        if dist is not None:
+            dist.all_reduce(stats)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    bfsm.profile(True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    lib.mk_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    sync_all()
+    launches = int(lib.mk_launch_count(0))
+    clocks = sampler.result() if sampler else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    kern = bfsm.kernel_ms(min(args.steps, 64))
+    kms = torch.tensor([float(np.mean(kern))], device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kms, op=dist.ReduceOp.MAX)
+    ms_total, kernel_ms = float(ms), float(kms)
+    bfsm.profile(False)
+    logz_mean = float(stats[0]) / (B * world)
+
+    # ---- e2e: the public API on HOST buffers, copies inside the timed region
+    Vh = torch.empty((B, T, D), pin_memory=True)
+    Vh.copy_(V)
+    post_h = torch.empty((T, D, B), pin_memory=True)
+    ttl_h = torch.empty((B,), pin_memory=True)
+    Vh_np, post_np, ttl_np = Vh.numpy().transpose(0, 2, 1), post_h.numpy(), ttl_h.numpy()
+
+    def step_e2e():
+        mm.pdfposteriors(bfsm, Vh_np, out=(post_np, ttl_np))  # H2D + kernels + D2H + sync inside
+        return float(ttl_np.sum())
+
+    for _ in range(2):
+        step_e2e()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_t = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if dist is not None:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_t)
+    h2d = Vh.numel() * 4
+    d2h = (post_h.numel() + ttl_h.numel()) * 4
+    # the two paths must agree
+    torch.testing.assert_close(torch.from_numpy(ttl_np).cuda(), ttl, rtol=1e-5, atol=1e-3)
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    frames_total = world * B * T
+    value = frames_total * args.steps / (ms_total * 1e-3)
+    # roofline of the dominant kernel: algorithmic HBM bytes:
+    # w*(2*Ŝ + 3*D̂) per frame.utterance = α written + α read + emissions read twice + posteriors written
+    bytes_per_unit = 4 * (2 * fsm.nstates_hat + 3 * (D + 1))
+    units = B * T
+    achieved = bytes_per_unit * units / (kernel_ms * 1e-3) / 1e9
+    peak, which = hbm_peak()
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(world, B, T),
+        "e2e": {"value": frames_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})",
+                     "kernel": "shared_fb_kernel<float, Log>", "kernel_ms": kernel_ms,
+                     "bytes_per_frame_utt": bytes_per_unit, "units_per_launch": units,
+                     "kernel_share_of_step": kernel_ms / (ms_total / args.steps),
+                     "note": "HBM is not the binding ceiling of this kernel: the recursion is bound by the L2 "
+                             "gather of state vectors and the MUFU ex2 rate (DESIGN.md)"},
+        "mean_logz": logz_mean,
+    }
+    if world == 1 and not args.skip_cpu_baseline:
+        import oracle
+        threads = oracle.num_threads()
+        n_utts, frames = threads, T
+        v = cpu_sample(fsm, pdfids, n_utts, frames, threads)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                               "sample": f"{n_utts} utterances x {frames} frames of the workload, one utterance per "
+                                         f"thread (OpenMP), C++ oracle port of src/inference.jl"}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="utterances per GPU")
+    ap.add_argument("--frames", type=int, default=T_FRAMES)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if args.gpus != world and world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

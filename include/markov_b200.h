@@ -142,11 +142,12 @@ int mk_bestpath_host(mk_batch* b, const void* ll, int64_t stride_b, int64_t stri
  * the last reset (bench.py's gpu_launches), and workspace bytes held by a batch. */
 int64_t mk_launch_count(int reset);
 int64_t mk_batch_workspace_bytes(const mk_batch* b);
-/* When enabled, CUDA events are recorded (on the call's stream) around the dominant kernel of
- * the next calls — the shared-graph forward-backward kernel; mk_batch_last_kernel_ms waits for
- * the last recorded pair and returns its duration (of the batch's last shared-graph group). */
+/* When enabled, CUDA events are recorded (on the call's stream) around every launch of the
+ * dominant kernel — the shared-graph forward-backward kernel — into a ring of 64 pairs;
+ * mk_batch_kernel_ms waits for and returns the durations of the most recent launches (up to
+ * `cap`, oldest first).  Enabling resets the ring. */
 int mk_batch_profile(mk_batch* b, int enable);
-int mk_batch_last_kernel_ms(mk_batch* b, float* ms);
+int mk_batch_kernel_ms(mk_batch* b, float* ms, int cap, int* n);
 
 #ifdef __cplusplus
 }

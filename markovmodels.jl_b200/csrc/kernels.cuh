@@ -218,95 +218,235 @@ __device__ __forceinline__ V4<T> row_reduce(const Arc<T>* __restrict__ arcs, int
     return out;
 }
 
+// ---- ordered integer keys: float max through integer atomicMax (works for negatives, -Inf) ----
+constexpr int kKeyMin = int(0x80000000);
+__device__ __forceinline__ int fkey(float x) {
+    int b = __float_as_int(x);
+    return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float fkey_inv(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+// the per-frame normaliser: the (float-rounded) maximum if it is finite, else 0
+template <int SR, typename T> __device__ __forceinline__ T shift_from_key(int k) {
+    if (SR != SR_LOG || k == kKeyMin) return T(0);
+    float f = fkey_inv(k);
+    return (f > -3.0e38f && f < 3.0e38f) ? T(f) : T(0);
+}
+template <typename T> __device__ __forceinline__ bool all_zero_bar(const V4<T>& e) {  // all four are 0̄
+    return e.v[0] == neg_inf<T>() && e.v[1] == neg_inf<T>() && e.v[2] == neg_inf<T>() && e.v[3] == neg_inf<T>();
+}
+
 // ================================================================================================
 // Shared-graph kernel
 // ================================================================================================
+// Forward work items: a full destination row, or one segment of a long row (in-degree above the
+// split threshold, e.g. the phony final state whose in-arcs are all the final weights).  A segment
+// writes its partial ⊕ to a scratch slot; every CTA combines the slots of the long rows at the
+// start of the next frame (redundantly, identical bits) so no second grid barrier is needed.
+//
+// Normalisation (Log semiring): the stored forward vector is a_n = α_n - Ca_n with
+// Ca_n = Σ_{k<=n} shift_k (float64) and shift_n = max_s a_{n-1}[s]; likewise b_n = β_n - Cb_n.  The
+// stored values stay O(10) whatever the sequence length, so Float32 keeps ~1e-6 absolute accuracy
+// in the log domain where the un-normalised recursion loses ulp(|α|) ≈ 3e-5 per operation.
 template <typename T> struct SharedParams {
     int S;       // Ŝ states incl. phony final (last)
     int Dh;      // D̂ pdfs incl. phony (last)
     int N1;      // N̂ frames incl. phony (last)
     int U4;      // utterances in the group, padded to a multiple of 4
     int ntiles;  // ceil(U4 / 128)
-    const int* in_ptr;  const Arc<T>* in_arcs;    // T̂ᵀ rows (by destination)
+    const Arc<T>* in_arcs;                        // T̂ᵀ rows (by destination)
+    const int4* fwd_items;                        // {row, arc_beg, arc_end, slot or -1}
+    const int* fwd_warp_items;                    // [grid*warps + 1] item ranges per warp
+    int n_long; const int4* fwd_long;             // {row, pseudo_beg, pseudo_end, 0}
+    const Arc<T>* fwd_long_arcs;                  // pseudo arcs {slot, 1̄} of the long rows
+    int n_slots; T* part;                         // [2][n_slots][U4] segment partials
     const int* out_ptr; const Arc<T>* out_arcs;   // T̂ rows (by source)
+    const int* bwd_rows;                          // [grid*warps + 1] row ranges per warp
     const int* pdf;                               // state -> pdf (0-based)
     const T* init_dense;                          // α̂ as a dense vector [S]
-    const int* fwd_rows;                          // [grid*warps + 1] row ranges per warp
-    const int* bwd_rows;
     const T* E;      // expanded, transposed emissions [N1][Dh][U4]
-    T* alpha;        // [N1][S][U4]
-    T* bt;           // [2][S][U4]   β_{n+1} ⊗ e_{n+1} ping-pong
-    T* beta_out;     // optional [N1][S][U4]
+    T* alpha;        // [N1][S][U4]   normalised a_n
+    T* bt;           // [2][S][U4]    b_{n+1} ⊗ e_{n+1} ping-pong
+    T* beta_out;     // optional [N1][S][U4]  normalised b_n
+    int* gkey;       // [2][N1][U4]   per-frame maxima (ordered keys): forward, backward
+    double* Coff;    // [2][N1][U4]   Ca_n, Cb_n
     // posterior output, the reference's (B, D, N) b-fastest array
     T* post; int B; int D; int Tn;
     const int* utt_b;  // [U4] global utterance index per group lane (-1 = padding)
     int post_vec4;     // 1: the 4 utterances of every lane are b0..b0+3, 16 B aligned
     T* zsum;           // [N1][B] per-frame normalisers (linear, relative to lz)
-    T* lz;             // [B] forward total log-likelihood (reference for γ)
+    T* lz;             // [B] forward total log-likelihood
     unsigned* barrier;
     int do_fwd, do_bwd, do_post;
 };
 
+// combine the segment partials of the long rows into a_m (every CTA, identical result)
+template <typename T, int SR>
+__device__ __forceinline__ void fwd_combine(const SharedParams<T>& p, int m, const T* s_shift, int* s_key) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int U4 = p.U4;
+    const size_t frame = size_t(p.S) * U4;
+    const T* Em = p.E + size_t(m) * p.Dh * U4;
+    const T* part = p.part + size_t(m & 1) * p.n_slots * U4;
+    for (int k = warp; k < p.n_long; k += kSharedWarps) {
+        const int4 lr = __ldg(p.fwd_long + k);
+        const int r = lr.x;
+        const int pdf = __ldg(p.pdf + r);
+        for (int tile = 0; tile < p.ntiles; ++tile) {
+            const int uoff = tile * kTileUtts + lane * 4;
+            if (uoff >= U4) continue;
+            V4<T> e = ld4_cs(Em + size_t(pdf) * U4 + uoff);
+            V4<T> val;
+            if (m == 0) {
+                T a0 = __ldg(p.init_dense + r);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) val.v[j] = a0;
+            } else if (all_zero_bar(e)) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) val.v[j] = neg_inf<T>();
+            } else {
+                val = row_reduce<T, SR>(p.fwd_long_arcs, lr.y, lr.z, part, U4, uoff);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                val.v[j] = val.v[j] + e.v[j] - s_shift[uoff + j];
+                atomicMax(&s_key[uoff + j], fkey(float(val.v[j])));
+            }
+            st4_cg(p.alpha + size_t(m) * frame + size_t(r) * U4 + uoff, val);
+        }
+    }
+}
+
 template <typename T, int SR>
 __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(SharedParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* s_lz = reinterpret_cast<T*>(smem_raw);  // [U4]
-    T* s_z = s_lz + p.U4;                      // [U4]
+    const int S = p.S, U4 = p.U4;
+    double* s_C = reinterpret_cast<double*>(smem_raw);   // [U4] running Ca (forward) / Cb (backward)
+    double* s_lz = s_C + U4;                              // [U4] log Z
+    T* s_shift = reinterpret_cast<T*>(s_lz + U4);         // [U4] shift of the current frame
+    T* s_g = s_shift + U4;                                // [U4] Ca_n + Cb_n - log Z
+    T* s_z = s_g + U4;                                    // [U4] per-frame posterior mass
+    int* s_key = reinterpret_cast<int*>(s_z + U4);        // [U4] running maxima
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * kSharedWarps + warp;
-    const int S = p.S, U4 = p.U4;
     const size_t frame = size_t(S) * U4;
     unsigned bar_target = 0;
 
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < size_t(2) * p.N1 * U4;
+         i += size_t(gridDim.x) * blockDim.x)
+        p.gkey[i] = kKeyMin;
+    for (int u = threadIdx.x; u < U4; u += blockDim.x) {
+        s_C[u] = 0.0; s_lz[u] = 0.0; s_shift[u] = T(0); s_g[u] = T(0); s_z[u] = T(0); s_key[u] = kKeyMin;
+    }
+    grid_sync(p.barrier, bar_target);
+
     // ---------------------------------------------------------------- forward (αrecursion)
     if (p.do_fwd) {
-        const int r0 = p.fwd_rows[gw], r1 = p.fwd_rows[gw + 1];
+        const int i0 = p.fwd_warp_items[gw], i1 = p.fwd_warp_items[gw + 1];
         for (int n = 0; n < p.N1; ++n) {
+            if (n >= 1) {
+                if (p.n_long) {
+                    fwd_combine<T, SR>(p, n - 1, s_shift, s_key);
+                    __syncthreads();
+                }
+                for (int u = threadIdx.x; u < U4; u += blockDim.x) {
+                    int k = max(__ldcg(p.gkey + size_t(n - 1) * U4 + u), s_key[u]);
+                    T sh = shift_from_key<SR, T>(k);
+                    s_shift[u] = sh;
+                    s_C[u] += double(sh);
+                    s_key[u] = kKeyMin;
+                    if (blockIdx.x == 0) p.Coff[size_t(n) * U4 + u] = s_C[u];
+                }
+                __syncthreads();
+            } else if (blockIdx.x == 0) {
+                for (int u = threadIdx.x; u < U4; u += blockDim.x) p.Coff[u] = 0.0;
+            }
             const T* prev = p.alpha + size_t(n > 0 ? n - 1 : 0) * frame;
             T* cur = p.alpha + size_t(n) * frame;
             const T* En = p.E + size_t(n) * p.Dh * U4;
+            T* part = p.part + size_t(n & 1) * p.n_slots * U4;
             for (int tile = 0; tile < p.ntiles; ++tile) {
                 const int uoff = tile * kTileUtts + lane * 4;
                 if (uoff >= U4) continue;
-                for (int r = r0; r < r1; ++r) {
+                T mx[4] = {neg_inf<T>(), neg_inf<T>(), neg_inf<T>(), neg_inf<T>()};
+                T sh[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sh[j] = s_shift[uoff + j];
+                for (int i = i0; i < i1; ++i) {
+                    const int4 it = __ldg(p.fwd_items + i);
+                    const int r = it.x;
+                    V4<T> e = ld4_cs(En + size_t(__ldg(p.pdf + r)) * U4 + uoff);
+                    const bool dead = all_zero_bar(e);  // ⊗ 0̄: the row's ⊕ cannot matter
+                    if (it.w >= 0) {  // segment of a long row: partial ⊕ only
+                        if (n > 0 && !dead)
+                            st4_cg(part + size_t(it.w) * U4 + uoff,
+                                   row_reduce<T, SR>(p.in_arcs, it.y, it.z, prev, U4, uoff));
+                        continue;
+                    }
                     V4<T> acc;
                     if (n == 0) {
                         T a0 = __ldg(p.init_dense + r);  // A[:,1] = α̂ ⊗ e₁  (:68)
 #pragma unroll
                         for (int j = 0; j < 4; ++j) acc.v[j] = a0;
-                    } else {
-                        acc = row_reduce<T, SR>(p.in_arcs, __ldg(p.in_ptr + r), __ldg(p.in_ptr + r + 1),
-                                                prev, U4, uoff);  // T̂ᵀ A[:,n-1]  (:70)
-                    }
-                    V4<T> e = ld4_cs(En + size_t(__ldg(p.pdf + r)) * U4 + uoff);
+                    } else if (dead) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc.v[j] += e.v[j];  // ⊗ e_n  (:71)
+                        for (int j = 0; j < 4; ++j) acc.v[j] = neg_inf<T>();
+                    } else {
+                        acc = row_reduce<T, SR>(p.in_arcs, it.y, it.z, prev, U4, uoff);  // T̂ᵀ A[:,n-1]  (:70)
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc.v[j] = acc.v[j] + e.v[j] - sh[j];  // ⊗ e_n  (:71), normalised
+                        mx[j] = max_(mx[j], acc.v[j]);
+                    }
                     st4_cg(cur + size_t(r) * U4 + uoff, acc);
                 }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) atomicMax(&s_key[uoff + j], fkey(float(mx[j])));
+            }
+            __syncthreads();
+            for (int u = threadIdx.x; u < U4; u += blockDim.x) {
+                int k = s_key[u];
+                if (k != kKeyMin) atomicMax(p.gkey + size_t(n) * U4 + u, k);
+                s_key[u] = kKeyMin;
             }
             grid_sync(p.barrier, bar_target);
         }
-        // total log-likelihood = α_{N̂}[phony final]
+        if (p.n_long) {
+            fwd_combine<T, SR>(p, p.N1 - 1, s_shift, s_key);
+            __syncthreads();
+        }
+        // log Z = α_{N̂}[phony final] = a + Ca
         const T* last = p.alpha + size_t(p.N1 - 1) * frame + size_t(S - 1) * U4;
-        if (blockIdx.x == 0)
-            for (int u = threadIdx.x; u < U4; u += blockDim.x) {
-                int b = p.utt_b[u];
-                if (b >= 0) p.lz[b] = __ldcg(last + u);
-            }
+        for (int u = threadIdx.x; u < U4; u += blockDim.x) {
+            T a = __ldcg(last + u);
+            double z = (a == neg_inf<T>()) ? double(a) : double(a) + s_C[u];
+            s_lz[u] = z;
+            int b = p.utt_b[u];
+            if (blockIdx.x == 0 && b >= 0) p.lz[b] = T(z);
+        }
+        __syncthreads();
     }
     if (!p.do_bwd) return;
 
     // ---------------------------------------------------------------- backward (βrecursion + γ)
-    if (p.do_post) {
-        const T* last = p.alpha + size_t(p.N1 - 1) * frame + size_t(S - 1) * U4;
+    for (int u = threadIdx.x; u < U4; u += blockDim.x) { s_C[u] = 0.0; s_key[u] = kKeyMin; s_z[u] = T(0); }
+    __syncthreads();
+    const int r0 = p.bwd_rows[gw], r1 = p.bwd_rows[gw + 1];
+    int* gkey_b = p.gkey + size_t(p.N1) * U4;
+    double* Cb = p.Coff + size_t(p.N1) * U4;
+    for (int n = p.N1 - 1; n >= 0; --n) {
         for (int u = threadIdx.x; u < U4; u += blockDim.x) {
-            s_lz[u] = __ldcg(last + u);
-            s_z[u] = T(0);
+            T sh = T(0);
+            if (n < p.N1 - 1) sh = shift_from_key<SR, T>(__ldcg(gkey_b + size_t(n + 1) * U4 + u));
+            s_shift[u] = sh;
+            s_C[u] += double(sh);
+            if (blockIdx.x == 0 && p.beta_out) Cb[size_t(n) * U4 + u] = s_C[u];
+            if (p.do_post) {
+                double lz = s_lz[u];
+                s_g[u] = (lz == double(neg_inf<T>())) ? T(0) : T(__ldcg(p.Coff + size_t(n) * U4 + u) + s_C[u] - lz);
+            }
         }
         __syncthreads();
-    }
-    const int r0 = p.bwd_rows[gw], r1 = p.bwd_rows[gw + 1];
-    for (int n = p.N1 - 1; n >= 0; --n) {
         const T* bt_next = p.bt + size_t((n + 1) & 1) * frame;
         T* bt_cur = p.bt + size_t(n & 1) * frame;
         const T* En = p.E + size_t(n) * p.Dh * U4;
@@ -315,32 +455,36 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(SharedPara
             const int uoff = tile * kTileUtts + lane * 4;
             if (uoff >= U4) continue;
             T zs[4] = {T(0), T(0), T(0), T(0)};
-            V4<T> lz;
-            if (p.do_post) {
+            T mx[4] = {neg_inf<T>(), neg_inf<T>(), neg_inf<T>(), neg_inf<T>()};
+            T sh[4], g[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    T v = s_lz[uoff + j];
-                    lz.v[j] = (v == neg_inf<T>()) ? T(0) : v;
-                }
-            }
+            for (int j = 0; j < 4; ++j) { sh[j] = s_shift[uoff + j]; g[j] = s_g[uoff + j]; }
             for (int i = r0; i < r1; ++i) {
+                const int pdf = __ldg(p.pdf + i);
+                V4<T> e = ld4_cs(En + size_t(pdf) * U4 + uoff);
+                // e_n = 0̄ kills α_n (so γ) and b_n ⊗ e_n; only an explicit β output still needs β_n
+                const bool dead = !p.beta_out && all_zero_bar(e);
                 V4<T> beta;
                 if (n == p.N1 - 1) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) beta.v[j] = T(0);  // B[:,end] = 1̄  (:104)
+                } else if (dead) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) beta.v[j] = neg_inf<T>();
                 } else {
-                    beta = row_reduce<T, SR>(p.out_arcs, __ldg(p.out_ptr + i), __ldg(p.out_ptr + i + 1),
-                                             bt_next, U4, uoff);  // T̂ (B[:,n+1] ⊗ e_{n+1})  (:106-107)
+                    beta = row_reduce<T, SR>(p.out_arcs, __ldg(p.out_ptr + i), __ldg(p.out_ptr + i + 1), bt_next,
+                                             U4, uoff);  // T̂ (B[:,n+1] ⊗ e_{n+1})  (:106-107)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) beta.v[j] -= sh[j];
                 }
-                const int pdf = __ldg(p.pdf + i);
                 if (p.beta_out) st4_cg(p.beta_out + size_t(n) * frame + size_t(i) * U4 + uoff, beta);
-                if (p.do_post) {
-                    // γ = α ⊗ β ⊘ logZ, exp, per-pdf ⊕  (:154-160)
+                if (p.do_post && !dead) {
+                    // γ = α ⊗ β ⊘ Z, exp, per-pdf ⊕  (:154-160)
                     V4<T> a = ld4_cs(An + size_t(i) * U4 + uoff);
                     V4<T> pg;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        pg.v[j] = exp_(a.v[j] + beta.v[j] - lz.v[j]);
+                        pg.v[j] = exp_(a.v[j] + beta.v[j] + g[j]);
                         zs[j] = lin_add<SR>(zs[j], pg.v[j]);
                     }
                     if (n < p.Tn && pdf < p.D) {
@@ -351,29 +495,35 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(SharedPara
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 int b = p.utt_b[uoff + j];
-                                if (b >= 0) red1<SR>(dst + b, pg.v[j]);
+                                if (b >= 0 && pg.v[j] > T(0)) red1<SR>(dst + b, pg.v[j]);
                             }
                         }
                     }
                 }
                 if (n > 0) {
-                    V4<T> e = ld4_cs(En + size_t(pdf) * U4 + uoff);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) beta.v[j] += e.v[j];
+                    for (int j = 0; j < 4; ++j) {
+                        beta.v[j] += e.v[j];
+                        mx[j] = max_(mx[j], beta.v[j]);
+                    }
                     st4_cg(bt_cur + size_t(i) * U4 + uoff, beta);
                 }
             }
-            if (p.do_post) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 4; ++j) {
+                if (n > 0) atomicMax(&s_key[uoff + j], fkey(float(mx[j])));
+                if (p.do_post) {
                     if (SR == SR_LOG) atomicAdd(&s_z[uoff + j], zs[j]);
                     else red_max1(&s_z[uoff + j], zs[j]);
                 }
             }
         }
-        if (p.do_post) {
-            __syncthreads();
-            for (int u = threadIdx.x; u < U4; u += blockDim.x) {
+        __syncthreads();
+        for (int u = threadIdx.x; u < U4; u += blockDim.x) {
+            int k = s_key[u];
+            if (k != kKeyMin) atomicMax(gkey_b + size_t(n) * U4 + u, k);
+            s_key[u] = kKeyMin;
+            if (p.do_post) {
                 int b = p.utt_b[u];
                 T v = s_z[u];
                 if (b >= 0 && v > T(0)) red1<SR>(p.zsum + size_t(n) * p.B + b, v);
@@ -443,6 +593,7 @@ template <typename T> struct UttDesc {
     int b;        // global utterance index
     long long ws_off;   // offset of this utterance's [N1][S] block in the α workspace
     long long out_off;  // state offset off_b in the virtual union (for user-layout outputs)
+    long long c_off;    // offset of this utterance's [N1] block in the Ca workspace
 };
 
 template <typename T> struct SmallParams {
@@ -450,10 +601,12 @@ template <typename T> struct SmallParams {
     const T* ll; long long sb, sd, sn;
     int D, Tn, expanded, Dh, N1;
     const int* seqlens;
-    // α destination: element (n, s) of utterance u at alpha + base + n*alpha_sn + s, with
-    // base = ws_off (workspace, alpha_sn = -1 meaning S) or out_off (user layout, alpha_sn = ΣŜ)
+    // α destination.  alpha_user == 0: normalised a_n into the workspace, element (n, s) at
+    // alpha + ws_off + n*S + s.  alpha_user == 1: un-normalised α into the caller's (ΣŜ x N̂)
+    // array, element at alpha + out_off + n*alpha_sn + s.
     T* alpha; long long alpha_sn; int alpha_user;
-    T* beta_out; long long beta_sn;  // user layout only
+    T* beta_out; long long beta_sn;  // user layout only (un-normalised β)
+    double* Ca;                      // [Σ N1] forward offsets
     T* post; int B;
     T* zsum; T* lz;
     int do_fwd, do_bwd, do_post;
@@ -461,20 +614,12 @@ template <typename T> struct SmallParams {
 
 template <typename T, int SR>
 __device__ __forceinline__ T small_row(const Arc<T>* __restrict__ arcs, int beg, int end, const T* vec) {
-    if (SR == SR_TROP) {
-        T m = neg_inf<T>();
-        for (int a = beg; a < end; ++a) {
-            Arc<T> arc = ld_arc(arcs + a);
-            m = max_(m, arc.w + vec[arc.idx]);
-        }
-        return m;
-    }
     T m = neg_inf<T>();
     for (int a = beg; a < end; ++a) {
         Arc<T> arc = ld_arc(arcs + a);
         m = max_(m, arc.w + vec[arc.idx]);
     }
-    if (m == neg_inf<T>()) return m;
+    if (SR == SR_TROP || m == neg_inf<T>()) return m;
     T s = T(0);
     for (int a = beg; a < end; ++a) {
         Arc<T> arc = ld_arc(arcs + a);
@@ -483,70 +628,105 @@ __device__ __forceinline__ T small_row(const Arc<T>* __restrict__ arcs, int beg,
     return m + log_(s);
 }
 
-template <typename T, int SR> __global__ void small_fb_kernel(SmallParams<T> p) {
+// block-wide maximum of per-thread keys through a parity-double-buffered shared array: the
+// value written in frame n is read by every thread at the start of frame n+1 (after the frame's
+// __syncthreads), so no extra barrier is needed.
+__device__ __forceinline__ void publish_key(int* s_keys, int parity, int key) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(0xffffffffu, key, o));
+    if ((threadIdx.x & 31) == 0) s_keys[parity * 32 + (threadIdx.x >> 5)] = key;
+}
+__device__ __forceinline__ int collect_key(const int* s_keys, int parity) {
+    int k = kKeyMin;
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int w = 0; w < nw; ++w) k = max(k, s_keys[parity * 32 + w]);
+    return k;
+}
+
+template <typename T, int SR> __global__ void __launch_bounds__(1024, 1) small_fb_kernel(SmallParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const UttDesc<T> u = p.utts[blockIdx.x];
     const int S = u.S;
     T* v0 = reinterpret_cast<T*>(smem_raw);
     T* v1 = v0 + S;
-    T* s_red = v1 + S;  // [32]
+    T* s_red = v1 + S;                               // [2][32] posterior mass per warp (frame parity)
+    int* s_keys = reinterpret_cast<int*>(s_red + 64);  // [2][32] maxima per warp (frame parity)
     const int b = u.b;
     const int L = p.seqlens ? p.seqlens[b] : p.Tn;
-    const long long a_sn = p.alpha_user ? p.alpha_sn : S;
     T* A = p.alpha + (p.alpha_user ? u.out_off : u.ws_off);
+    const long long a_sn = p.alpha_user ? p.alpha_sn : S;
+    double* Ca = p.Ca + u.c_off;
+    double C = 0.0;  // every thread tracks the same running offset
 
     if (p.do_fwd) {
         for (int n = 0; n < p.N1; ++n) {
             const T* prev = (n & 1) ? v0 : v1;
             T* cur = (n & 1) ? v1 : v0;
+            const T sh = n > 0 ? shift_from_key<SR, T>(collect_key(s_keys, (n - 1) & 1)) : T(0);
+            C += double(sh);
+            if (threadIdx.x == 0) Ca[n] = C;
+            int key = kKeyMin;
             for (int s = threadIdx.x; s < S; s += blockDim.x) {
                 T e = emission<T>(p.ll, p.sb, p.sd, p.sn, p.D, p.expanded, L, b, u.pdf[s], n);
                 T acc = (n == 0) ? u.init_dense[s]
-                                 : small_row<T, SR>(u.in_arcs, u.in_ptr[s], u.in_ptr[s + 1], prev);
-                acc += e;
+                        : (e == neg_inf<T>()) ? e : small_row<T, SR>(u.in_arcs, u.in_ptr[s], u.in_ptr[s + 1], prev);
+                acc = acc + e - sh;
                 cur[s] = acc;
-                A[size_t(n) * a_sn + s] = acc;
+                key = max(key, fkey(float(acc)));
+                A[size_t(n) * a_sn + s] = p.alpha_user ? T(double(acc) + C) : acc;
             }
+            publish_key(s_keys, n & 1, key);
             __syncthreads();
         }
-        if (threadIdx.x == 0) p.lz[b] = A[size_t(p.N1 - 1) * a_sn + (S - 1)];
+    }
+    // log Z = a_{N̂}[phony final] + Ca   (all threads; also orders the α store for the sweep below)
+    double lz = 0.0;
+    if (p.do_fwd) {
+        const T a = ((p.N1 - 1) & 1 ? v1 : v0)[S - 1];
+        lz = (a == neg_inf<T>()) ? double(a) : double(a) + C;
+        if (threadIdx.x == 0) p.lz[b] = T(lz);
     }
     if (!p.do_bwd) return;
-    __syncthreads();  // make A (global, written by this CTA) visible to the whole CTA
+    __syncthreads();
 
-    T lzv = T(0);
-    if (p.do_post) {
-        lzv = A[size_t(p.N1 - 1) * a_sn + (S - 1)];
-        if (lzv == neg_inf<T>()) lzv = T(0);
-    }
     T* Bo = p.beta_out ? p.beta_out + u.out_off : nullptr;
+    C = 0.0;  // now Cb
     for (int n = p.N1 - 1; n >= 0; --n) {
-        const T* nxt = (n & 1) ? v0 : v1;  // β_{n+1} ⊗ e_{n+1}
+        const T* nxt = (n & 1) ? v0 : v1;  // b_{n+1} ⊗ e_{n+1}
         T* cur = (n & 1) ? v1 : v0;
+        const T sh = n < p.N1 - 1 ? shift_from_key<SR, T>(collect_key(s_keys, (n + 1) & 1)) : T(0);
+        C += double(sh);
+        T g = T(0);
+        if (p.do_post && lz != double(neg_inf<T>())) g = T(Ca[n] + C - lz);
         T zs = T(0);
+        int key = kKeyMin;
         for (int i = threadIdx.x; i < S; i += blockDim.x) {
             const int pdf = u.pdf[i];
-            T e = (n > 0) ? emission<T>(p.ll, p.sb, p.sd, p.sn, p.D, p.expanded, L, b, pdf, n) : T(0);
+            T e = emission<T>(p.ll, p.sb, p.sd, p.sn, p.D, p.expanded, L, b, pdf, n);
+            const bool dead = !Bo && e == neg_inf<T>();
             T beta = (n == p.N1 - 1) ? T(0)
-                                     : small_row<T, SR>(u.out_arcs, u.out_ptr[i], u.out_ptr[i + 1], nxt);
-            if (Bo) Bo[size_t(n) * p.beta_sn + i] = beta;
-            if (p.do_post) {
-                T pg = exp_(A[size_t(n) * a_sn + i] + beta - lzv);
+                     : dead ? neg_inf<T>()
+                            : small_row<T, SR>(u.out_arcs, u.out_ptr[i], u.out_ptr[i + 1], nxt) - sh;
+            if (Bo) Bo[size_t(n) * p.beta_sn + i] = T(double(beta) + C);
+            if (p.do_post && !dead) {
+                T pg = exp_(A[size_t(n) * a_sn + i] + beta + g);
                 zs = lin_add<SR>(zs, pg);
-                if (n < p.Tn && pdf < p.D && pg > T(0))
-                    red1<SR>(p.post + (size_t(n) * p.D + pdf) * p.B + b, pg);
+                if (n < p.Tn && pdf < p.D && pg > T(0)) red1<SR>(p.post + (size_t(n) * p.D + pdf) * p.B + b, pg);
             }
-            cur[i] = beta + e;
+            beta += e;
+            cur[i] = beta;
+            key = max(key, fkey(float(beta)));
         }
+        publish_key(s_keys, n & 1, key);
         if (p.do_post) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) zs = lin_add<SR>(zs, __shfl_xor_sync(0xffffffffu, zs, o));
-            if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = zs;
+            if ((threadIdx.x & 31) == 0) s_red[(n & 1) * 32 + (threadIdx.x >> 5)] = zs;
         }
         __syncthreads();
         if (p.do_post && threadIdx.x == 0) {
             T z = T(0);
-            for (int w = 0; w < (blockDim.x + 31) / 32; ++w) z = lin_add<SR>(z, s_red[w]);
+            for (int w = 0; w < (blockDim.x + 31) / 32; ++w) z = lin_add<SR>(z, s_red[(n & 1) * 32 + w]);
             p.zsum[size_t(n) * p.B + b] = z;
         }
     }
@@ -580,12 +760,14 @@ template <typename T> __global__ void total_kernel(const T* zsum, const T* lz, T
 
 // ================================================================================================
 // Layout conversion for the αrecursion / βrecursion entry points:
-//   src [N1][S][U4] (shared-graph layout) -> dst[(off_b + s) + total*n]  (reference layout)
+//   src [N1][S][U4] (shared-graph layout, normalised) + C[n][u] -> dst[(off_b + s) + total*n]
+//   (reference layout, un-normalised)
 // grid (ceil(S/32), ceil(U4/32), N1), block (32, 8)
 // ================================================================================================
 template <typename T>
 __global__ void unpack_states_kernel(const T* src, int S, int U4, const int* utt_b,
-                                     const long long* utt_off, T* dst, long long total) {
+                                     const long long* utt_off, const double* C /* [N1][U4] */, T* dst,
+                                     long long total) {
     __shared__ T tile[32][33];
     const int n = blockIdx.z, s0 = blockIdx.x * 32, u0 = blockIdx.y * 32;
     for (int k = threadIdx.y; k < 32; k += 8) {
@@ -595,7 +777,8 @@ __global__ void unpack_states_kernel(const T* src, int S, int U4, const int* utt
     __syncthreads();
     for (int k = threadIdx.y; k < 32; k += 8) {
         int u = u0 + k, s = s0 + threadIdx.x;
-        if (s < S && u < U4 && utt_b[u] >= 0) dst[utt_off[u] + s + total * n] = tile[threadIdx.x][k];
+        if (s < S && u < U4 && utt_b[u] >= 0)
+            dst[utt_off[u] + s + total * n] = T(double(tile[threadIdx.x][k]) + C[size_t(n) * U4 + u]);
     }
 }
 

@@ -101,15 +101,69 @@ struct mk_graph {
     int64_t S = 0, nnz = 0, Dh = 0;
     int max_in_deg = 0, max_out_deg = 0;
     int *d_in_ptr = nullptr, *d_out_ptr = nullptr, *d_pdf = nullptr;
-    int *d_fwd_rows = nullptr, *d_bwd_rows = nullptr;
-    void *d_in_arcs = nullptr, *d_out_arcs = nullptr, *d_init_dense = nullptr;
+    int *d_fwd_warp_items = nullptr, *d_bwd_rows = nullptr;
+    int4 *d_fwd_items = nullptr, *d_fwd_long = nullptr;
+    void *d_in_arcs = nullptr, *d_out_arcs = nullptr, *d_init_dense = nullptr, *d_fwd_long_arcs = nullptr;
+    int n_long = 0, n_slots = 0;
     size_t bytes = 0;
     ~mk_graph() {
         cudaFree(d_in_ptr); cudaFree(d_out_ptr); cudaFree(d_pdf);
-        cudaFree(d_fwd_rows); cudaFree(d_bwd_rows);
-        cudaFree(d_in_arcs); cudaFree(d_out_arcs); cudaFree(d_init_dense);
+        cudaFree(d_fwd_warp_items); cudaFree(d_bwd_rows); cudaFree(d_fwd_items); cudaFree(d_fwd_long);
+        cudaFree(d_in_arcs); cudaFree(d_out_arcs); cudaFree(d_init_dense); cudaFree(d_fwd_long_arcs);
     }
 };
+
+// Forward work items.  Rows with more than kLongRow in-arcs (typically the phony final state:
+// one in-arc per final state) are cut into segments that spread over all warps; each segment
+// writes a partial ⊕ into a scratch slot and every CTA combines the slots at the start of the
+// next frame (kernels.cuh, fwd_combine).  Segment length keeps the slot count per row <= 48 so
+// that the (per-CTA, serial) combine stays short.
+constexpr int kLongRow = 128;
+constexpr int kMinSegment = 64;
+constexpr int kMaxSlotsPerRow = 48;
+
+template <typename T>
+static void build_fwd_items(const std::vector<int>& in_ptr, int S, int n_warps, std::vector<int4>& items,
+                            std::vector<int>& warp_items, std::vector<int4>& long_rows,
+                            std::vector<Arc<T>>& long_arcs, int& n_slots) {
+    n_slots = 0;
+    for (int r = 0; r < S; ++r) {
+        const int beg = in_ptr[r], end = in_ptr[r + 1], deg = end - beg;
+        if (deg <= kLongRow) {
+            items.push_back(make_int4(r, beg, end, -1));
+            continue;
+        }
+        const int seg = std::max(kMinSegment, (deg + kMaxSlotsPerRow - 1) / kMaxSlotsPerRow);
+        const int pseudo_beg = int(long_arcs.size());
+        for (int a = beg; a < end; a += seg) {
+            items.push_back(make_int4(r, a, std::min(end, a + seg), n_slots));
+            Arc<T> pa;
+            std::memset(&pa, 0, sizeof pa);
+            pa.idx = n_slots++;
+            pa.w = T(0);  // 1̄
+            long_arcs.push_back(pa);
+        }
+        long_rows.push_back(make_int4(r, pseudo_beg, int(long_arcs.size()), 0));
+    }
+    // contiguous item ranges per warp, balanced by (arcs + 2) per item
+    const int n_items = int(items.size());
+    double total = 0;
+    for (const int4& it : items) total += double(it.z - it.y) + 2.0;
+    warp_items.assign(n_warps + 1, n_items);
+    warp_items[0] = 0;
+    double acc = 0;
+    int i = 0;
+    for (int k = 1; k < n_warps; ++k) {
+        const double target = total * k / n_warps;
+        while (i < n_items) {
+            double c = double(items[i].z - items[i].y) + 2.0;
+            if (acc + 0.5 * c > target) break;
+            acc += c;
+            ++i;
+        }
+        warp_items[k] = i;
+    }
+}
 
 // contiguous row ranges per warp, balanced by (arcs + 2) per row
 static std::vector<int> partition_rows(const std::vector<int>& ptr, int S, int n_warps) {
@@ -199,7 +253,11 @@ static int build_graph(mk_graph* g, const int64_t* colptr, const int64_t* rowval
         init[s] = init_w[k];
     }
     const int n_warps = g->n_sms * kSharedWarps;
-    std::vector<int> fwd = partition_rows(in_ptr, S, n_warps), bwd = partition_rows(out_ptr, S, n_warps);
+    std::vector<int> bwd = partition_rows(out_ptr, S, n_warps), fwd_warp_items;
+    std::vector<int4> fwd_items, fwd_long;
+    std::vector<Arc<T>> fwd_long_arcs;
+    build_fwd_items<T>(in_ptr, S, n_warps, fwd_items, fwd_warp_items, fwd_long, fwd_long_arcs, g->n_slots);
+    g->n_long = int(fwd_long.size());
 
     TRY(upload(in_ptr, (void**)&g->d_in_ptr));
     TRY(upload(out_ptr, (void**)&g->d_out_ptr));
@@ -207,7 +265,10 @@ static int build_graph(mk_graph* g, const int64_t* colptr, const int64_t* rowval
     TRY(upload(out_arcs, &g->d_out_arcs));
     TRY(upload(pdf, (void**)&g->d_pdf));
     TRY(upload(init, &g->d_init_dense));
-    TRY(upload(fwd, (void**)&g->d_fwd_rows));
+    TRY(upload(fwd_items, (void**)&g->d_fwd_items));
+    TRY(upload(fwd_warp_items, (void**)&g->d_fwd_warp_items));
+    TRY(upload(fwd_long, (void**)&g->d_fwd_long));
+    TRY(upload(fwd_long_arcs, &g->d_fwd_long_arcs));
     TRY(upload(bwd, (void**)&g->d_bwd_rows));
     g->bytes = 2 * (S + 1) * sizeof(int) + 2 * nnz * sizeof(Arc<T>) + S * (sizeof(int) + sizeof(T)) +
                2 * (n_warps + 1) * sizeof(int);
@@ -224,7 +285,7 @@ struct Group {  // utterances sharing one graph, run by shared_fb_kernel
     bool vec4 = false;
     int* d_utt_b = nullptr;
     long long* d_utt_off = nullptr;
-    DevBuf E, alpha, bt;
+    DevBuf E, alpha, bt, part, gkey, coff;
 };
 
 struct mk_batch {
@@ -237,36 +298,40 @@ struct mk_batch {
     std::vector<int> small;  // utterances run by small_fb_kernel
     int small_smax = 0;
     int64_t small_cached_n1 = -1;
-    DevBuf small_descs, small_alpha, zsum, lz, seqlens, barrier, trace, h_ll, h_post, h_logz, h_path;
+    DevBuf small_descs, small_alpha, small_ca, zsum, lz, seqlens, barrier, trace, h_ll, h_post, h_logz, h_path;
     cudaStream_t own_stream = nullptr;
     size_t max_smem_optin = 0;
     // optional timing of the dominant kernel (bench.py roofline): events around the last
     // shared_fb_kernel launch, on the stream it was launched on
+    static constexpr int kProfRing = 64;
     bool profile = false;
-    bool prof_valid = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int prof_n = 0;  // launches recorded since profiling was (re)enabled
+    cudaEvent_t ev0[kProfRing] = {}, ev1[kProfRing] = {};
     ~mk_batch() {
         for (auto& gr : groups) {
             cudaFree(gr.d_utt_b); cudaFree(gr.d_utt_off);
             gr.E.release(); gr.alpha.release(); gr.bt.release();
+            gr.part.release(); gr.gkey.release(); gr.coff.release();
         }
-        DevBuf* all[] = {&small_descs, &small_alpha, &zsum, &lz, &seqlens, &barrier, &trace,
+        DevBuf* all[] = {&small_descs, &small_alpha, &small_ca, &zsum, &lz, &seqlens, &barrier, &trace,
                          &h_ll, &h_post, &h_logz, &h_path};
         for (DevBuf* d : all) d->release();
         if (own_stream) cudaStreamDestroy(own_stream);
-        if (ev0) cudaEventDestroy(ev0);
-        if (ev1) cudaEventDestroy(ev1);
+        for (int i = 0; i < kProfRing; ++i) {
+            if (ev0[i]) cudaEventDestroy(ev0[i]);
+            if (ev1[i]) cudaEventDestroy(ev1[i]);
+        }
     }
     size_t ws_bytes() const {
-        size_t t = small_descs.cap + small_alpha.cap + zsum.cap + lz.cap + seqlens.cap + barrier.cap +
+        size_t t = small_descs.cap + small_alpha.cap + small_ca.cap + zsum.cap + lz.cap + seqlens.cap + barrier.cap +
                    trace.cap + h_ll.cap + h_post.cap + h_logz.cap + h_path.cap;
-        for (auto& gr : groups) t += gr.E.cap + gr.alpha.cap + gr.bt.cap;
+        for (auto& gr : groups) t += gr.E.cap + gr.alpha.cap + gr.bt.cap + gr.part.cap + gr.gkey.cap + gr.coff.cap;
         return t;
     }
 };
 
 static size_t tsize(int dtype) { return dtype == MK_F32 ? 4 : 8; }
-static size_t small_smem_bytes(int S, int dtype) { return (2 * size_t(S) + 32) * tsize(dtype); }
+static size_t small_smem_bytes(int S, int dtype) { return (2 * size_t(S) + 64) * tsize(dtype) + 64 * sizeof(int); }
 
 // ------------------------------------------------------------------------------------------------
 // run
@@ -290,6 +355,9 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     TRY(gr.E.ensure(size_t(N1) * Dh * U4 * sizeof(T)));
     TRY(gr.alpha.ensure(size_t(N1) * frame));
     if (mode == MODE_POST || mode == MODE_BETA) TRY(gr.bt.ensure(2 * frame));
+    TRY(gr.part.ensure(2 * size_t(std::max(g->n_slots, 1)) * U4 * sizeof(T)));
+    TRY(gr.gkey.ensure(2 * size_t(N1) * U4 * sizeof(int)));
+    TRY(gr.coff.ensure(2 * size_t(N1) * U4 * sizeof(double)));
 
     EmisParams<T> ep;
     ep.ll = static_cast<const T*>(c.ll); ep.sb = c.sb; ep.sd = c.sd; ep.sn = c.sn;
@@ -302,10 +370,15 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
 
     SharedParams<T> p;
     p.S = S; p.Dh = Dh; p.N1 = N1; p.U4 = U4; p.ntiles = (U4 + kTileUtts - 1) / kTileUtts;
-    p.in_ptr = g->d_in_ptr; p.in_arcs = static_cast<const Arc<T>*>(g->d_in_arcs);
+    p.in_arcs = static_cast<const Arc<T>*>(g->d_in_arcs);
+    p.fwd_items = g->d_fwd_items; p.fwd_warp_items = g->d_fwd_warp_items;
+    p.n_long = g->n_long; p.fwd_long = g->d_fwd_long;
+    p.fwd_long_arcs = static_cast<const Arc<T>*>(g->d_fwd_long_arcs);
+    p.n_slots = g->n_slots; p.part = static_cast<T*>(gr.part.p);
     p.out_ptr = g->d_out_ptr; p.out_arcs = static_cast<const Arc<T>*>(g->d_out_arcs);
+    p.bwd_rows = g->d_bwd_rows;
     p.pdf = g->d_pdf; p.init_dense = static_cast<const T*>(g->d_init_dense);
-    p.fwd_rows = g->d_fwd_rows; p.bwd_rows = g->d_bwd_rows;
+    p.gkey = static_cast<int*>(gr.gkey.p); p.Coff = static_cast<double*>(gr.coff.p);
     p.E = static_cast<const T*>(gr.E.p);
     p.alpha = static_cast<T*>(gr.alpha.p);
     p.bt = static_cast<T*>(gr.bt.p);
@@ -326,17 +399,19 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     }
     CK(cudaMemsetAsync(bt->barrier.p, 0, sizeof(unsigned), c.stream));
     void* args[] = {&p};
-    size_t smem = 2 * size_t(U4) * sizeof(T);
+    size_t smem = size_t(U4) * (2 * sizeof(double) + 3 * sizeof(T) + sizeof(int));
     auto kern = shared_fb_kernel<T, SR>;
-    if (bt->profile) CK(cudaEventRecord(bt->ev0, c.stream));
+    const int slot = bt->prof_n % mk_batch::kProfRing;
+    if (bt->profile) CK(cudaEventRecord(bt->ev0[slot], c.stream));
     CK(cudaLaunchCooperativeKernel((void*)kern, dim3(g->n_sms), dim3(kSharedThreads), args, smem, c.stream));
     ++g_launches;
-    if (bt->profile) { CK(cudaEventRecord(bt->ev1, c.stream)); bt->prof_valid = true; }
+    if (bt->profile) { CK(cudaEventRecord(bt->ev1[slot], c.stream)); ++bt->prof_n; }
 
     if (mode == MODE_ALPHA || mode == MODE_BETA) {
         dim3 ug((S + 31) / 32, (U4 + 31) / 32, N1), ub(32, 8);
+        const double* C = static_cast<const double*>(gr.coff.p) + (mode == MODE_BETA ? size_t(N1) * U4 : 0);
         unpack_states_kernel<T><<<ug, ub, 0, c.stream>>>(static_cast<const T*>(gr.alpha.p), S, U4, gr.d_utt_b,
-                                                        gr.d_utt_off, static_cast<T*>(c.out0), bt->total);
+                                                        gr.d_utt_off, C, static_cast<T*>(c.out0), bt->total);
         CK(cudaGetLastError());
         ++g_launches;
     }
@@ -359,11 +434,12 @@ static int launch_small(mk_batch* bt, Mode mode, const CallArgs& c, int Dh, int 
             d.in_ptr = g->d_in_ptr; d.in_arcs = static_cast<const Arc<T>*>(g->d_in_arcs);
             d.out_ptr = g->d_out_ptr; d.out_arcs = static_cast<const Arc<T>*>(g->d_out_arcs);
             d.pdf = g->d_pdf; d.init_dense = static_cast<const T*>(g->d_init_dense);
-            d.S = int(g->S); d.b = b; d.ws_off = off; d.out_off = bt->off[b];
+            d.S = int(g->S); d.b = b; d.ws_off = off; d.out_off = bt->off[b]; d.c_off = (long long)k * N1;
             off += (long long)N1 * g->S;
         }
         TRY(bt->small_descs.ensure(n * sizeof(UttDesc<T>)));
         TRY(bt->small_alpha.ensure(size_t(off) * sizeof(T)));
+        TRY(bt->small_ca.ensure(size_t(n) * N1 * sizeof(double)));
         CK(cudaMemcpyAsync(bt->small_descs.p, descs.data(), n * sizeof(UttDesc<T>), cudaMemcpyHostToDevice,
                            c.stream));
         CK(cudaStreamSynchronize(c.stream));  // descs is a stack-lifetime host buffer
@@ -376,6 +452,7 @@ static int launch_small(mk_batch* bt, Mode mode, const CallArgs& c, int Dh, int 
     p.seqlens = d_seqlens;
     p.alpha = static_cast<T*>(bt->small_alpha.p); p.alpha_sn = 0; p.alpha_user = 0;
     p.beta_out = nullptr; p.beta_sn = 0;
+    p.Ca = static_cast<double*>(bt->small_ca.p);
     p.post = nullptr; p.B = int(bt->B);
     p.zsum = static_cast<T*>(bt->zsum.p); p.lz = static_cast<T*>(bt->lz.p);
     p.do_fwd = p.do_bwd = p.do_post = 0;
@@ -670,21 +747,27 @@ int64_t mk_batch_workspace_bytes(const mk_batch* b) { return b ? int64_t(b->ws_b
 int mk_batch_profile(mk_batch* b, int enable) {
     if (!b) return fail(MK_EINVAL, "null batch");
     DeviceGuard guard(b->device);
-    if (enable && !b->ev0) {
-        CK(cudaEventCreate(&b->ev0));
-        CK(cudaEventCreate(&b->ev1));
-    }
+    if (enable && !b->ev0[0])
+        for (int i = 0; i < mk_batch::kProfRing; ++i) {
+            CK(cudaEventCreate(&b->ev0[i]));
+            CK(cudaEventCreate(&b->ev1[i]));
+        }
     b->profile = enable != 0;
-    b->prof_valid = false;
+    b->prof_n = 0;
     return MK_OK;
 }
 
-int mk_batch_last_kernel_ms(mk_batch* b, float* ms) {
-    if (!b || !ms) return fail(MK_EINVAL, "null argument");
-    if (!b->prof_valid) return fail(MK_EINVAL, "no profiled launch recorded");
+int mk_batch_kernel_ms(mk_batch* b, float* ms, int cap, int* n) {
+    if (!b || !ms || !n) return fail(MK_EINVAL, "null argument");
     DeviceGuard guard(b->device);
-    CK(cudaEventSynchronize(b->ev1));
-    CK(cudaEventElapsedTime(ms, b->ev0, b->ev1));
+    int have = std::min(b->prof_n, int(mk_batch::kProfRing));
+    int cnt = std::min(have, cap);
+    for (int k = 0; k < cnt; ++k) {  // the most recent `cnt` launches, oldest first
+        int slot = (b->prof_n - cnt + k) % mk_batch::kProfRing;
+        CK(cudaEventSynchronize(b->ev1[slot]));
+        CK(cudaEventElapsedTime(&ms[k], b->ev0[slot], b->ev1[slot]));
+    }
+    *n = cnt;
     return MK_OK;
 }
 

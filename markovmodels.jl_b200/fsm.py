@@ -115,6 +115,12 @@ class FSM:
                               [((a, b), K(c)) for a, b, c in data["arcs"]],
                               [(a, K(b)) for a, b in data["finalstates"]], list(data["labels"]))
 
+    def astype(self, K):
+        """The same graph with another semiring type / payload precision (``convert`` in the
+        reference's tests, test/test_algorithms.jl:277)."""
+        return FSM(K, self.nstates_hat, self.init_idx, self.init_w.astype(K.dtype), self.colptr, self.rowval,
+                   self.nzval.astype(K.dtype), self.labels)
+
     # ---- views (src/fsm.jl:30-40) --------------------------------------------------------------
     @property
     def nstates(self):

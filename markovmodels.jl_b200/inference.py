@@ -158,10 +158,12 @@ class BatchedFSM:
     def profile(self, enable=True):
         _lib.check(_lib.lib().mk_batch_profile(self._h, int(enable)))
 
-    def last_kernel_ms(self):
-        ms = C.c_float()
-        _lib.check(_lib.lib().mk_batch_last_kernel_ms(self._h, C.byref(ms)))
-        return ms.value
+    def kernel_ms(self, cap=64):
+        """Durations (ms) of the most recent shared-graph kernel launches, oldest first."""
+        ms = (C.c_float * cap)()
+        n = C.c_int()
+        _lib.check(_lib.lib().mk_batch_kernel_ms(self._h, ms, cap, C.byref(n)))
+        return list(ms[:n.value])
 
     def __del__(self):
         h = getattr(self, "_h", None)

@@ -1,0 +1,115 @@
+# SPDX-License-Identifier: MIT
+#
+# MarkovModelsB200.jl — the reference-side binding of libmarkov_b200.so: the methods a
+# MarkovModels.jl maintainer adds so that `compile` / `batch` / `αrecursion` / `βrecursion` /
+# `pdfposteriors` / `bestpath` run in the B200 library instead of the CUDA.jl kernels of
+# src/linalg.jl.  NOT RUNNABLE IN THIS IMAGE (no julia binary, SURVEY.md G4): it documents the
+# ccall layer; the same entry points are exercised through ctypes by tests/ and bench.py.
+#
+# Memory facts used (SURVEY.md A.4): Matrix{LogSemiring{Float32}} is bit-identical to
+# Matrix{Float32}; the CPU FSM stores T̂ as SparseMatrixCSC{K,Int64} (colptr/rowval/nzval,
+# 1-based) and α̂ as SparseVector{K,Int64} — passed as they are with index_base = 1.
+module MarkovModelsB200
+
+using CUDA, SparseArrays, Semirings
+import MarkovModels: FSM, nstates
+
+const LIB = "libmarkov_b200"
+
+semiring_code(::Type{<:LogSemiring}) = Cint(0)
+semiring_code(::Type{<:TropicalSemiring}) = Cint(1)
+dtype_code(::Type{Float32}) = Cint(0)
+dtype_code(::Type{Float64}) = Cint(1)
+payload(::Type{<:Semiring{T}}) where T = T   # val(x)::T
+
+function check(rc::Cint)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:mk_last_error, LIB), Cstring, ()))
+    rc == 22 ? throw(DimensionMismatch(msg)) : error("libmarkov_b200 error $rc: $msg")
+end
+
+# CompiledFSM{K} (src/inference.jl:3-12) -> an opaque mk_graph handle on the current device
+mutable struct B200CompiledFSM{K}
+    handle::Ptr{Cvoid}
+    nstates_hat::Int
+    npdf_hat::Int
+end
+
+# compile(fsm, Ĉ): Ĉ has one 1̄ per row (examples/prepare-lfmmi-graphs.jl:15-23)
+function compile(fsm::FSM{K}, Ĉ::AbstractSparseMatrix{K}) where K
+    T = payload(K)
+    state2pdf = Cint[findnz(Ĉ[s, :])[1][1] for s in 1:size(Ĉ, 1)]
+    T̂, α̂ = fsm.T̂, fsm.α̂
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:mk_graph_create, LIB), Cint,
+                (Ref{Ptr{Cvoid}}, Cint, Cint, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Cvoid},
+                 Int64, Ptr{Int64}, Ptr{Cvoid}, Ptr{Cint}, Int64, Cint, Cint),
+                h, semiring_code(K), dtype_code(T), size(T̂, 1), nnz(T̂),
+                T̂.colptr, T̂.rowval, reinterpret(T, T̂.nzval),
+                nnz(α̂), α̂.nzind, reinterpret(T, α̂.nzval), state2pdf, size(Ĉ, 2), 1, -1))
+    c = B200CompiledFSM{K}(h[], size(T̂, 1), size(Ĉ, 2))
+    finalizer(x -> ccall((:mk_graph_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle), c)
+end
+
+# batch(fsm1, fsms...) (src/inference.jl:28-36): a descriptor, no blockdiag
+mutable struct B200Batch{K}
+    handle::Ptr{Cvoid}
+    fsms::Vector{B200CompiledFSM{K}}   # keeps the graphs alive
+end
+function batch(fsm1::B200CompiledFSM{K}, fsms::B200CompiledFSM{K}...) where K
+    all = [fsm1, fsms...]
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:mk_batch_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Int64),
+                h, [f.handle for f in all], length(all)))
+    b = B200Batch{K}(h[], all)
+    finalizer(x -> ccall((:mk_batch_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle), b)
+end
+
+# pdfposteriors(cfsm, V̂s) (src/inference.jl:164-180): V̂s are the expanded D̂ x N̂ CuMatrix{K};
+# vcat'ed exactly like :146 so that element (b, d, n) sits at b*D̂ + d + n*B*D̂.
+function pdfposteriors(b::B200Batch{K}, V̂s::Vector{<:CuMatrix{K}}) where K
+    T = payload(K)
+    V̂ = vcat(V̂s...)
+    B, D̂, N̂ = length(V̂s), size(V̂s[1], 1), size(V̂s[1], 2)
+    post = CUDA.zeros(T, B, D̂ - 1, N̂ - 1)
+    ttl = CUDA.zeros(T, B)
+    check(ccall((:mk_pdfposteriors, LIB), Cint,
+                (Ptr{Cvoid}, CuPtr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Cint, Ptr{Cint},
+                 CuPtr{Cvoid}, CuPtr{Cvoid}, Ptr{Cvoid}),
+                b.handle, pointer(V̂), D̂, 1, B * D̂, D̂, N̂, 1, C_NULL,
+                pointer(post), pointer(ttl), CUDA.stream().handle))
+    post, ttl
+end
+
+# αrecursion / βrecursion (src/inference.jl:62-74, 99-110): (ΣŜ) x N̂ CuMatrix{K}
+for (fn, sym) in ((:αrecursion, :mk_alpha), (:βrecursion, :mk_beta))
+    @eval function $fn(b::B200Batch{K}, V̂s::Vector{<:CuMatrix{K}}) where K
+        T = payload(K)
+        V̂ = vcat(V̂s...)
+        B, D̂, N̂ = length(V̂s), size(V̂s[1], 1), size(V̂s[1], 2)
+        total = sum(f.nstates_hat for f in b.fsms)
+        out = CuArray{K}(undef, total, N̂)
+        check(ccall(($(QuoteNode(sym)), LIB), Cint,
+                    (Ptr{Cvoid}, CuPtr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Cint, Ptr{Cint},
+                     CuPtr{Cvoid}, Ptr{Cvoid}),
+                    b.handle, pointer(V̂), D̂, 1, B * D̂, D̂, N̂, 1, C_NULL,
+                    pointer(out), CUDA.stream().handle))
+        out
+    end
+end
+
+# bestpath(cfsm, lhs) (historical signature, examples/demo.ipynb cell 23): un-expanded D x N
+# likelihoods for every utterance, (B, D, N) CuArray, plus sequence lengths
+function bestpath(b::B200Batch{K}, lhs::CuArray{T,3}, seqlengths::Vector{<:Integer}) where {K<:TropicalSemiring,T}
+    B, D, N = size(lhs)
+    path = CUDA.zeros(Cint, N, B)   # column-major (N, B) == the ABI's [B][T]
+    score = CUDA.zeros(T, B)
+    check(ccall((:mk_bestpath, LIB), Cint,
+                (Ptr{Cvoid}, CuPtr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Cint, Ptr{Cint},
+                 CuPtr{Cint}, CuPtr{Cvoid}, Ptr{Cvoid}),
+                b.handle, pointer(lhs), 1, B, B * D, D, N, 0, Cint.(seqlengths),
+                pointer(path), pointer(score), CUDA.stream().handle))
+    permutedims(path), score
+end
+
+end # module

@@ -74,6 +74,34 @@ def dev(torch, V_btd):
     return torch.from_numpy(np.ascontiguousarray(V_btd)).cuda().permute(0, 2, 1)
 
 
+def check_posteriors(mm, orc, graphs, D, V, lens, post, ttl, dtype):
+    """The parity bar.  Float64: 1e-9 against the oracle.  Float32: the oracle evaluated in Float32
+    (the reference's arithmetic) carries its own rounding error — ulp(|α|) per ⊕, |α| growing with
+    the frame index — so two correct Float32 evaluations cannot agree to 1e-4 on long sequences.
+    The CUDA path must (i) match the exact answer (the Float64 oracle on the same Float32 inputs)
+    within 1e-4 relative, and (ii) be no further from the Float32 oracle than twice that
+    oracle's own distance from the exact answer."""
+    post, ttl = np.asarray(post.cpu() if hasattr(post, "cpu") else post), np.asarray(ttl.cpu() if hasattr(ttl, "cpu") else ttl)
+    opost, ottl = orc.pdfposteriors(orc_graphs(orc, graphs, D), V, lens)
+    if dtype == np.float64:
+        np.testing.assert_allclose(ttl, ottl, rtol=1e-9)
+        np.testing.assert_allclose(post, opost, **TOL[dtype])
+        return
+    K64 = (mm.LogSemiring if graphs[0][0].K.code == 0 else mm.TropicalSemiring)[np.float64]
+    cache = {}
+    g64 = []
+    for f, p in graphs:
+        if id(f) not in cache:
+            cache[id(f)] = (f.astype(K64), p)
+        g64.append(cache[id(f)])
+    xpost, xttl = orc.pdfposteriors(orc_graphs(orc, g64, D), V.astype(np.float64), lens)
+    np.testing.assert_allclose(ttl, xttl, rtol=1e-4)
+    np.testing.assert_allclose(ttl, ottl, rtol=1e-4)
+    np.testing.assert_allclose(post, xpost, **TOL[dtype])                       # (i)
+    ref_err = np.abs(opost - xpost).max()
+    assert np.abs(post - opost).max() <= 2 * ref_err + 1e-6, (np.abs(post - opost).max(), ref_err)  # (ii)
+
+
 def assert_states_close(got, want, dtype):
     got, want = np.asarray(got), np.asarray(want)
     inf_w = np.isneginf(want)
@@ -169,10 +197,8 @@ def test_numerator_batch_vs_oracle(torch, mm, orc, dtype):
     lens[0] = T
     b = gpu_batch(mm, graphs, D)
     post, ttl = mm.pdfposteriors(b, dev(torch, V), seqlengths=lens)
-    opost, ottl = orc.pdfposteriors(orc_graphs(orc, graphs, D), V, lens)
-    assert np.isfinite(ottl).all()
-    np.testing.assert_allclose(ttl.cpu().numpy(), ottl, rtol=TOL[dtype]["rtol"])
-    np.testing.assert_allclose(post.cpu().numpy(), opost, **TOL[dtype])
+    assert bool(torch.isfinite(ttl).all())
+    check_posteriors(mm, orc, graphs, D, V, lens, post, ttl, dtype)
     for k in range(B):
         assert np.all(post[k, :, int(lens[k]):].cpu().numpy() == 0.0)
 
@@ -189,9 +215,7 @@ def test_denominator_vs_oracle(torch, mm, orc, dtype, force):
     lens = rng.integers(T // 2, T + 1, B).astype(np.int32)
     b = gpu_batch(mm, [g] * B, D, force)
     post, ttl = mm.pdfposteriors(b, dev(torch, V), seqlengths=lens)
-    opost, ottl = orc.pdfposteriors(orc_graphs(orc, [g] * B, D), V, lens)
-    np.testing.assert_allclose(ttl.cpu().numpy(), ottl, rtol=TOL[dtype]["rtol"])
-    np.testing.assert_allclose(post.cpu().numpy(), opost, **TOL[dtype])
+    check_posteriors(mm, orc, [g] * B, D, V, lens, post, ttl, dtype)
 
 
 def test_mixed_batch_vs_oracle(torch, mm, orc):
@@ -212,9 +236,7 @@ def test_mixed_batch_vs_oracle(torch, mm, orc):
     lens = rng.integers(T // 2, T + 1, B).astype(np.int32)
     b = gpu_batch(mm, graphs, D)
     post, ttl = mm.pdfposteriors(b, dev(torch, V), seqlengths=lens)
-    opost, ottl = orc.pdfposteriors(orc_graphs(orc, graphs, D), V, lens)
-    np.testing.assert_allclose(ttl.cpu().numpy(), ottl, rtol=1e-4)
-    np.testing.assert_allclose(post.cpu().numpy(), opost, **TOL[np.float32])
+    check_posteriors(mm, orc, graphs, D, V, lens, post, ttl, np.float32)
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
@@ -306,10 +328,8 @@ def test_expanded_inputs_and_reference_call_shape(torch, mm, orc):
     Vhats = [torch.from_numpy(mm.expand(V[k].T, lens[k])).cuda() for k in range(3)]
     Cs = [mm.statemap(f, D, p) for f, p in fsms]
     post, ttl = mm.pdfposteriors(mm.rawunion(*[f for f, _ in fsms]), Vhats, Cs)
-    opost, ottl = orc.pdfposteriors(orc_graphs(orc, fsms, D), V, lens)
     assert tuple(post.shape) == (3, D, T)
-    np.testing.assert_allclose(ttl.cpu().numpy(), ottl, rtol=1e-4)
-    np.testing.assert_allclose(post.cpu().numpy(), opost, **TOL[np.float32])
+    check_posteriors(mm, orc, fsms, D, V, lens, post, ttl, np.float32)
 
 
 def test_host_buffer_entry_point(torch, mm, orc):
@@ -322,9 +342,7 @@ def test_host_buffer_entry_point(torch, mm, orc):
     b = gpu_batch(mm, [g] * B, D)
     post, ttl = mm.pdfposteriors(b, V.transpose(0, 2, 1))
     assert isinstance(post, np.ndarray)
-    opost, ottl = orc.pdfposteriors(orc_graphs(orc, [g] * B, D), V)
-    np.testing.assert_allclose(ttl, ottl, rtol=1e-4)
-    np.testing.assert_allclose(post, opost, **TOL[np.float32])
+    check_posteriors(mm, orc, [g] * B, D, V, None, post, ttl, np.float32)
     Kt = mm.TropicalSemiring[np.float32]
     gt = mm.graphs.denominator(Kt, n_tokens=1100, n_pdf=D, seed=2)
     path, score = mm.bestpath(gpu_batch(mm, [gt] * B, D), V.transpose(0, 2, 1))
@@ -377,9 +395,7 @@ def test_cfg3_full_size_properties(torch, mm, orc):
     # sampled oracle comparison: 3 utterances of the 128
     idx = [0, 77, 127]
     Vh = V[idx].cpu().numpy()
-    opost, ottl = orc.pdfposteriors(orc_graphs(orc, [g] * len(idx), D), Vh)
-    np.testing.assert_allclose(ttl[idx].cpu().numpy(), ottl, rtol=1e-4)
-    np.testing.assert_allclose(post[idx].cpu().numpy(), opost, **TOL[np.float32])
+    check_posteriors(mm, orc, [g] * len(idx), D, Vh, None, post[idx], ttl[idx], np.float32)
 
 
 def test_cfg5_bestpath_full_graph(torch, mm, orc):
@@ -394,8 +410,6 @@ def test_cfg5_bestpath_full_graph(torch, mm, orc):
     b = gpu_batch(mm, [g] * B, D)
     path, score = mm.bestpath(b, dev(torch, V))
     path, score = path.cpu().numpy(), score.cpu().numpy()
-    Tm = fsm.T if fsm.nstates <= 4000 else None
-    assert Tm is None
     import scipy.sparse as sp
     src, dst, w = fsm.arcs_hat()
     M = sp.csr_matrix((w.astype(np.float64) + 1e3, (src, dst)), shape=(fsm.nstates_hat,) * 2)  # shift: keep zeros explicit
