@@ -67,6 +67,12 @@ __device__ __forceinline__ float exp_(float x) { return ex2_approx(x * 1.4426950
 __device__ __forceinline__ double exp_(double x) { return exp(x); }
 __device__ __forceinline__ float log_(float x) { return lg2_approx(x) * 0.6931471805599453f; }
 __device__ __forceinline__ double log_(double x) { return log(x); }
+// log2-domain variants: the shared-graph kernel stores its Log-semiring vectors in log2 units so that
+// ⊕ needs no multiply around ex2 / lg2
+__device__ __forceinline__ float ex2_(float x) { return ex2_approx(x); }
+__device__ __forceinline__ double ex2_(double x) { return exp2(x); }
+__device__ __forceinline__ float lg2_(float x) { return lg2_approx(x); }
+__device__ __forceinline__ double lg2_(double x) { return log2(x); }
 __device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
 
@@ -77,6 +83,16 @@ __device__ __forceinline__ Arc<float> ld_arc(const Arc<float>* p) {
 }
 __device__ __forceinline__ Arc<double> ld_arc(const Arc<double>* p) {
     int4 t = __ldg(reinterpret_cast<const int4*>(p));
+    Arc<double> a; a.idx = t.x; a.w = __hiloint2double(t.w, t.z); return a;
+}
+
+// generic-address variants: the shared-graph kernel keeps its arcs in shared memory when they fit
+__device__ __forceinline__ Arc<float> ld_arc_g(const Arc<float>* p) {
+    int2 t = *reinterpret_cast<const int2*>(p);
+    Arc<float> a; a.idx = t.x; a.w = __int_as_float(t.y); return a;
+}
+__device__ __forceinline__ Arc<double> ld_arc_g(const Arc<double>* p) {
+    int4 t = *reinterpret_cast<const int4*>(p);
     Arc<double> a; a.idx = t.x; a.w = __hiloint2double(t.w, t.z); return a;
 }
 
@@ -153,7 +169,7 @@ __device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& target) {
     __syncthreads();
 }
 
-// ---- per-lane ⊕ over one row's arcs for 4 utterances -------------------------------------------
+// ---- per-lane ⊕ over one row's arcs for 4 utterances (exact two-pass form, log2 units) -----------
 // One chunk of CNT arcs: gather CNT x 16 B, then fold into the running (m, s) pair (Log) or
 // into m (Tropical).
 template <typename T, int SR, int CNT>
@@ -177,9 +193,9 @@ __device__ __forceinline__ void chunk_fold(const Arc<T>* __restrict__ arcs, cons
         } else {
             T mn = first ? mc : max_(m[j], mc);
             T ms = (mn == neg_inf<T>()) ? T(0) : mn;
-            T acc = first ? T(0) : s[j] * exp_(m[j] - ms);
+            T acc = first ? T(0) : s[j] * ex2_(m[j] - ms);
 #pragma unroll
-            for (int k = 0; k < CNT; ++k) acc += exp_(x[k][j] - ms);
+            for (int k = 0; k < CNT; ++k) acc += ex2_(x[k][j] - ms);
             s[j] = acc;
             m[j] = mn;
         }
@@ -213,7 +229,7 @@ __device__ __forceinline__ V4<T> row_reduce(const Arc<T>* __restrict__ arcs, int
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         if (SR == SR_TROP) out.v[j] = m[j];
-        else out.v[j] = (s[j] > T(0)) ? m[j] + log_(s[j]) : neg_inf<T>();
+        else out.v[j] = (s[j] > T(0)) ? m[j] + lg2_(s[j]) : neg_inf<T>();
     }
     return out;
 }
@@ -235,37 +251,226 @@ template <typename T> __device__ __forceinline__ bool all_zero_bar(const V4<T>& 
     return e.v[0] == neg_inf<T>() && e.v[1] == neg_inf<T>() && e.v[2] == neg_inf<T>() && e.v[3] == neg_inf<T>();
 }
 
+// ---- work plan of one direction ---------------------------------------------------------------
+// Built by the host (markov_b200.cu, build_plan).  Items are rows (or segments of long forward
+// rows) in row order.  Their arcs are re-laid out chunk by chunk into PADDED arrays: every chunk
+// starts and ends on a multiple of four arcs (pads: weight 0̄), every item owns at least one arc
+// (an empty row gets one pad arc), and a per-quad flag byte marks the arcs that end an item — so
+// the streaming loop needs no per-arc bookkeeping beyond one flag test.
+template <typename T> struct DirPlan {
+    const int4* items;           // {row, pdf, slot or -1, 0}
+    const int2* item_arcs;       // {beg, end} in the un-padded arc array (exact fallback only)
+    const int4* chunks;          // {parc_begin, parc_end, item_begin, item_end}
+    const int* cta_chunks;       // [grid + 1]: CTA c pulls chunks [cta_chunks[c], cta_chunks[c+1])
+    const int* pidx;             // padded arcs: neighbour state
+    const T* pw;                 // padded arcs: (w - R) in kernel units, 0̄ on pads
+    const unsigned char* qflags; // per quad of padded arcs: bit k set = arc 4q+k ends an item
+    const Arc<T>* arcs;          // un-padded arcs (w - R, kernel units) for the exact fallback
+    T R;                         // bound on the ⊕ exponents (0 for Tropical)
+};
+
+// out-of-line: the rare exact path must not bloat (or take registers from) the streaming loop
+template <typename T, int SR>
+__device__ __noinline__ void row_reduce_slow(const Arc<T>* arcs, int beg, int end, const T* vec, int U4, int uoff,
+                                             T* out4) {
+    V4<T> r = row_reduce<T, SR>(arcs, beg, end, vec, U4, uoff);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out4[j] = r.v[j];
+}
+
+// single-pass ⊕ of an item's arcs, resolved to log2 Σ 2^(v + w) for 4 utterances.  acc is the
+// linear sum against the bound R (Log) or the running maximum (Tropical).  A sum that underflowed
+// for an utterance whose emission is alive is redone with the exact two-pass row_reduce (which
+// also recognises a genuinely dead row).
+template <typename T, int SR>
+__device__ __forceinline__ V4<T> resolve_sum(const V4<T>& acc, const V4<T>& e, bool need_all, const DirPlan<T>& pl,
+                                             int item, const T* vec, int U4, int uoff) {
+    V4<T> val;
+    if (SR == SR_TROP) return acc;
+    const T tiny = T(1e-30);
+    bool redo = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        val.v[j] = lg2_(acc.v[j]) + pl.R;  // acc == 0 -> -Inf
+        redo |= (acc.v[j] < tiny) && (need_all || e.v[j] != neg_inf<T>());
+    }
+    if (redo) {
+        const int2 ar = __ldg(pl.item_arcs + item);
+        if (ar.y > ar.x) {
+            T ex[4];
+            row_reduce_slow<T, SR>(pl.arcs, ar.x, ar.y, vec, U4, uoff, ex);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (acc.v[j] < tiny) val.v[j] = ex[j] + pl.R;
+        }
+    }
+    return val;
+}
+
+// ---- arc source: the CTA's shared-memory cache (SA) or the global padded arrays ---------------------
+// The cache holds, per padded arc, the row offset pre-multiplied (idx * U4/4, in units of one
+// lane's 4 utterances) and the weight; per quad the flag byte.
+constexpr int kQueue = 8;  // finished items per drain: two quads
+template <typename T, bool SA> struct ArcSrc {
+    const int* gidx; const T* gw; const unsigned char* gqf;  // global
+    unsigned soff, sw, sqf;  // shared addresses of (virtual) padded arc 0 / quad 0
+    int U4q;                 // U4 / 4
+    // row offsets of the quad's four arcs, in units of one lane's 4 utterances
+    __device__ __forceinline__ void offsets(int aq, unsigned (&off)[4]) const {
+        if (SA) {
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(off[0]), "=r"(off[1]), "=r"(off[2]), "=r"(off[3]) : "r"(soff + unsigned(aq) * 4u));
+        } else {
+            const int4 ix = __ldg(reinterpret_cast<const int4*>(gidx + aq));
+            off[0] = unsigned(ix.x) * U4q; off[1] = unsigned(ix.y) * U4q;
+            off[2] = unsigned(ix.z) * U4q; off[3] = unsigned(ix.w) * U4q;
+        }
+    }
+    __device__ __forceinline__ void weights(int aq, T (&w)[4], unsigned& flags) const;
+};
+__device__ __forceinline__ void lds_w4(unsigned a, float (&w)[4]) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w[0]), "=f"(w[1]), "=f"(w[2]), "=f"(w[3]) : "r"(a));
+}
+__device__ __forceinline__ void lds_w4(unsigned a, double (&w)[4]) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(w[0]), "=d"(w[1]) : "r"(a));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(w[2]), "=d"(w[3]) : "r"(a + 16u));
+}
+template <typename T, bool SA>
+__device__ __forceinline__ void ArcSrc<T, SA>::weights(int aq, T (&w)[4], unsigned& flags) const {
+    if (SA) {
+        lds_w4(sw + unsigned(aq) * unsigned(sizeof(T)), w);
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(flags) : "r"(sqf + (unsigned(aq) >> 2)));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[k] = __ldg(gw + aq + k);
+        flags = __ldg(gqf + (aq >> 2));
+    }
+}
+
+__device__ __forceinline__ void sts_row(unsigned saddr, const V4<float>& x) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(x.v[0]), "f"(x.v[1]), "f"(x.v[2]),
+                 "f"(x.v[3]) : "memory");
+}
+__device__ __forceinline__ void sts_row(unsigned saddr, const V4<double>& x) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(saddr), "d"(x.v[0]), "d"(x.v[1]) : "memory");
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(saddr + 16), "d"(x.v[2]), "d"(x.v[3]) : "memory");
+}
+__device__ __forceinline__ V4<float> lds_row(unsigned saddr, float) {
+    V4<float> r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "r"(saddr) : "memory");
+    return r;
+}
+__device__ __forceinline__ V4<double> lds_row(unsigned saddr, double) {
+    V4<double> r;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "r"(saddr) : "memory");
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.v[2]), "=d"(r.v[3]) : "r"(saddr + 16) : "memory");
+    return r;
+}
+
+// ---- streaming loop ----------------------------------------------------------------------------------
+// One chunk: quads of four gathers (one 16/32-byte load per lane and arc, 512 B per warp and arc),
+// double-buffered in registers.  Loads are issued a whole quad at a time and consumed a whole quad
+// at a time — the in-order scoreboards then overlap quad q+1's latency with quad q's arithmetic.
+// Per arc and utterance: one add, one ex2, one add.  A finished item's sum goes to a small
+// per-warp shared-memory queue (lane-private columns); the queue is drained after every two quads
+// by the single finalise site fin(item_index, acc).
+template <typename T> struct Quad {
+    V4<T> v[4];
+};
+template <typename T, bool SA>
+__device__ __forceinline__ void quad_issue(Quad<T>& q, const ArcSrc<T, SA>& src, int aq, const T* vec_lane) {
+    unsigned off[4];
+    src.offsets(aq, off);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q.v[k] = ld4_cg(vec_lane + size_t(off[k]) * 4);
+}
+// weights and flags are re-read at consume time (two shared-memory loads per quad) rather than held
+// in registers while the gathers are in flight
+template <typename T, int SR, bool SA>
+__device__ __forceinline__ void quad_consume(const Quad<T>& q, const ArcSrc<T, SA>& src, int aq, V4<T>& acc,
+                                             unsigned queue, int& npush) {
+    constexpr unsigned QSLOT = 128 * sizeof(T);
+    T w[4];
+    unsigned flags;
+    src.weights(aq, w, flags);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const T x = q.v[k].v[j] + w[k];
+            if (SR == SR_LOG) acc.v[j] += ex2_(x);
+            else acc.v[j] = max_(acc.v[j], x);
+        }
+        if (flags & (1u << k)) {  // this arc ends an item (warp-uniform)
+            sts_row(queue + unsigned(npush) * QSLOT, acc);
+            ++npush;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc.v[j] = SR == SR_LOG ? T(0) : neg_inf<T>();
+        }
+    }
+}
+
+template <typename T, int SR, bool SA, class Fin>
+__device__ __forceinline__ void stream_chunk(const ArcSrc<T, SA>& src, const int4 ch, const T* vec_lane,
+                                             unsigned queue, Fin& fin) {
+    constexpr unsigned QSLOT = 128 * sizeof(T);
+    const int nq = (ch.y - ch.x) >> 2;
+    int item = ch.z;
+    fin.prefetch(item);
+    Quad<T> A, B;
+    quad_issue<T, SA>(A, src, ch.x, vec_lane);
+    V4<T> acc;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc.v[j] = SR == SR_LOG ? T(0) : neg_inf<T>();
+    for (int q = 0; q < nq; q += 2) {
+        const int aq = ch.x + q * 4;
+        int npush = 0;
+        if (q + 1 < nq) quad_issue<T, SA>(B, src, aq + 4, vec_lane);
+        quad_consume<T, SR, SA>(A, src, aq, acc, queue, npush);
+        if (q + 2 < nq) quad_issue<T, SA>(A, src, aq + 8, vec_lane);
+        if (q + 1 < nq) quad_consume<T, SR, SA>(B, src, aq + 4, acc, queue, npush);
+        for (int k = 0; k < npush; ++k) {  // the only finalise site
+            const V4<T> r = lds_row(queue + unsigned(k) * QSLOT, T());
+            fin(item, r);
+            if (++item < ch.w) fin.prefetch(item);
+        }
+    }
+}
+
 // ================================================================================================
 // Shared-graph kernel
 // ================================================================================================
-// Forward work items: a full destination row, or one segment of a long row (in-degree above the
-// split threshold, e.g. the phony final state whose in-arcs are all the final weights).  A segment
-// writes its partial ⊕ to a scratch slot; every CTA combines the slots of the long rows at the
-// start of the next frame (redundantly, identical bits) so no second grid barrier is needed.
+// Long forward rows (in-degree above the split threshold, e.g. the phony final state whose in-arcs
+// are all the final weights) are cut into segment items; a segment writes its partial ⊕ to a
+// scratch slot and every CTA combines the slots of the long rows at the start of the next frame
+// (redundantly, identical bits) so no second grid barrier is needed.
 //
-// Normalisation (Log semiring): the stored forward vector is a_n = α_n - Ca_n with
-// Ca_n = Σ_{k<=n} shift_k (float64) and shift_n = max_s a_{n-1}[s]; likewise b_n = β_n - Cb_n.  The
-// stored values stay O(10) whatever the sequence length, so Float32 keeps ~1e-6 absolute accuracy
-// in the log domain where the un-normalised recursion loses ulp(|α|) ≈ 3e-5 per operation.
+// Normalisation (Log semiring; all stored quantities in log2 units):
+//   a_n[s] = log2 Σ_i 2^(a_{n-1}[i] + w_is) + (e_n[s] - emax_n) - shift_n,   shift_n = max_s a_{n-1}[s],
+//   α_n = (a_n + Ca_n) ln 2,   Ca_n = Σ_{k<=n} (shift_k + emax_k)   (float64),
+// and likewise b_n, Cb_n for β.  Hence a_n <= log2(max column ⊕-sum of T̂) and the ⊕ of a row is
+// evaluated in ONE pass against the compile-time bound R (the arcs hold w - R, so every exponent
+// is <= 0): one ex2 per arc, no running maximum, no rescaling.  If a row's sum underflows although
+// the utterance is alive, the row is redone with the exact two-pass row_reduce.  Stored values stay
+// O(10) whatever the sequence length, so Float32 keeps ~1e-6 absolute accuracy in the log domain
+// where the un-normalised recursion loses ulp(|α|) per ⊕.
 template <typename T> struct SharedParams {
     int S;       // Ŝ states incl. phony final (last)
     int Dh;      // D̂ pdfs incl. phony (last)
     int N1;      // N̂ frames incl. phony (last)
     int U4;      // utterances in the group, padded to a multiple of 4
     int ntiles;  // ceil(U4 / 128)
-    const Arc<T>* in_arcs;                        // T̂ᵀ rows (by destination)
-    const int4* fwd_items;                        // {row, arc_beg, arc_end, slot or -1}
-    const int* fwd_warp_items;                    // [grid*warps + 1] item ranges per warp
-    int n_long; const int4* fwd_long;             // {row, pseudo_beg, pseudo_end, 0}
+    DirPlan<T> fwd, bwd;                          // T̂ᵀ rows (by destination) / T̂ rows (by source)
+    int cache_f, cache_b;                         // padded arcs per CTA held in shared memory (SA kernels)
+    int n_long; const int4* fwd_long;             // {row, pseudo_beg, pseudo_end, pdf}
     const Arc<T>* fwd_long_arcs;                  // pseudo arcs {slot, 1̄} of the long rows
     int n_slots; T* part;                         // [2][n_slots][U4] segment partials
-    const int* out_ptr; const Arc<T>* out_arcs;   // T̂ rows (by source)
-    const int* bwd_rows;                          // [grid*warps + 1] row ranges per warp
-    const int* pdf;                               // state -> pdf (0-based)
-    const T* init_dense;                          // α̂ as a dense vector [S]
-    const T* E;      // expanded, transposed emissions [N1][Dh][U4]
+    const T* init_dense;                          // α̂ as a dense vector [S] (kernel units)
+    const T* E;      // expanded, transposed emissions minus emax (kernel units): [N1][Dh][U4]
+    const T* emax;   // [N1][U4]
     T* alpha;        // [N1][S][U4]   normalised a_n
-    T* bt;           // [2][S][U4]    b_{n+1} ⊗ e_{n+1} ping-pong
+    T* bt;           // [2][S][U4]    b_{n+1} ⊗ e'_{n+1} ping-pong
     T* beta_out;     // optional [N1][S][U4]  normalised b_n
     int* gkey;       // [2][N1][U4]   per-frame maxima (ordered keys): forward, backward
     double* Coff;    // [2][N1][U4]   Ca_n, Cb_n
@@ -274,10 +479,21 @@ template <typename T> struct SharedParams {
     const int* utt_b;  // [U4] global utterance index per group lane (-1 = padding)
     int post_vec4;     // 1: the 4 utterances of every lane are b0..b0+3, 16 B aligned
     T* zsum;           // [N1][B] per-frame normalisers (linear, relative to lz)
-    T* lz;             // [B] forward total log-likelihood
+    T* lz;             // [B] forward total log-likelihood (natural log)
     unsigned* barrier;
     int do_fwd, do_bwd, do_post;
 };
+
+template <typename T> __device__ __forceinline__ V4<T> ld4_nc(const T* p);
+template <> __device__ __forceinline__ V4<float> ld4_nc<float>(const float* p) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    V4<float> r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
+}
+template <> __device__ __forceinline__ V4<double> ld4_nc<double>(const double* p) {
+    double2 a = __ldg(reinterpret_cast<const double2*>(p));
+    double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    V4<double> r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; return r;
+}
 
 // combine the segment partials of the long rows into a_m (every CTA, identical result)
 template <typename T, int SR>
@@ -290,11 +506,10 @@ __device__ __forceinline__ void fwd_combine(const SharedParams<T>& p, int m, con
     for (int k = warp; k < p.n_long; k += kSharedWarps) {
         const int4 lr = __ldg(p.fwd_long + k);
         const int r = lr.x;
-        const int pdf = __ldg(p.pdf + r);
         for (int tile = 0; tile < p.ntiles; ++tile) {
             const int uoff = tile * kTileUtts + lane * 4;
             if (uoff >= U4) continue;
-            V4<T> e = ld4_cs(Em + size_t(pdf) * U4 + uoff);
+            V4<T> e = ld4_nc<T>(Em + size_t(lr.w) * U4 + uoff);
             V4<T> val;
             if (m == 0) {
                 T a0 = __ldg(p.init_dense + r);
@@ -316,8 +531,129 @@ __device__ __forceinline__ void fwd_combine(const SharedParams<T>& p, int m, con
     }
 }
 
-template <typename T, int SR>
-__global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(SharedParams<T> p) {
+template <typename T, int SR> struct FwdFin {
+    const SharedParams<T>& p;
+    const T* prev; T* cur; T* part; const T* En;
+    int uoff;
+    const T* s_shift; int* s_key;  // per-utterance shift of this frame / running maxima (shared memory)
+    int4 it;   // the item being streamed and its emissions, requested when the item starts
+    V4<T> e;
+    __device__ __forceinline__ void prefetch(int item) {
+        it = __ldg(p.fwd.items + item);
+        e = ld4_nc<T>(En + size_t(it.y) * p.U4 + uoff);
+    }
+    __device__ __forceinline__ void operator()(int item, const V4<T>& acc) {
+        V4<T> val = resolve_sum<T, SR>(acc, e, false, p.fwd, item, prev, p.U4, uoff);  // T̂ᵀ A[:,n-1] (:70)
+        if (it.z >= 0) {  // segment of a long row: partial ⊕ only
+            st4_cg(part + size_t(it.z) * p.U4 + uoff, val);
+            return;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            val.v[j] = val.v[j] + e.v[j] - s_shift[uoff + j];  // ⊗ e_n (:71), normalised
+            atomicMax(&s_key[uoff + j], fkey(float(val.v[j])));
+        }
+        st4_cg(cur + size_t(it.x) * p.U4 + uoff, val);
+    }
+};
+
+template <typename T, int SR> struct BwdFin {
+    const SharedParams<T>& p;
+    const T* bt_next; T* bt_cur; const T* En; const T* An;
+    int n, uoff;
+    const T* s_shift; const T* s_g; T* s_z; int* s_key;  // per-utterance scalars (shared memory)
+    int4 it;     // the item being streamed, its emissions and α, requested when the item starts
+    V4<T> e, a;
+    __device__ __forceinline__ void prefetch(int item) {
+        it = __ldg(p.bwd.items + item);
+        e = ld4_nc<T>(En + size_t(it.y) * p.U4 + uoff);
+        if (p.do_post) a = ld4_cs(An + size_t(it.x) * p.U4 + uoff);
+    }
+    __device__ __forceinline__ void finish(V4<T> beta) {
+        const size_t frame = size_t(p.S) * p.U4;
+        const int row = it.x, pdf = it.y;
+        if (p.beta_out) st4_cg(p.beta_out + size_t(n) * frame + size_t(row) * p.U4 + uoff, beta);
+        if (p.do_post) {
+            // γ = α ⊗ β ⊘ Z, exp, per-pdf ⊕  (:154-160)
+            V4<T> pg;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const T x = a.v[j] + beta.v[j] + s_g[uoff + j];
+                pg.v[j] = SR == SR_LOG ? ex2_(x) : exp_(x);
+                if (pg.v[j] > T(0)) {
+                    if (SR == SR_LOG) atomicAdd(&s_z[uoff + j], pg.v[j]);
+                    else red_max1(&s_z[uoff + j], pg.v[j]);
+                }
+            }
+            if (n < p.Tn && pdf < p.D) {
+                T* dst = p.post + (size_t(n) * p.D + pdf) * p.B;
+                if (p.post_vec4 && SR == SR_LOG) {
+                    red_add4(dst + p.utt_b[uoff], pg);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        int b = p.utt_b[uoff + j];
+                        if (b >= 0 && pg.v[j] > T(0)) red1<SR>(dst + b, pg.v[j]);
+                    }
+                }
+            }
+        }
+        if (n > 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                beta.v[j] += e.v[j];
+                atomicMax(&s_key[uoff + j], fkey(float(beta.v[j])));
+            }
+            st4_cg(bt_cur + size_t(row) * p.U4 + uoff, beta);
+        }
+    }
+    __device__ __forceinline__ void operator()(int item, const V4<T>& acc) {
+        // an explicit β output needs β_n even where e_n = 0̄ kills α_n and b_n ⊗ e_n
+        V4<T> beta = resolve_sum<T, SR>(acc, e, p.beta_out != nullptr, p.bwd, item, bt_next, p.U4, uoff);  // (:106-107)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) beta.v[j] -= s_shift[uoff + j];
+        finish(beta);
+    }
+};
+
+// fill this CTA's shared-memory arc cache for one direction; returns the arc source
+template <typename T, bool SA>
+__device__ __forceinline__ ArcSrc<T, SA> make_arc_src(const DirPlan<T>& pl, int cap, unsigned char* smem, int U4q) {
+    ArcSrc<T, SA> src;
+    src.gidx = pl.pidx; src.gw = pl.pw; src.gqf = pl.qflags; src.U4q = U4q;
+    src.soff = src.sw = src.sqf = 0;
+    if (SA) {
+        // the CTA's chunks cover one contiguous range of padded arcs
+        int a0 = 0x7fffffff, a1 = 0;
+        for (int c = pl.cta_chunks[blockIdx.x]; c < pl.cta_chunks[blockIdx.x + 1]; ++c) {
+            const int4 ch = pl.chunks[c];
+            a0 = min(a0, ch.x);
+            a1 = max(a1, ch.y);
+        }
+        if (a0 > a1) a0 = a1 = 0;
+        unsigned* s_off = reinterpret_cast<unsigned*>(smem);
+        T* s_w = reinterpret_cast<T*>(smem + size_t(cap) * 4);
+        unsigned char* s_qf = smem + size_t(cap) * (4 + sizeof(T));
+        for (int a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
+            s_off[a - a0] = unsigned(pl.pidx[a]) * unsigned(U4q);
+            s_w[a - a0] = pl.pw[a];
+        }
+        for (int q = (a0 >> 2) + threadIdx.x; q < (a1 >> 2); q += blockDim.x) s_qf[q - (a0 >> 2)] = pl.qflags[q];
+        src.soff = unsigned(__cvta_generic_to_shared(s_off)) - unsigned(a0) * 4u;
+        src.sw = unsigned(__cvta_generic_to_shared(s_w)) - unsigned(a0) * unsigned(sizeof(T));
+        src.sqf = unsigned(__cvta_generic_to_shared(s_qf)) - (unsigned(a0) >> 2);
+    }
+    return src;
+}
+__host__ __device__ inline size_t arc_cache_bytes(int cap, size_t tsize) {
+    return (size_t(cap) * (4 + tsize) + size_t(cap) / 4 + 15) & ~size_t(15);
+}
+__host__ __device__ inline size_t shared_scalars_bytes(int U4, size_t tsize) {
+    return (size_t(U4) * (2 * sizeof(double) + 3 * tsize + sizeof(int)) + 16 + 15) & ~size_t(15);
+}
+
+template <typename T, int SR, bool SA>
+__global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __grid_constant__ SharedParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = p.S, U4 = p.U4;
     double* s_C = reinterpret_cast<double*>(smem_raw);   // [U4] running Ca (forward) / Cb (backward)
@@ -326,10 +662,21 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(SharedPara
     T* s_g = s_shift + U4;                                // [U4] Ca_n + Cb_n - log Z
     T* s_z = s_g + U4;                                    // [U4] per-frame posterior mass
     int* s_key = reinterpret_cast<int*>(s_z + U4);        // [U4] running maxima
+    int* s_next = s_key + U4;                             // dynamic chunk counter
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gw = blockIdx.x * kSharedWarps + warp;
     const size_t frame = size_t(S) * U4;
     unsigned bar_target = 0;
+
+    // per-warp queue of finished items (lane-private columns), then the arc caches
+    const size_t scalars_bytes = shared_scalars_bytes(U4, sizeof(T));
+    constexpr unsigned QSLOT = 128 * sizeof(T);
+    const unsigned queue = unsigned(__cvta_generic_to_shared(smem_raw + scalars_bytes)) + warp * (kQueue * QSLOT) +
+                           lane * 4 * unsigned(sizeof(T));
+    unsigned char* cache = smem_raw + scalars_bytes + size_t(kSharedWarps) * kQueue * QSLOT;
+    // This CTA's arcs stay in shared memory for the whole launch: the per-frame fence of the grid
+    // barrier invalidates L1, shared memory survives.
+    const ArcSrc<T, SA> fwd_src = make_arc_src<T, SA>(p.fwd, p.cache_f, cache, U4 >> 2);
+    const ArcSrc<T, SA> bwd_src = make_arc_src<T, SA>(p.bwd, p.cache_b, cache + arc_cache_bytes(p.cache_f, sizeof(T)), U4 >> 2);
 
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < size_t(2) * p.N1 * U4;
          i += size_t(gridDim.x) * blockDim.x)
@@ -341,67 +688,53 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(SharedPara
 
     // ---------------------------------------------------------------- forward (αrecursion)
     if (p.do_fwd) {
-        const int i0 = p.fwd_warp_items[gw], i1 = p.fwd_warp_items[gw + 1];
+        const int c0 = p.fwd.cta_chunks[blockIdx.x], c1 = p.fwd.cta_chunks[blockIdx.x + 1];
+        const int work1 = c0 + (c1 - c0) * p.ntiles;  // (chunk, tile) pairs
         for (int n = 0; n < p.N1; ++n) {
-            if (n >= 1) {
-                if (p.n_long) {
-                    fwd_combine<T, SR>(p, n - 1, s_shift, s_key);
-                    __syncthreads();
-                }
-                for (int u = threadIdx.x; u < U4; u += blockDim.x) {
-                    int k = max(__ldcg(p.gkey + size_t(n - 1) * U4 + u), s_key[u]);
-                    T sh = shift_from_key<SR, T>(k);
-                    s_shift[u] = sh;
-                    s_C[u] += double(sh);
-                    s_key[u] = kKeyMin;
-                    if (blockIdx.x == 0) p.Coff[size_t(n) * U4 + u] = s_C[u];
-                }
+            if (n >= 1 && p.n_long) {
+                fwd_combine<T, SR>(p, n - 1, s_shift, s_key);
                 __syncthreads();
-            } else if (blockIdx.x == 0) {
-                for (int u = threadIdx.x; u < U4; u += blockDim.x) p.Coff[u] = 0.0;
             }
-            const T* prev = p.alpha + size_t(n > 0 ? n - 1 : 0) * frame;
-            T* cur = p.alpha + size_t(n) * frame;
-            const T* En = p.E + size_t(n) * p.Dh * U4;
-            T* part = p.part + size_t(n & 1) * p.n_slots * U4;
-            for (int tile = 0; tile < p.ntiles; ++tile) {
-                const int uoff = tile * kTileUtts + lane * 4;
-                if (uoff >= U4) continue;
-                T mx[4] = {neg_inf<T>(), neg_inf<T>(), neg_inf<T>(), neg_inf<T>()};
-                T sh[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) sh[j] = s_shift[uoff + j];
-                for (int i = i0; i < i1; ++i) {
-                    const int4 it = __ldg(p.fwd_items + i);
-                    const int r = it.x;
-                    V4<T> e = ld4_cs(En + size_t(__ldg(p.pdf + r)) * U4 + uoff);
-                    const bool dead = all_zero_bar(e);  // ⊗ 0̄: the row's ⊕ cannot matter
-                    if (it.w >= 0) {  // segment of a long row: partial ⊕ only
-                        if (n > 0 && !dead)
-                            st4_cg(part + size_t(it.w) * U4 + uoff,
-                                   row_reduce<T, SR>(p.in_arcs, it.y, it.z, prev, U4, uoff));
-                        continue;
-                    }
-                    V4<T> acc;
+            for (int u = threadIdx.x; u < U4; u += blockDim.x) {
+                T sh = T(0);
+                if (n >= 1) sh = shift_from_key<SR, T>(max(__ldcg(p.gkey + size_t(n - 1) * U4 + u), s_key[u]));
+                s_shift[u] = sh;
+                s_C[u] += double(sh) + double(__ldg(p.emax + size_t(n) * U4 + u));
+                s_key[u] = kKeyMin;
+                if (blockIdx.x == 0) p.Coff[size_t(n) * U4 + u] = s_C[u];
+            }
+            if (threadIdx.x == 0) *s_next = c0;
+            __syncthreads();
+            for (;;) {  // warps pull (chunk, tile) pairs, largest chunks first
+                int wk = 0;
+                if (lane == 0) wk = atomicAdd(s_next, 1);
+                wk = __shfl_sync(0xffffffffu, wk, 0);
+                if (wk >= work1) break;
+                const int4 ch = __ldg(p.fwd.chunks + c0 + (wk - c0) / p.ntiles);
+                const int uoff = ((wk - c0) % p.ntiles) * kTileUtts + lane * 4;
+                if (uoff < U4) {  // (lanes beyond the batch stay converged for the next pull)
+                    FwdFin<T, SR> fin{p, p.alpha + size_t(n > 0 ? n - 1 : 0) * frame, p.alpha + size_t(n) * frame,
+                                      p.part + size_t(n & 1) * p.n_slots * U4, p.E + size_t(n) * p.Dh * U4, uoff,
+                                      s_shift, s_key};
                     if (n == 0) {
-                        T a0 = __ldg(p.init_dense + r);  // A[:,1] = α̂ ⊗ e₁  (:68)
+                        for (int i = ch.z; i < ch.w; ++i) {
+                            const int4 it = __ldg(p.fwd.items + i);
+                            if (it.z >= 0) continue;
+                            V4<T> e = ld4_nc<T>(fin.En + size_t(it.y) * U4 + uoff);
+                            const T a0 = __ldg(p.init_dense + it.x);  // A[:,1] = α̂ ⊗ e₁  (:68)
+                            V4<T> acc;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) acc.v[j] = a0;
-                    } else if (dead) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) acc.v[j] = neg_inf<T>();
+                            for (int j = 0; j < 4; ++j) {
+                                acc.v[j] = a0 + e.v[j];
+                                atomicMax(&s_key[uoff + j], fkey(float(acc.v[j])));
+                            }
+                            st4_cg(fin.cur + size_t(it.x) * U4 + uoff, acc);
+                        }
                     } else {
-                        acc = row_reduce<T, SR>(p.in_arcs, it.y, it.z, prev, U4, uoff);  // T̂ᵀ A[:,n-1]  (:70)
+                        stream_chunk<T, SR, SA>(fwd_src, ch, fin.prev + uoff, queue, fin);
                     }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        acc.v[j] = acc.v[j] + e.v[j] - sh[j];  // ⊗ e_n  (:71), normalised
-                        mx[j] = max_(mx[j], acc.v[j]);
-                    }
-                    st4_cg(cur + size_t(r) * U4 + uoff, acc);
                 }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) atomicMax(&s_key[uoff + j], fkey(float(mx[j])));
+                __syncwarp();
             }
             __syncthreads();
             for (int u = threadIdx.x; u < U4; u += blockDim.x) {
@@ -415,14 +748,14 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(SharedPara
             fwd_combine<T, SR>(p, p.N1 - 1, s_shift, s_key);
             __syncthreads();
         }
-        // log Z = α_{N̂}[phony final] = a + Ca
+        // log Z = α_{N̂}[phony final] = a + Ca   (kernel units inside, natural log out)
         const T* last = p.alpha + size_t(p.N1 - 1) * frame + size_t(S - 1) * U4;
         for (int u = threadIdx.x; u < U4; u += blockDim.x) {
             T a = __ldcg(last + u);
             double z = (a == neg_inf<T>()) ? double(a) : double(a) + s_C[u];
             s_lz[u] = z;
             int b = p.utt_b[u];
-            if (blockIdx.x == 0 && b >= 0) p.lz[b] = T(z);
+            if (blockIdx.x == 0 && b >= 0) p.lz[b] = T(SR == SR_LOG ? z * 0.6931471805599453 : z);
         }
         __syncthreads();
     }
@@ -431,92 +764,50 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(SharedPara
     // ---------------------------------------------------------------- backward (βrecursion + γ)
     for (int u = threadIdx.x; u < U4; u += blockDim.x) { s_C[u] = 0.0; s_key[u] = kKeyMin; s_z[u] = T(0); }
     __syncthreads();
-    const int r0 = p.bwd_rows[gw], r1 = p.bwd_rows[gw + 1];
+    const int c0 = p.bwd.cta_chunks[blockIdx.x], c1 = p.bwd.cta_chunks[blockIdx.x + 1];
+    const int work1 = c0 + (c1 - c0) * p.ntiles;
     int* gkey_b = p.gkey + size_t(p.N1) * U4;
     double* Cb = p.Coff + size_t(p.N1) * U4;
     for (int n = p.N1 - 1; n >= 0; --n) {
         for (int u = threadIdx.x; u < U4; u += blockDim.x) {
             T sh = T(0);
-            if (n < p.N1 - 1) sh = shift_from_key<SR, T>(__ldcg(gkey_b + size_t(n + 1) * U4 + u));
+            if (n < p.N1 - 1) {
+                sh = shift_from_key<SR, T>(__ldcg(gkey_b + size_t(n + 1) * U4 + u));
+                s_C[u] += double(sh) + double(__ldg(p.emax + size_t(n + 1) * U4 + u));
+            }
             s_shift[u] = sh;
-            s_C[u] += double(sh);
             if (blockIdx.x == 0 && p.beta_out) Cb[size_t(n) * U4 + u] = s_C[u];
             if (p.do_post) {
                 double lz = s_lz[u];
                 s_g[u] = (lz == double(neg_inf<T>())) ? T(0) : T(__ldcg(p.Coff + size_t(n) * U4 + u) + s_C[u] - lz);
             }
         }
+        if (threadIdx.x == 0) *s_next = c0;
         __syncthreads();
-        const T* bt_next = p.bt + size_t((n + 1) & 1) * frame;
-        T* bt_cur = p.bt + size_t(n & 1) * frame;
-        const T* En = p.E + size_t(n) * p.Dh * U4;
-        const T* An = p.alpha + size_t(n) * frame;
-        for (int tile = 0; tile < p.ntiles; ++tile) {
-            const int uoff = tile * kTileUtts + lane * 4;
-            if (uoff >= U4) continue;
-            T zs[4] = {T(0), T(0), T(0), T(0)};
-            T mx[4] = {neg_inf<T>(), neg_inf<T>(), neg_inf<T>(), neg_inf<T>()};
-            T sh[4], g[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { sh[j] = s_shift[uoff + j]; g[j] = s_g[uoff + j]; }
-            for (int i = r0; i < r1; ++i) {
-                const int pdf = __ldg(p.pdf + i);
-                V4<T> e = ld4_cs(En + size_t(pdf) * U4 + uoff);
-                // e_n = 0̄ kills α_n (so γ) and b_n ⊗ e_n; only an explicit β output still needs β_n
-                const bool dead = !p.beta_out && all_zero_bar(e);
-                V4<T> beta;
+        for (;;) {
+            int wk = 0;
+            if (lane == 0) wk = atomicAdd(s_next, 1);
+            wk = __shfl_sync(0xffffffffu, wk, 0);
+            if (wk >= work1) break;
+            const int4 ch = __ldg(p.bwd.chunks + c0 + (wk - c0) / p.ntiles);
+            const int uoff = ((wk - c0) % p.ntiles) * kTileUtts + lane * 4;
+            if (uoff < U4) {
+                BwdFin<T, SR> fin{p, p.bt + size_t((n + 1) & 1) * frame, p.bt + size_t(n & 1) * frame,
+                                  p.E + size_t(n) * p.Dh * U4, p.alpha + size_t(n) * frame, n, uoff,
+                                  s_shift, s_g, s_z, s_key};
                 if (n == p.N1 - 1) {
+                    for (int i = ch.z; i < ch.w; ++i) {
+                        fin.prefetch(i);
+                        V4<T> beta;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) beta.v[j] = T(0);  // B[:,end] = 1̄  (:104)
-                } else if (dead) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) beta.v[j] = neg_inf<T>();
+                        for (int j = 0; j < 4; ++j) beta.v[j] = T(0);  // B[:,end] = 1̄  (:104)
+                        fin.finish(beta);
+                    }
                 } else {
-                    beta = row_reduce<T, SR>(p.out_arcs, __ldg(p.out_ptr + i), __ldg(p.out_ptr + i + 1), bt_next,
-                                             U4, uoff);  // T̂ (B[:,n+1] ⊗ e_{n+1})  (:106-107)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) beta.v[j] -= sh[j];
-                }
-                if (p.beta_out) st4_cg(p.beta_out + size_t(n) * frame + size_t(i) * U4 + uoff, beta);
-                if (p.do_post && !dead) {
-                    // γ = α ⊗ β ⊘ Z, exp, per-pdf ⊕  (:154-160)
-                    V4<T> a = ld4_cs(An + size_t(i) * U4 + uoff);
-                    V4<T> pg;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        pg.v[j] = exp_(a.v[j] + beta.v[j] + g[j]);
-                        zs[j] = lin_add<SR>(zs[j], pg.v[j]);
-                    }
-                    if (n < p.Tn && pdf < p.D) {
-                        T* dst = p.post + (size_t(n) * p.D + pdf) * p.B;
-                        if (p.post_vec4 && SR == SR_LOG) {
-                            red_add4(dst + p.utt_b[uoff], pg);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                int b = p.utt_b[uoff + j];
-                                if (b >= 0 && pg.v[j] > T(0)) red1<SR>(dst + b, pg.v[j]);
-                            }
-                        }
-                    }
-                }
-                if (n > 0) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        beta.v[j] += e.v[j];
-                        mx[j] = max_(mx[j], beta.v[j]);
-                    }
-                    st4_cg(bt_cur + size_t(i) * U4 + uoff, beta);
+                    stream_chunk<T, SR, SA>(bwd_src, ch, fin.bt_next + uoff, queue, fin);
                 }
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (n > 0) atomicMax(&s_key[uoff + j], fkey(float(mx[j])));
-                if (p.do_post) {
-                    if (SR == SR_LOG) atomicAdd(&s_z[uoff + j], zs[j]);
-                    else red_max1(&s_z[uoff + j], zs[j]);
-                }
-            }
+            __syncwarp();
         }
         __syncthreads();
         for (int u = threadIdx.x; u < U4; u += blockDim.x) {
@@ -578,6 +869,27 @@ template <typename T> __global__ void expand_transpose_kernel(EmisParams<T> p) {
     for (int k = threadIdx.y; k < 32; k += 8) {
         int d = d0 + k, u = u0 + threadIdx.x;
         if (d < p.Dh && u < p.U4) p.E[(size_t(n) * p.Dh + d) * p.U4 + u] = tile[threadIdx.x][k];
+    }
+}
+
+// emax[n][u] = scale * max_d E[n][d][u] (0 when the whole column is 0̄);
+// E[n][d][u] = scale * (E[n][d][u] - max).   scale = log2(e): the kernel works in log2 units.
+// grid (ceil(U4/32), N1), block (32, 8)
+template <typename T> __global__ void emission_max_kernel(T* E, T* emax, int Dh, int U4, T scale) {
+    __shared__ T red[8][32];
+    const int n = blockIdx.y, u = blockIdx.x * 32 + threadIdx.x;
+    T* En = E + size_t(n) * Dh * U4;
+    T m = neg_inf<T>();
+    if (u < U4)
+        for (int d = threadIdx.y; d < Dh; d += 8) m = max_(m, En[size_t(d) * U4 + u]);
+    red[threadIdx.y][threadIdx.x] = m;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m = max_(m, red[k][threadIdx.x]);
+    if (m == neg_inf<T>()) m = T(0);
+    if (u < U4) {
+        if (threadIdx.y == 0) emax[size_t(n) * U4 + u] = m * scale;
+        for (int d = threadIdx.y; d < Dh; d += 8) En[size_t(d) * U4 + u] = (En[size_t(d) * U4 + u] - m) * scale;
     }
 }
 
@@ -766,7 +1078,7 @@ template <typename T> __global__ void total_kernel(const T* zsum, const T* lz, T
 // ================================================================================================
 template <typename T>
 __global__ void unpack_states_kernel(const T* src, int S, int U4, const int* utt_b,
-                                     const long long* utt_off, const double* C /* [N1][U4] */, T* dst,
+                                     const long long* utt_off, const double* C /* [N1][U4] */, double unit, T* dst,
                                      long long total) {
     __shared__ T tile[32][33];
     const int n = blockIdx.z, s0 = blockIdx.x * 32, u0 = blockIdx.y * 32;
@@ -778,7 +1090,7 @@ __global__ void unpack_states_kernel(const T* src, int S, int U4, const int* utt
     for (int k = threadIdx.y; k < 32; k += 8) {
         int u = u0 + k, s = s0 + threadIdx.x;
         if (s < S && u < U4 && utt_b[u] >= 0)
-            dst[utt_off[u] + s + total * n] = T(double(tile[threadIdx.x][k]) + C[size_t(n) * U4 + u]);
+            dst[utt_off[u] + s + total * n] = T((double(tile[threadIdx.x][k]) + C[size_t(n) * U4 + u]) * unit);
     }
 }
 

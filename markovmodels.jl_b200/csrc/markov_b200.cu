@@ -96,94 +96,162 @@ template <typename T> static int upload(const std::vector<T>& h, void** d) {
 // ------------------------------------------------------------------------------------------------
 // mk_graph
 // ------------------------------------------------------------------------------------------------
+// device-side work plan of one direction (kernels.cuh DirPlan)
+struct DirDev {
+    int4 *items = nullptr, *chunks = nullptr;
+    int2* item_arcs = nullptr;
+    int *cta_chunks = nullptr, *pidx = nullptr;
+    void *pw = nullptr, *arcs = nullptr;  // arcs: un-padded Arc<T> holding w - R in kernel units
+    unsigned char* qflags = nullptr;
+    int cache_cap = 0;  // largest per-CTA range of padded arcs (multiple of 4)
+    double R = 0;       // bound on the ⊕ exponents, kernel units
+    void release() {
+        cudaFree(items); cudaFree(chunks); cudaFree(item_arcs); cudaFree(cta_chunks); cudaFree(pidx);
+        cudaFree(pw); cudaFree(arcs); cudaFree(qflags);
+    }
+};
+
 struct mk_graph {
     int semiring = 0, dtype = 0, device = 0, n_sms = 0;
     int64_t S = 0, nnz = 0, Dh = 0;
     int max_in_deg = 0, max_out_deg = 0;
+    // true weights, both orientations: per-utterance kernel, back-trace
     int *d_in_ptr = nullptr, *d_out_ptr = nullptr, *d_pdf = nullptr;
-    int *d_fwd_warp_items = nullptr, *d_bwd_rows = nullptr;
-    int4 *d_fwd_items = nullptr, *d_fwd_long = nullptr;
-    void *d_in_arcs = nullptr, *d_out_arcs = nullptr, *d_init_dense = nullptr, *d_fwd_long_arcs = nullptr;
+    void *d_in_arcs = nullptr, *d_out_arcs = nullptr, *d_init_dense = nullptr;
+    // shared-graph kernel plans
+    DirDev fwd, bwd;
+    int4* d_fwd_long = nullptr;
+    void *d_fwd_long_arcs = nullptr, *d_init_dense_s = nullptr;
     int n_long = 0, n_slots = 0;
     size_t bytes = 0;
     ~mk_graph() {
         cudaFree(d_in_ptr); cudaFree(d_out_ptr); cudaFree(d_pdf);
-        cudaFree(d_fwd_warp_items); cudaFree(d_bwd_rows); cudaFree(d_fwd_items); cudaFree(d_fwd_long);
-        cudaFree(d_in_arcs); cudaFree(d_out_arcs); cudaFree(d_init_dense); cudaFree(d_fwd_long_arcs);
+        cudaFree(d_in_arcs); cudaFree(d_out_arcs); cudaFree(d_init_dense);
+        fwd.release(); bwd.release();
+        cudaFree(d_fwd_long); cudaFree(d_fwd_long_arcs); cudaFree(d_init_dense_s);
     }
 };
 
-// Forward work items.  Rows with more than kLongRow in-arcs (typically the phony final state:
-// one in-arc per final state) are cut into segments that spread over all warps; each segment
-// writes a partial ⊕ into a scratch slot and every CTA combines the slots at the start of the
-// next frame (kernels.cuh, fwd_combine).  Segment length keeps the slot count per row <= 48 so
-// that the (per-CTA, serial) combine stays short.
+// Work plan of one direction.  Rows with more than kLongRow arcs (forward only — typically the
+// phony final state: one in-arc per final state) are cut into segment items that spread over all
+// CTAs; each segment writes a partial ⊕ into a scratch slot and every CTA combines the slots at
+// the start of the next frame (kernels.cuh, fwd_combine).  Items are cut into per-CTA ranges
+// balanced by arcs, and inside a CTA into chunks of ~kChunkArcs arcs that the warps pull
+// dynamically, largest first.  The arcs are re-laid out chunk by chunk into padded arrays (see
+// kernels.cuh DirPlan): every chunk spans a multiple of four arcs, every item owns >= 1 arc.
 constexpr int kLongRow = 128;
 constexpr int kMinSegment = 64;
-constexpr int kMaxSlotsPerRow = 48;
+constexpr int kMaxSlotsPerRow = 160;
+constexpr int kChunkArcs = 64;
+
+template <typename T> struct DirHost {
+    std::vector<int4> items, chunks;
+    std::vector<int2> item_arcs;
+    std::vector<int> cta_chunks, pidx;
+    std::vector<T> pw;
+    std::vector<unsigned char> qflags;
+    int cache_cap = 0;
+};
 
 template <typename T>
-static void build_fwd_items(const std::vector<int>& in_ptr, int S, int n_warps, std::vector<int4>& items,
-                            std::vector<int>& warp_items, std::vector<int4>& long_rows,
-                            std::vector<Arc<T>>& long_arcs, int& n_slots) {
+static void build_plan(const std::vector<int>& ptr, const std::vector<Arc<T>>& arcs, const std::vector<int>& pdf,
+                       int S, int n_ctas, bool split, DirHost<T>& d, std::vector<int4>& long_rows,
+                       std::vector<Arc<T>>& long_arcs, int& n_slots) {
+    const T ninf = -std::numeric_limits<T>::infinity();
     n_slots = 0;
     for (int r = 0; r < S; ++r) {
-        const int beg = in_ptr[r], end = in_ptr[r + 1], deg = end - beg;
-        if (deg <= kLongRow) {
-            items.push_back(make_int4(r, beg, end, -1));
+        const int beg = ptr[r], end = ptr[r + 1], deg = end - beg;
+        if (!split || deg <= kLongRow) {
+            d.items.push_back(make_int4(r, pdf[r], -1, 0));
+            d.item_arcs.push_back(make_int2(beg, end));
             continue;
         }
         const int seg = std::max(kMinSegment, (deg + kMaxSlotsPerRow - 1) / kMaxSlotsPerRow);
         const int pseudo_beg = int(long_arcs.size());
         for (int a = beg; a < end; a += seg) {
-            items.push_back(make_int4(r, a, std::min(end, a + seg), n_slots));
+            d.items.push_back(make_int4(r, pdf[r], n_slots, 0));
+            d.item_arcs.push_back(make_int2(a, std::min(end, a + seg)));
             Arc<T> pa;
             std::memset(&pa, 0, sizeof pa);
             pa.idx = n_slots++;
             pa.w = T(0);  // 1̄
             long_arcs.push_back(pa);
         }
-        long_rows.push_back(make_int4(r, pseudo_beg, int(long_arcs.size()), 0));
+        long_rows.push_back(make_int4(r, pseudo_beg, int(long_arcs.size()), pdf[r]));
     }
-    // contiguous item ranges per warp, balanced by (arcs + 2) per item
-    const int n_items = int(items.size());
+    const int n_items = int(d.items.size());
+    auto cost = [&](int i) { return double(d.item_arcs[i].y - d.item_arcs[i].x) + 2.0; };
     double total = 0;
-    for (const int4& it : items) total += double(it.z - it.y) + 2.0;
-    warp_items.assign(n_warps + 1, n_items);
-    warp_items[0] = 0;
+    for (int i = 0; i < n_items; ++i) total += cost(i);
+    std::vector<int> cta_items(n_ctas + 1, n_items);
+    cta_items[0] = 0;
     double acc = 0;
     int i = 0;
-    for (int k = 1; k < n_warps; ++k) {
-        const double target = total * k / n_warps;
+    for (int k = 1; k < n_ctas; ++k) {
+        const double target = total * k / n_ctas;
         while (i < n_items) {
-            double c = double(items[i].z - items[i].y) + 2.0;
+            double c = cost(i);
             if (acc + 0.5 * c > target) break;
             acc += c;
             ++i;
         }
-        warp_items[k] = i;
+        cta_items[k] = i;
     }
+    d.cta_chunks.assign(n_ctas + 1, 0);
+    auto emit = [&](int idx, T w) { d.pidx.push_back(idx); d.pw.push_back(w); };
+    for (int k = 0; k < n_ctas; ++k) {
+        const size_t first = d.chunks.size();
+        const int cta_arc0 = int(d.pidx.size());
+        int cb = cta_items[k], n_arcs = 0, pb = int(d.pidx.size());
+        for (int it = cta_items[k]; it < cta_items[k + 1]; ++it) {
+            const int2 ar = d.item_arcs[it];
+            for (int a = ar.x; a < ar.y; ++a) emit(arcs[a].idx, arcs[a].w);
+            if (ar.y == ar.x) emit(0, ninf);  // an empty row still owns one (pad) arc
+            const size_t last = d.pidx.size() - 1;
+            if (d.qflags.size() <= last / 4) d.qflags.resize(last / 4 + 1, 0);
+            d.qflags[last / 4] |= (unsigned char)(1u << (last % 4));
+            n_arcs += std::max(1, ar.y - ar.x);
+            if (n_arcs >= kChunkArcs || it + 1 == cta_items[k + 1]) {
+                while (d.pidx.size() % 4) emit(0, ninf);
+                d.chunks.push_back(make_int4(pb, int(d.pidx.size()), cb, it + 1));
+                cb = it + 1;
+                n_arcs = 0;
+                pb = int(d.pidx.size());
+            }
+        }
+        std::stable_sort(d.chunks.begin() + first, d.chunks.end(),
+                         [](const int4& x, const int4& y) { return x.y - x.x > y.y - y.x; });
+        d.cta_chunks[k + 1] = int(d.chunks.size());
+        d.cache_cap = std::max(d.cache_cap, int(d.pidx.size()) - cta_arc0);
+    }
+    d.qflags.resize(d.pidx.size() / 4 + 1, 0);
 }
 
-// contiguous row ranges per warp, balanced by (arcs + 2) per row
-static std::vector<int> partition_rows(const std::vector<int>& ptr, int S, int n_warps) {
-    std::vector<int> b(n_warps + 1, S);
-    const double total = double(ptr[S]) + 2.0 * S;
-    double acc = 0;
-    int r = 0;
-    b[0] = 0;
-    for (int k = 1; k < n_warps; ++k) {
-        const double target = total * k / n_warps;
-        while (r < S) {
-            double c = double(ptr[r + 1] - ptr[r]) + 2.0;
-            if (acc + 0.5 * c > target) break;
-            acc += c;
-            ++r;
-        }
-        b[k] = r;
+template <typename T> static int upload_plan(const DirHost<T>& hst, const std::vector<Arc<T>>& arcs, DirDev& dev) {
+    TRY(upload(hst.items, (void**)&dev.items));
+    TRY(upload(hst.item_arcs, (void**)&dev.item_arcs));
+    TRY(upload(hst.chunks, (void**)&dev.chunks));
+    TRY(upload(hst.cta_chunks, (void**)&dev.cta_chunks));
+    TRY(upload(hst.pidx, (void**)&dev.pidx));
+    TRY(upload(hst.pw, &dev.pw));
+    TRY(upload(hst.qflags, (void**)&dev.qflags));
+    TRY(upload(arcs, &dev.arcs));
+    dev.cache_cap = hst.cache_cap;
+    return MK_OK;
+}
+
+// log of the largest ⊕-sum of a row's weights (Log semiring bound; rows given by ptr)
+template <typename T> static double max_row_logsum(const std::vector<int>& ptr, const std::vector<Arc<T>>& arcs, int S) {
+    double best = -std::numeric_limits<double>::infinity();
+    for (int r = 0; r < S; ++r) {
+        double m = -std::numeric_limits<double>::infinity();
+        for (int a = ptr[r]; a < ptr[r + 1]; ++a) m = std::max(m, double(arcs[a].w));
+        if (!(m > -std::numeric_limits<double>::infinity())) continue;
+        double sum = 0;
+        for (int a = ptr[r]; a < ptr[r + 1]; ++a) sum += std::exp(double(arcs[a].w) - m);
+        best = std::max(best, m + std::log(sum));
     }
-    b[n_warps] = S;
-    return b;
+    return best;
 }
 
 template <typename T>
@@ -252,11 +320,38 @@ static int build_graph(mk_graph* g, const int64_t* colptr, const int64_t* rowval
         if (s < 0 || s >= S) return fail(MK_EINVAL, "init_idx[%lld] out of range", (long long)k);
         init[s] = init_w[k];
     }
-    const int n_warps = g->n_sms * kSharedWarps;
-    std::vector<int> bwd = partition_rows(out_ptr, S, n_warps), fwd_warp_items;
-    std::vector<int4> fwd_items, fwd_long;
-    std::vector<Arc<T>> fwd_long_arcs;
-    build_fwd_items<T>(in_ptr, S, n_warps, fwd_items, fwd_warp_items, fwd_long, fwd_long_arcs, g->n_slots);
+    // Bounds for the single-pass ⊕ (kernels.cuh): stored a_n <= max(log max column-sum, max α̂),
+    // stored b_n ⊗ e' <= max(log max row-sum, 0); every exponent v + (w - R) is then <= 0.
+    double R_f = 0, R_b = 0;
+    if (g->semiring == MK_LOG && nnz > 0) {
+        const double ninf_d = -std::numeric_limits<double>::infinity();
+        double wmax = ninf_d, li = ninf_d;
+        for (int64_t a = 0; a < nnz; ++a) wmax = std::max(wmax, double(in_arcs[a].w));
+        for (int64_t k = 0; k < n_init; ++k) li = std::max(li, double(init_w[k]));
+        if (wmax > ninf_d && wmax < std::numeric_limits<double>::infinity()) {
+            double vf = std::max(max_row_logsum<T>(in_ptr, in_arcs, S), li);
+            double vb = std::max(max_row_logsum<T>(out_ptr, out_arcs, S), 0.0);
+            if (!(vf > ninf_d)) vf = 0;
+            R_f = vf + wmax;
+            R_b = vb + wmax;
+        }
+    }
+    // the shared-graph kernel works in log2 units for the Log semiring
+    const double unit = g->semiring == MK_LOG ? 1.4426950408889634 : 1.0;
+    std::vector<Arc<T>> in_s(in_arcs), out_s(out_arcs);
+    for (auto& a : in_s) a.w = T((double(a.w) - R_f) * unit);
+    for (auto& a : out_s) a.w = T((double(a.w) - R_b) * unit);
+    std::vector<T> init_s(init);
+    for (auto& x : init_s) x = T(double(x) * unit);
+    g->fwd.R = R_f * unit;
+    g->bwd.R = R_b * unit;
+
+    DirHost<T> fwd, bwd;
+    std::vector<int4> fwd_long, no_long;
+    std::vector<Arc<T>> fwd_long_arcs, no_arcs;
+    int no_slots = 0;
+    build_plan<T>(in_ptr, in_s, pdf, S, g->n_sms, true, fwd, fwd_long, fwd_long_arcs, g->n_slots);
+    build_plan<T>(out_ptr, out_s, pdf, S, g->n_sms, false, bwd, no_long, no_arcs, no_slots);
     g->n_long = int(fwd_long.size());
 
     TRY(upload(in_ptr, (void**)&g->d_in_ptr));
@@ -265,13 +360,13 @@ static int build_graph(mk_graph* g, const int64_t* colptr, const int64_t* rowval
     TRY(upload(out_arcs, &g->d_out_arcs));
     TRY(upload(pdf, (void**)&g->d_pdf));
     TRY(upload(init, &g->d_init_dense));
-    TRY(upload(fwd_items, (void**)&g->d_fwd_items));
-    TRY(upload(fwd_warp_items, (void**)&g->d_fwd_warp_items));
+    TRY(upload(init_s, &g->d_init_dense_s));
+    TRY(upload_plan<T>(fwd, in_s, g->fwd));
+    TRY(upload_plan<T>(bwd, out_s, g->bwd));
     TRY(upload(fwd_long, (void**)&g->d_fwd_long));
     TRY(upload(fwd_long_arcs, &g->d_fwd_long_arcs));
-    TRY(upload(bwd, (void**)&g->d_bwd_rows));
-    g->bytes = 2 * (S + 1) * sizeof(int) + 2 * nnz * sizeof(Arc<T>) + S * (sizeof(int) + sizeof(T)) +
-               2 * (n_warps + 1) * sizeof(int);
+    g->bytes = 2 * (S + 1) * sizeof(int) + 4 * nnz * sizeof(Arc<T>) + S * (sizeof(int) + 2 * sizeof(T)) +
+               (fwd.pidx.size() + bwd.pidx.size()) * (sizeof(int) + sizeof(T));
     return MK_OK;
 }
 
@@ -285,7 +380,7 @@ struct Group {  // utterances sharing one graph, run by shared_fb_kernel
     bool vec4 = false;
     int* d_utt_b = nullptr;
     long long* d_utt_off = nullptr;
-    DevBuf E, alpha, bt, part, gkey, coff;
+    DevBuf E, emax, alpha, bt, part, gkey, coff;
 };
 
 struct mk_batch {
@@ -311,7 +406,7 @@ struct mk_batch {
         for (auto& gr : groups) {
             cudaFree(gr.d_utt_b); cudaFree(gr.d_utt_off);
             gr.E.release(); gr.alpha.release(); gr.bt.release();
-            gr.part.release(); gr.gkey.release(); gr.coff.release();
+            gr.part.release(); gr.gkey.release(); gr.coff.release(); gr.emax.release();
         }
         DevBuf* all[] = {&small_descs, &small_alpha, &small_ca, &zsum, &lz, &seqlens, &barrier, &trace,
                          &h_ll, &h_post, &h_logz, &h_path};
@@ -325,7 +420,7 @@ struct mk_batch {
     size_t ws_bytes() const {
         size_t t = small_descs.cap + small_alpha.cap + small_ca.cap + zsum.cap + lz.cap + seqlens.cap + barrier.cap +
                    trace.cap + h_ll.cap + h_post.cap + h_logz.cap + h_path.cap;
-        for (auto& gr : groups) t += gr.E.cap + gr.alpha.cap + gr.bt.cap + gr.part.cap + gr.gkey.cap + gr.coff.cap;
+        for (auto& gr : groups) t += gr.E.cap + gr.alpha.cap + gr.bt.cap + gr.part.cap + gr.gkey.cap + gr.coff.cap + gr.emax.cap;
         return t;
     }
 };
@@ -357,6 +452,7 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     if (mode == MODE_POST || mode == MODE_BETA) TRY(gr.bt.ensure(2 * frame));
     TRY(gr.part.ensure(2 * size_t(std::max(g->n_slots, 1)) * U4 * sizeof(T)));
     TRY(gr.gkey.ensure(2 * size_t(N1) * U4 * sizeof(int)));
+    TRY(gr.emax.ensure(size_t(N1) * U4 * sizeof(T)));
     TRY(gr.coff.ensure(2 * size_t(N1) * U4 * sizeof(double)));
 
     EmisParams<T> ep;
@@ -367,17 +463,30 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     expand_transpose_kernel<T><<<eg, eb, 0, c.stream>>>(ep);
     CK(cudaGetLastError());
     ++g_launches;
+    if (SR == SR_LOG) {
+        emission_max_kernel<T><<<dim3((U4 + 31) / 32, N1), dim3(32, 8), 0, c.stream>>>(
+            static_cast<T*>(gr.E.p), static_cast<T*>(gr.emax.p), Dh, U4, T(1.4426950408889634));
+        CK(cudaGetLastError());
+        ++g_launches;
+    } else {
+        CK(cudaMemsetAsync(gr.emax.p, 0, size_t(N1) * U4 * sizeof(T), c.stream));
+    }
 
     SharedParams<T> p;
     p.S = S; p.Dh = Dh; p.N1 = N1; p.U4 = U4; p.ntiles = (U4 + kTileUtts - 1) / kTileUtts;
-    p.in_arcs = static_cast<const Arc<T>*>(g->d_in_arcs);
-    p.fwd_items = g->d_fwd_items; p.fwd_warp_items = g->d_fwd_warp_items;
+    auto plan = [](const DirDev& d) {
+        DirPlan<T> q;
+        q.items = d.items; q.item_arcs = d.item_arcs; q.chunks = d.chunks; q.cta_chunks = d.cta_chunks;
+        q.pidx = d.pidx; q.pw = static_cast<const T*>(d.pw); q.qflags = d.qflags;
+        q.arcs = static_cast<const Arc<T>*>(d.arcs); q.R = T(d.R);
+        return q;
+    };
+    p.fwd = plan(g->fwd); p.bwd = plan(g->bwd);
     p.n_long = g->n_long; p.fwd_long = g->d_fwd_long;
     p.fwd_long_arcs = static_cast<const Arc<T>*>(g->d_fwd_long_arcs);
     p.n_slots = g->n_slots; p.part = static_cast<T*>(gr.part.p);
-    p.out_ptr = g->d_out_ptr; p.out_arcs = static_cast<const Arc<T>*>(g->d_out_arcs);
-    p.bwd_rows = g->d_bwd_rows;
-    p.pdf = g->d_pdf; p.init_dense = static_cast<const T*>(g->d_init_dense);
+    p.init_dense = static_cast<const T*>(g->d_init_dense_s);
+    p.emax = static_cast<const T*>(gr.emax.p);
     p.gkey = static_cast<int*>(gr.gkey.p); p.Coff = static_cast<double*>(gr.coff.p);
     p.E = static_cast<const T*>(gr.E.p);
     p.alpha = static_cast<T*>(gr.alpha.p);
@@ -399,10 +508,23 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     }
     CK(cudaMemsetAsync(bt->barrier.p, 0, sizeof(unsigned), c.stream));
     void* args[] = {&p};
-    size_t smem = size_t(U4) * (2 * sizeof(double) + 3 * sizeof(T) + sizeof(int));
-    auto kern = shared_fb_kernel<T, SR>;
+    size_t smem = shared_scalars_bytes(U4, sizeof(T)) + size_t(kSharedWarps) * kQueue * 128 * sizeof(T);
+    // shared-memory arc caches (both directions) when they fit next to the scalars and queues
+    p.cache_f = p.cache_b = 0;
+    {
+        size_t need = arc_cache_bytes(g->fwd.cache_cap, sizeof(T)) + arc_cache_bytes(g->bwd.cache_cap, sizeof(T));
+        if (smem + need <= bt->max_smem_optin) {
+            p.cache_f = g->fwd.cache_cap;
+            p.cache_b = g->bwd.cache_cap;
+            smem += need;
+        }
+    }
+    void (*kern)(SharedParams<T>) = shared_fb_kernel<T, SR, false>;
+    if (p.cache_f > 0) kern = shared_fb_kernel<T, SR, true>;
     const int slot = bt->prof_n % mk_batch::kProfRing;
     if (bt->profile) CK(cudaEventRecord(bt->ev0[slot], c.stream));
+    if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     CK(cudaLaunchCooperativeKernel((void*)kern, dim3(g->n_sms), dim3(kSharedThreads), args, smem, c.stream));
     ++g_launches;
     if (bt->profile) { CK(cudaEventRecord(bt->ev1[slot], c.stream)); ++bt->prof_n; }
@@ -411,7 +533,8 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
         dim3 ug((S + 31) / 32, (U4 + 31) / 32, N1), ub(32, 8);
         const double* C = static_cast<const double*>(gr.coff.p) + (mode == MODE_BETA ? size_t(N1) * U4 : 0);
         unpack_states_kernel<T><<<ug, ub, 0, c.stream>>>(static_cast<const T*>(gr.alpha.p), S, U4, gr.d_utt_b,
-                                                        gr.d_utt_off, C, static_cast<T*>(c.out0), bt->total);
+                                                        gr.d_utt_off, C, SR == SR_LOG ? 0.6931471805599453 : 1.0,
+                                                        static_cast<T*>(c.out0), bt->total);
         CK(cudaGetLastError());
         ++g_launches;
     }
