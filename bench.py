@@ -159,17 +159,14 @@ def run_ours(args):
     Vd = V.permute(0, 2, 1)                                        # (B, D, T) view the API takes
     post = torch.empty((T, D, B), device="cuda")
     ttl = torch.empty((B,), device="cuda")
-    stats = torch.zeros((D + 2,), device="cuda")
+    post_bdn = post.permute(2, 1, 0)
     lib = mm.lib()
+    last = {}
 
     def step():
         mm.pdfposteriors(bfsm, Vd, out=(post, ttl))
-        # the data-parallel exchange: Σ logZ, #frames, per-pdf occupancy (12 KB)
-        stats[0] = ttl.sum()
-        stats[1] = float(B * T)
-        stats[2:] = post.sum(dim=(0, 2))
-        if dist is not None:
-            dist.all_reduce(stats)
+        # the data-parallel exchange: one all-reduce of [Σ logZ, #frames, pdf occupancy[D]] (~24 KB)
+        last["stats"] = mm.sharding.allreduce_stats(mm.sharding.local_stats(post_bdn, ttl))
 
     def sync_all():
         torch.cuda.synchronize()
@@ -201,7 +198,7 @@ def run_ours(args):
         dist.all_reduce(kms, op=dist.ReduceOp.MAX)
     ms_total, kernel_ms = float(ms), float(kms)
     bfsm.profile(False)
-    logz_mean = float(stats[0]) / (B * world)
+    logz_mean = float(last["stats"][0]) / (B * world)
 
     # ---- e2e: the public API on HOST buffers, copies inside the timed region
     Vh = torch.empty((B, T, D), pin_memory=True)

@@ -310,7 +310,7 @@ __device__ __forceinline__ V4<T> resolve_sum(const V4<T>& acc, const V4<T>& e, b
 // ---- arc source: the CTA's shared-memory cache (SA) or the global padded arrays ---------------------
 // The cache holds, per padded arc, the row offset pre-multiplied (idx * U4/4, in units of one
 // lane's 4 utterances) and the weight; per quad the flag byte.
-constexpr int kQueue = 8;  // finished items per drain: two quads
+constexpr int kQueue = 12;  // finished items per drain: three quads
 template <typename T, bool SA> struct ArcSrc {
     const int* gidx; const T* gw; const unsigned char* gqf;  // global
     unsigned soff, sw, sqf;  // shared addresses of (virtual) padded arc 0 / quad 0
@@ -418,18 +418,22 @@ __device__ __forceinline__ void stream_chunk(const ArcSrc<T, SA>& src, const int
     const int nq = (ch.y - ch.x) >> 2;
     int item = ch.z;
     fin.prefetch(item);
-    Quad<T> A, B;
+    // three quads rotate: two are in flight while one is consumed
+    Quad<T> A, B, C;
     quad_issue<T, SA>(A, src, ch.x, vec_lane);
+    if (nq > 1) quad_issue<T, SA>(B, src, ch.x + 4, vec_lane);
     V4<T> acc;
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc.v[j] = SR == SR_LOG ? T(0) : neg_inf<T>();
-    for (int q = 0; q < nq; q += 2) {
+    for (int q = 0; q < nq; q += 3) {
         const int aq = ch.x + q * 4;
         int npush = 0;
-        if (q + 1 < nq) quad_issue<T, SA>(B, src, aq + 4, vec_lane);
+        if (q + 2 < nq) quad_issue<T, SA>(C, src, aq + 8, vec_lane);
         quad_consume<T, SR, SA>(A, src, aq, acc, queue, npush);
-        if (q + 2 < nq) quad_issue<T, SA>(A, src, aq + 8, vec_lane);
+        if (q + 3 < nq) quad_issue<T, SA>(A, src, aq + 12, vec_lane);
         if (q + 1 < nq) quad_consume<T, SR, SA>(B, src, aq + 4, acc, queue, npush);
+        if (q + 4 < nq) quad_issue<T, SA>(B, src, aq + 16, vec_lane);
+        if (q + 2 < nq) quad_consume<T, SR, SA>(C, src, aq + 8, acc, queue, npush);
         for (int k = 0; k < npush; ++k) {  // the only finalise site
             const V4<T> r = lds_row(queue + unsigned(k) * QSLOT, T());
             fin(item, r);

@@ -142,7 +142,11 @@ struct mk_graph {
 constexpr int kLongRow = 128;
 constexpr int kMinSegment = 64;
 constexpr int kMaxSlotsPerRow = 160;
-constexpr int kChunkArcs = 64;
+static int chunk_arcs() {  // target arcs per dynamically scheduled chunk (MK_CHUNK_ARCS overrides, for tuning)
+    const char* e = getenv("MK_CHUNK_ARCS");
+    int v = e ? atoi(e) : 64;
+    return v >= 4 ? v : 64;
+}
 
 template <typename T> struct DirHost {
     std::vector<int4> items, chunks;
@@ -198,6 +202,7 @@ static void build_plan(const std::vector<int>& ptr, const std::vector<Arc<T>>& a
         cta_items[k] = i;
     }
     d.cta_chunks.assign(n_ctas + 1, 0);
+    const int chunk_target = chunk_arcs();
     auto emit = [&](int idx, T w) { d.pidx.push_back(idx); d.pw.push_back(w); };
     for (int k = 0; k < n_ctas; ++k) {
         const size_t first = d.chunks.size();
@@ -211,7 +216,7 @@ static void build_plan(const std::vector<int>& ptr, const std::vector<Arc<T>>& a
             if (d.qflags.size() <= last / 4) d.qflags.resize(last / 4 + 1, 0);
             d.qflags[last / 4] |= (unsigned char)(1u << (last % 4));
             n_arcs += std::max(1, ar.y - ar.x);
-            if (n_arcs >= kChunkArcs || it + 1 == cta_items[k + 1]) {
+            if (n_arcs >= chunk_target || it + 1 == cta_items[k + 1]) {
                 while (d.pidx.size() % 4) emit(0, ninf);
                 d.chunks.push_back(make_int4(pb, int(d.pidx.size()), cb, it + 1));
                 cb = it + 1;
