@@ -49,6 +49,9 @@ def build(force=False, verbose=False):
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "markov_b200.cu")]
+    for knob in ("MK_RING", "MK_THREADS", "MK_PROFILE_BARRIER"):  # kernel tuning knobs (defaults in kernels.cuh)
+        if os.environ.get(knob):
+            cmd.insert(1, f"-D{knob}={os.environ[knob]}")
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -34,7 +34,10 @@ namespace mk {
 
 enum { SR_LOG = 0, SR_TROP = 1 };
 
-constexpr int kSharedThreads = 512;  // 16 warps / CTA, 1 CTA / SM
+#ifndef MK_THREADS
+#define MK_THREADS 384
+#endif
+constexpr int kSharedThreads = MK_THREADS;  // 12 warps / CTA, 1 CTA / SM (170 registers per thread: the quad buffers must not spill)
 constexpr int kSharedWarps = kSharedThreads / 32;
 constexpr int kChunk = 8;       // arcs cached in registers per ⊕ chunk
 constexpr int kTileUtts = 128;  // utterances covered by one warp pass (32 lanes x 4)
@@ -96,6 +99,8 @@ __device__ __forceinline__ Arc<double> ld_arc_g(const Arc<double>* p) {
     Arc<double> a; a.idx = t.x; a.w = __hiloint2double(t.w, t.z); return a;
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 template <typename T> struct V4 { T v[4]; };
 
 // L2-coherent (L1-bypassing) accesses: the state vectors are rewritten by other SMs each frame.
@@ -117,6 +122,20 @@ __device__ __forceinline__ V4<double> ld4_cs(const double* p) {
     double2 a = __ldcs(reinterpret_cast<const double2*>(p));
     double2 b = __ldcs(reinterpret_cast<const double2*>(p) + 1);
     V4<double> r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; return r;
+}
+// L1-allocating loads for rows that were prefetched into L1 (the α store on the backward sweep:
+// written earlier in this launch by other SMs with L1-bypassing stores, never cached before)
+__device__ __forceinline__ V4<float> ld4_ca(const float* p) {
+    V4<float> r;
+    asm volatile("ld.global.ca.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ V4<double> ld4_ca(const double* p) {
+    V4<double> r;
+    asm volatile("ld.global.ca.v2.f64 {%0, %1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "l"(p) : "memory");
+    asm volatile("ld.global.ca.v2.f64 {%0, %1}, [%2];" : "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p + 2) : "memory");
+    return r;
 }
 __device__ __forceinline__ void st4_cg(float* p, const V4<float>& x) {
     __stcg(reinterpret_cast<float4*>(p), make_float4(x.v[0], x.v[1], x.v[2], x.v[3]));
@@ -155,8 +174,18 @@ template <int SR, typename T> __device__ __forceinline__ T lin_add(T a, T b) {
 // Monotonic counter; the kernel is launched cooperatively (all CTAs co-resident).  Writers'
 // stores are ordered by bar.sync + fence + the atomic; the waiting thread uses an acquire load
 // and every consumer then reads other CTAs' data with L1-bypassing loads only (ld4_cg).
+#ifdef MK_PROFILE_BARRIER
+__device__ unsigned long long g_prof[148 * 4];  // per CTA: cycles before arriving, cycles waiting, ...
+#endif
 __device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& target) {
+#ifdef MK_PROFILE_BARRIER
+    static __shared__ long long t_last;
+    long long t0 = clock64();
+#endif
     __syncthreads();
+#ifdef MK_PROFILE_BARRIER
+    long long t1 = clock64();
+#endif
     if (threadIdx.x == 0) {
         target += gridDim.x;
         __threadfence();
@@ -167,6 +196,17 @@ __device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& target) {
         } while (v < target);
     }
     __syncthreads();
+#ifdef MK_PROFILE_BARRIER
+    if (threadIdx.x == 0) {
+        long long t2 = clock64();
+        if (target > gridDim.x) {  // skip the first barrier
+            g_prof[blockIdx.x * 4 + 0] += (unsigned long long)(t0 - t_last);  // thread 0: work since last barrier
+            g_prof[blockIdx.x * 4 + 1] += (unsigned long long)(t1 - t0);      // thread 0 waiting for its CTA
+            g_prof[blockIdx.x * 4 + 2] += (unsigned long long)(t2 - t1);      // CTA waiting for the grid
+        }
+        t_last = t2;
+    }
+#endif
 }
 
 // ---- per-lane ⊕ over one row's arcs for 4 utterances (exact two-pass form, log2 units) -----------
@@ -258,7 +298,7 @@ template <typename T> __device__ __forceinline__ bool all_zero_bar(const V4<T>& 
 // (an empty row gets one pad arc), and a per-quad flag byte marks the arcs that end an item — so
 // the streaming loop needs no per-arc bookkeeping beyond one flag test.
 template <typename T> struct DirPlan {
-    const int4* items;           // {row, pdf, slot or -1, 0}
+    const int4* items;           // {row, pdf, slot or -1, run flags (see FwdFin / BwdFin)}
     const int2* item_arcs;       // {beg, end} in the un-padded arc array (exact fallback only)
     const int4* chunks;          // {parc_begin, parc_end, item_begin, item_end}
     const int* cta_chunks;       // [grid + 1]: CTA c pulls chunks [cta_chunks[c], cta_chunks[c+1])
@@ -310,11 +350,21 @@ __device__ __forceinline__ V4<T> resolve_sum(const V4<T>& acc, const V4<T>& e, b
 // ---- arc source: the CTA's shared-memory cache (SA) or the global padded arrays ---------------------
 // The cache holds, per padded arc, the row offset pre-multiplied (idx * U4/4, in units of one
 // lane's 4 utterances) and the weight; per quad the flag byte.
-constexpr int kQueue = 12;  // finished items per drain: three quads
+
 template <typename T, bool SA> struct ArcSrc {
     const int* gidx; const T* gw; const unsigned char* gqf;  // global
     unsigned soff, sw, sqf;  // shared addresses of (virtual) padded arc 0 / quad 0
+    const int4* gitems; unsigned sitems;  // item records: global array / shared address of (virtual) item 0
     int U4q;                 // U4 / 4
+    __device__ __forceinline__ int4 item(int i) const {
+        if (SA) {
+            int4 r;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(sitems + unsigned(i) * 16u));
+            return r;
+        }
+        return __ldg(gitems + i);
+    }
     // row offsets of the quad's four arcs, in units of one lane's 4 utterances
     __device__ __forceinline__ void offsets(int aq, unsigned (&off)[4]) const {
         if (SA) {
@@ -369,77 +419,103 @@ __device__ __forceinline__ V4<double> lds_row(unsigned saddr, double) {
 }
 
 // ---- streaming loop ----------------------------------------------------------------------------------
-// One chunk: quads of four gathers (one 16/32-byte load per lane and arc, 512 B per warp and arc),
-// double-buffered in registers.  Loads are issued a whole quad at a time and consumed a whole quad
-// at a time — the in-order scoreboards then overlap quad q+1's latency with quad q's arithmetic.
-// Per arc and utterance: one add, one ex2, one add.  A finished item's sum goes to a small
-// per-warp shared-memory queue (lane-private columns); the queue is drained after every two quads
-// by the single finalise site fin(item_index, acc).
-template <typename T> struct Quad {
-    V4<T> v[4];
-};
+// Register-destination loads cannot form a rolling window here: the 6 scoreboard slots are shared
+// with the MUFU results, ptxas puts every gather on the same slot and each consume then waits for
+// ALL outstanding gathers (measured: depth 2..6 made no difference).  Asynchronous copies do not
+// use register scoreboards: each warp owns a ring of kRing rows in shared memory, lane l copies its
+// own 4 utterances of every gathered row there with cp.async (16 B / 32 B) and reads them back
+// itself — no cross-lane traffic, no barrier.  Copies are committed per quad of arcs and
+// cp.async.wait_group gives exactly the rolling window: kRing/4 - 1 quads stay in flight while one
+// is consumed.  Per arc and utterance: one add, one ex2, one add.  A finished item's sum goes to a
+// small per-warp queue (lane-private columns) drained after every quad by the single finalise site.
+#ifndef MK_RING
+#define MK_RING 16
+#endif
+constexpr int kRingF32 = MK_RING;  // rows in flight per warp for 4-byte payloads (power of two, multiple of 4)
+template <typename T> struct RingOf { static constexpr int rows = sizeof(T) == 4 ? kRingF32 : (kRingF32 / 2 >= 8 ? kRingF32 / 2 : 8); };
+constexpr int kQueue = 4;        // finished items per drain: one quad
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void cp_async_row(unsigned sdst, const float* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_row(unsigned sdst, const double* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(g) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + 16), "l"(g + 2) : "memory");
+}
+
 template <typename T, bool SA>
-__device__ __forceinline__ void quad_issue(Quad<T>& q, const ArcSrc<T, SA>& src, int aq, const T* vec_lane) {
+__device__ __forceinline__ void quad_issue(unsigned slot0, const ArcSrc<T, SA>& src, int aq, const T* vec_lane) {
+    constexpr unsigned SLOT = 128 * sizeof(T);
     unsigned off[4];
     src.offsets(aq, off);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) q.v[k] = ld4_cg(vec_lane + size_t(off[k]) * 4);
-}
-// weights and flags are re-read at consume time (two shared-memory loads per quad) rather than held
-// in registers while the gathers are in flight
-template <typename T, int SR, bool SA>
-__device__ __forceinline__ void quad_consume(const Quad<T>& q, const ArcSrc<T, SA>& src, int aq, V4<T>& acc,
-                                             unsigned queue, int& npush) {
-    constexpr unsigned QSLOT = 128 * sizeof(T);
-    T w[4];
-    unsigned flags;
-    src.weights(aq, w, flags);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const T x = q.v[k].v[j] + w[k];
-            if (SR == SR_LOG) acc.v[j] += ex2_(x);
-            else acc.v[j] = max_(acc.v[j], x);
-        }
-        if (flags & (1u << k)) {  // this arc ends an item (warp-uniform)
-            sts_row(queue + unsigned(npush) * QSLOT, acc);
-            ++npush;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc.v[j] = SR == SR_LOG ? T(0) : neg_inf<T>();
-        }
-    }
+    for (int k = 0; k < 4; ++k) cp_async_row(slot0 + k * SLOT, vec_lane + size_t(off[k]) * 4);
 }
 
 template <typename T, int SR, bool SA, class Fin>
 __device__ __forceinline__ void stream_chunk(const ArcSrc<T, SA>& src, const int4 ch, const T* vec_lane,
-                                             unsigned queue, Fin& fin) {
-    constexpr unsigned QSLOT = 128 * sizeof(T);
+                                             unsigned ring, unsigned queue, Fin& fin) {
+    constexpr unsigned SLOT = 128 * sizeof(T);  // bytes per ring / queue slot: 32 lanes x 4 utterances
+    constexpr int NG = RingOf<T>::rows / 4;     // quads in the ring
+    static_assert((NG & (NG - 1)) == 0 && NG >= 2, "ring depth");
     const int nq = (ch.y - ch.x) >> 2;
     int item = ch.z;
-    fin.prefetch(item);
-    // three quads rotate: two are in flight while one is consumed
-    Quad<T> A, B, C;
-    quad_issue<T, SA>(A, src, ch.x, vec_lane);
-    if (nq > 1) quad_issue<T, SA>(B, src, ch.x + 4, vec_lane);
+    fin.warm(src, ch.z, ch.w);
+    fin.prefetch(src, item);
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        if (g < nq) quad_issue<T, SA>(ring + g * 4 * SLOT, src, ch.x + g * 4, vec_lane);
+        cp_async_commit();
+    }
     V4<T> acc;
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc.v[j] = SR == SR_LOG ? T(0) : neg_inf<T>();
-    for (int q = 0; q < nq; q += 3) {
+    for (int q = 0; q < nq; ++q) {
         const int aq = ch.x + q * 4;
+        const unsigned slot0 = ring + unsigned(q & (NG - 1)) * 4 * SLOT;
+        T w[4];
+        unsigned flags;
+        src.weights(aq, w, flags);
+        cp_async_wait<NG - 1>();  // the oldest quad has landed
         int npush = 0;
-        if (q + 2 < nq) quad_issue<T, SA>(C, src, aq + 8, vec_lane);
-        quad_consume<T, SR, SA>(A, src, aq, acc, queue, npush);
-        if (q + 3 < nq) quad_issue<T, SA>(A, src, aq + 12, vec_lane);
-        if (q + 1 < nq) quad_consume<T, SR, SA>(B, src, aq + 4, acc, queue, npush);
-        if (q + 4 < nq) quad_issue<T, SA>(B, src, aq + 16, vec_lane);
-        if (q + 2 < nq) quad_consume<T, SR, SA>(C, src, aq + 8, acc, queue, npush);
-        for (int k = 0; k < npush; ++k) {  // the only finalise site
-            const V4<T> r = lds_row(queue + unsigned(k) * QSLOT, T());
-            fin(item, r);
-            if (++item < ch.w) fin.prefetch(item);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const V4<T> v = lds_row(slot0 + k * SLOT, T());
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const T x = v.v[j] + w[k];
+                if (SR == SR_LOG) acc.v[j] += ex2_(x);
+                else acc.v[j] = max_(acc.v[j], x);
+            }
+            if (flags & (1u << k)) {  // this arc ends an item (warp-uniform)
+                sts_row(queue + unsigned(npush) * SLOT, acc);
+                ++npush;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc.v[j] = SR == SR_LOG ? T(0) : neg_inf<T>();
+            }
         }
+        if (q + NG < nq) quad_issue<T, SA>(slot0, src, aq + NG * 4, vec_lane);
+        cp_async_commit();
+#ifdef MK_PROFILE_BARRIER
+        long long td0 = clock64();
+#endif
+        for (int k = 0; k < npush; ++k) {  // the only finalise site
+            const V4<T> r = lds_row(queue + unsigned(k) * SLOT, T());
+            fin(item, r);
+            if (++item < ch.w) fin.prefetch(src, item);
+            while (item < ch.w && fin.is_reuse()) {  // rows of a merged run reuse the ⊕ just resolved
+                fin.reuse();
+                if (++item < ch.w) fin.prefetch(src, item);
+            }
+        }
+#ifdef MK_PROFILE_BARRIER
+        if ((threadIdx.x & 31) == 0) atomicAdd(&g_prof[blockIdx.x * 4 + 3], (unsigned long long)(clock64() - td0));
+#endif
     }
+    cp_async_wait<0>();
 }
 
 // ================================================================================================
@@ -461,19 +537,21 @@ __device__ __forceinline__ void stream_chunk(const ArcSrc<T, SA>& src, const int
 // where the un-normalised recursion loses ulp(|α|) per ⊕.
 template <typename T> struct SharedParams {
     int S;       // Ŝ states incl. phony final (last)
+    int Sq;      // rows of the forward vector: Ŝ + merged-run sources q_g
     int Dh;      // D̂ pdfs incl. phony (last)
     int N1;      // N̂ frames incl. phony (last)
     int U4;      // utterances in the group, padded to a multiple of 4
     int ntiles;  // ceil(U4 / 128)
     DirPlan<T> fwd, bwd;                          // T̂ᵀ rows (by destination) / T̂ rows (by source)
     int cache_f, cache_b;                         // padded arcs per CTA held in shared memory (SA kernels)
+    int cache_items_f, cache_items_b;             // item records per CTA held in shared memory
     int n_long; const int4* fwd_long;             // {row, pseudo_beg, pseudo_end, pdf}
     const Arc<T>* fwd_long_arcs;                  // pseudo arcs {slot, 1̄} of the long rows
     int n_slots; T* part;                         // [2][n_slots][U4] segment partials
     const T* init_dense;                          // α̂ as a dense vector [S] (kernel units)
     const T* E;      // expanded, transposed emissions minus emax (kernel units): [N1][Dh][U4]
     const T* emax;   // [N1][U4]
-    T* alpha;        // [N1][S][U4]   normalised a_n
+    T* alpha;        // [N1][Sq][U4]  normalised a_n, then the merged-run sources q_g
     T* bt;           // [2][S][U4]    b_{n+1} ⊗ e'_{n+1} ping-pong
     T* beta_out;     // optional [N1][S][U4]  normalised b_n
     int* gkey;       // [2][N1][U4]   per-frame maxima (ordered keys): forward, backward
@@ -484,6 +562,7 @@ template <typename T> struct SharedParams {
     int post_vec4;     // 1: the 4 utterances of every lane are b0..b0+3, 16 B aligned
     T* zsum;           // [N1][B] per-frame normalisers (linear, relative to lz)
     T* lz;             // [B] forward total log-likelihood (natural log)
+    double* lz2;       // [U4] the same in kernel units, handed from the forward to the backward launch
     unsigned* barrier;
     int do_fwd, do_bwd, do_post;
 };
@@ -504,7 +583,7 @@ template <typename T, int SR>
 __device__ __forceinline__ void fwd_combine(const SharedParams<T>& p, int m, const T* s_shift, int* s_key) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int U4 = p.U4;
-    const size_t frame = size_t(p.S) * U4;
+    const size_t frame = size_t(p.Sq) * U4;
     const T* Em = p.E + size_t(m) * p.Dh * U4;
     const T* part = p.part + size_t(m & 1) * p.n_slots * U4;
     for (int k = warp; k < p.n_long; k += kSharedWarps) {
@@ -539,12 +618,38 @@ template <typename T, int SR> struct FwdFin {
     const SharedParams<T>& p;
     const T* prev; T* cur; T* part; const T* En;
     int uoff;
-    const T* s_shift; int* s_key;  // per-utterance shift of this frame / running maxima (shared memory)
+    const T* s_shift;  // per-utterance shift of this frame (shared memory)
+    T mx[4];           // running maxima of this chunk's a values, flushed once per chunk
     int4 it;   // the item being streamed and its emissions, requested when the item starts
     V4<T> e;
-    __device__ __forceinline__ void prefetch(int item) {
-        it = __ldg(p.fwd.items + item);
+    V4<T> qacc;  // ⊕ of the a values of the current merged run
+    template <class Src> __device__ __forceinline__ void prefetch(const Src& src, int item) {
+        it = src.item(item);
         e = ld4_nc<T>(En + size_t(it.y) * p.U4 + uoff);
+    }
+    // bring the emission rows of a whole chunk into L1 ahead of the finalise chain
+    template <class Src> __device__ __forceinline__ void warm(const Src& src, int i0, int i1) {
+        for (int i = i0; i < i1; ++i) prefetch_l1(En + size_t(src.item(i).y) * p.U4 + uoff);
+    }
+    __device__ __forceinline__ bool is_reuse() const { return false; }
+    __device__ __forceinline__ void reuse() {}
+    // Row merging: item.w bit0 = member of a run, bit1 = first, bit2 = last, bits 4.. = run index g.  The
+    // run's virtual source q_g = ⊕_members a (row Ŝ + g of this frame's vector) feeds the members' common
+    // successors in the next frame.
+    __device__ __forceinline__ void emit_q(const V4<T>& val) {
+        if (!(it.w & 1)) return;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (it.w & 2) {
+                qacc.v[j] = val.v[j];
+            } else if (SR == SR_TROP) {
+                qacc.v[j] = max_(qacc.v[j], val.v[j]);
+            } else {
+                const T m = max_(qacc.v[j], val.v[j]), d = qacc.v[j] + val.v[j] - m - m;  // -|difference|
+                qacc.v[j] = (m == neg_inf<T>()) ? m : m + lg2_(T(1) + ex2_(d));
+            }
+        }
+        if (it.w & 4) st4_cg(cur + size_t(p.S + (it.w >> 4)) * p.U4 + uoff, qacc);
     }
     __device__ __forceinline__ void operator()(int item, const V4<T>& acc) {
         V4<T> val = resolve_sum<T, SR>(acc, e, false, p.fwd, item, prev, p.U4, uoff);  // T̂ᵀ A[:,n-1] (:70)
@@ -555,9 +660,10 @@ template <typename T, int SR> struct FwdFin {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             val.v[j] = val.v[j] + e.v[j] - s_shift[uoff + j];  // ⊗ e_n (:71), normalised
-            atomicMax(&s_key[uoff + j], fkey(float(val.v[j])));
+            mx[j] = max_(mx[j], val.v[j]);
         }
         st4_cg(cur + size_t(it.x) * p.U4 + uoff, val);
+        emit_q(val);
     }
 };
 
@@ -565,16 +671,27 @@ template <typename T, int SR> struct BwdFin {
     const SharedParams<T>& p;
     const T* bt_next; T* bt_cur; const T* En; const T* An;
     int n, uoff;
-    const T* s_shift; const T* s_g; T* s_z; int* s_key;  // per-utterance scalars (shared memory)
+    const T* s_shift; const T* s_g;  // per-utterance scalars of this frame (shared memory)
+    T mx[4], zs[4];                  // running maxima of b ⊗ e and posterior mass, flushed once per chunk
     int4 it;     // the item being streamed, its emissions and α, requested when the item starts
     V4<T> e, a;
-    __device__ __forceinline__ void prefetch(int item) {
-        it = __ldg(p.bwd.items + item);
+    V4<T> last;  // b_n of the last item that owned arcs: rows of a merged run share it (item.w bit0)
+    __device__ __forceinline__ bool is_reuse() const { return it.w & 1; }
+    __device__ __forceinline__ void reuse() { finish(last); }
+    template <class Src> __device__ __forceinline__ void prefetch(const Src& src, int item) {
+        it = src.item(item);
         e = ld4_nc<T>(En + size_t(it.y) * p.U4 + uoff);
-        if (p.do_post) a = ld4_cs(An + size_t(it.x) * p.U4 + uoff);
+        if (p.do_post) a = ld4_ca(An + size_t(it.x) * p.U4 + uoff);
+    }
+    template <class Src> __device__ __forceinline__ void warm(const Src& src, int i0, int i1) {
+        for (int i = i0; i < i1; ++i) {
+            const int4 t = src.item(i);
+            prefetch_l1(En + size_t(t.y) * p.U4 + uoff);
+            if (p.do_post) prefetch_l1(An + size_t(t.x) * p.U4 + uoff);
+        }
     }
     __device__ __forceinline__ void finish(V4<T> beta) {
-        const size_t frame = size_t(p.S) * p.U4;
+        const size_t frame = size_t(p.S) * p.U4;  // (β output frames hold Ŝ rows)
         const int row = it.x, pdf = it.y;
         if (p.beta_out) st4_cg(p.beta_out + size_t(n) * frame + size_t(row) * p.U4 + uoff, beta);
         if (p.do_post) {
@@ -584,10 +701,7 @@ template <typename T, int SR> struct BwdFin {
             for (int j = 0; j < 4; ++j) {
                 const T x = a.v[j] + beta.v[j] + s_g[uoff + j];
                 pg.v[j] = SR == SR_LOG ? ex2_(x) : exp_(x);
-                if (pg.v[j] > T(0)) {
-                    if (SR == SR_LOG) atomicAdd(&s_z[uoff + j], pg.v[j]);
-                    else red_max1(&s_z[uoff + j], pg.v[j]);
-                }
+                zs[j] = lin_add<SR>(zs[j], pg.v[j]);
             }
             if (n < p.Tn && pdf < p.D) {
                 T* dst = p.post + (size_t(n) * p.D + pdf) * p.B;
@@ -606,7 +720,7 @@ template <typename T, int SR> struct BwdFin {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 beta.v[j] += e.v[j];
-                atomicMax(&s_key[uoff + j], fkey(float(beta.v[j])));
+                mx[j] = max_(mx[j], beta.v[j]);
             }
             st4_cg(bt_cur + size_t(row) * p.U4 + uoff, beta);
         }
@@ -616,6 +730,7 @@ template <typename T, int SR> struct BwdFin {
         V4<T> beta = resolve_sum<T, SR>(acc, e, p.beta_out != nullptr, p.bwd, item, bt_next, p.U4, uoff);  // (:106-107)
 #pragma unroll
         for (int j = 0; j < 4; ++j) beta.v[j] -= s_shift[uoff + j];
+        last = beta;
         finish(beta);
     }
 };
@@ -625,19 +740,26 @@ template <typename T, bool SA>
 __device__ __forceinline__ ArcSrc<T, SA> make_arc_src(const DirPlan<T>& pl, int cap, unsigned char* smem, int U4q) {
     ArcSrc<T, SA> src;
     src.gidx = pl.pidx; src.gw = pl.pw; src.gqf = pl.qflags; src.U4q = U4q;
-    src.soff = src.sw = src.sqf = 0;
-    if (SA) {
+    src.gitems = pl.items;
+    src.soff = src.sw = src.sqf = src.sitems = 0;
+    if (SA && cap > 0) {  // (cap == 0: the other sweep's plan, unused in this launch)
         // the CTA's chunks cover one contiguous range of padded arcs
-        int a0 = 0x7fffffff, a1 = 0;
+        int a0 = 0x7fffffff, a1 = 0, i0 = 0x7fffffff, i1 = 0;
         for (int c = pl.cta_chunks[blockIdx.x]; c < pl.cta_chunks[blockIdx.x + 1]; ++c) {
             const int4 ch = pl.chunks[c];
             a0 = min(a0, ch.x);
             a1 = max(a1, ch.y);
+            i0 = min(i0, ch.z);
+            i1 = max(i1, ch.w);
         }
         if (a0 > a1) a0 = a1 = 0;
+        if (i0 > i1) i0 = i1 = 0;
         unsigned* s_off = reinterpret_cast<unsigned*>(smem);
         T* s_w = reinterpret_cast<T*>(smem + size_t(cap) * 4);
         unsigned char* s_qf = smem + size_t(cap) * (4 + sizeof(T));
+        int4* s_items = reinterpret_cast<int4*>(smem + ((size_t(cap) * (4 + sizeof(T)) + size_t(cap) / 4 + 15) & ~size_t(15)));
+        for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) s_items[i - i0] = pl.items[i];
+        src.sitems = unsigned(__cvta_generic_to_shared(s_items)) - unsigned(i0) * 16u;
         for (int a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
             s_off[a - a0] = unsigned(pl.pidx[a]) * unsigned(U4q);
             s_w[a - a0] = pl.pw[a];
@@ -649,14 +771,17 @@ __device__ __forceinline__ ArcSrc<T, SA> make_arc_src(const DirPlan<T>& pl, int 
     }
     return src;
 }
-__host__ __device__ inline size_t arc_cache_bytes(int cap, size_t tsize) {
-    return (size_t(cap) * (4 + tsize) + size_t(cap) / 4 + 15) & ~size_t(15);
+// padded arcs (offset, weight), quad flags, then the CTA's item records (at most one per arc)
+__host__ __device__ inline size_t arc_cache_bytes(int cap, int items, size_t tsize) {
+    return ((size_t(cap) * (4 + tsize) + size_t(cap) / 4 + 15) & ~size_t(15)) + size_t(items) * 16;
 }
 __host__ __device__ inline size_t shared_scalars_bytes(int U4, size_t tsize) {
     return (size_t(U4) * (2 * sizeof(double) + 3 * tsize + sizeof(int)) + 16 + 15) & ~size_t(15);
 }
 
-template <typename T, int SR, bool SA>
+// PHASE 0: forward sweep (αrecursion), leaves log Z in p.lz2.  PHASE 1: backward sweep (βrecursion + γ).
+// Two launches: each sweep gets its own register allocation.
+template <typename T, int SR, bool SA, int PHASE>
 __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __grid_constant__ SharedParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = p.S, U4 = p.U4;
@@ -668,30 +793,35 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
     int* s_key = reinterpret_cast<int*>(s_z + U4);        // [U4] running maxima
     int* s_next = s_key + U4;                             // dynamic chunk counter
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t frame = size_t(S) * U4;
+    const size_t frame = size_t(S) * U4;      // β-side vectors: Ŝ rows
+    const size_t frame_q = size_t(p.Sq) * U4;  // α store: Ŝ + merged-run rows
     unsigned bar_target = 0;
 
     // per-warp queue of finished items (lane-private columns), then the arc caches
     const size_t scalars_bytes = shared_scalars_bytes(U4, sizeof(T));
     constexpr unsigned QSLOT = 128 * sizeof(T);
-    const unsigned queue = unsigned(__cvta_generic_to_shared(smem_raw + scalars_bytes)) + warp * (kQueue * QSLOT) +
-                           lane * 4 * unsigned(sizeof(T));
-    unsigned char* cache = smem_raw + scalars_bytes + size_t(kSharedWarps) * kQueue * QSLOT;
+    const unsigned warp_smem = unsigned(__cvta_generic_to_shared(smem_raw + scalars_bytes)) +
+                               warp * ((kQueue + RingOf<T>::rows) * QSLOT) + lane * 4 * unsigned(sizeof(T));
+    const unsigned queue = warp_smem, ring = warp_smem + kQueue * QSLOT;
+    unsigned char* cache = smem_raw + scalars_bytes + size_t(kSharedWarps) * (kQueue + RingOf<T>::rows) * QSLOT;
     // This CTA's arcs stay in shared memory for the whole launch: the per-frame fence of the grid
     // barrier invalidates L1, shared memory survives.
-    const ArcSrc<T, SA> fwd_src = make_arc_src<T, SA>(p.fwd, p.cache_f, cache, U4 >> 2);
-    const ArcSrc<T, SA> bwd_src = make_arc_src<T, SA>(p.bwd, p.cache_b, cache + arc_cache_bytes(p.cache_f, sizeof(T)), U4 >> 2);
+    const ArcSrc<T, SA> fwd_src = make_arc_src<T, SA>(p.fwd, PHASE == 0 ? p.cache_f : 0, cache, U4 >> 2);
+    const ArcSrc<T, SA> bwd_src = make_arc_src<T, SA>(p.bwd, PHASE == 1 ? p.cache_b : 0, cache, U4 >> 2);
 
-    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < size_t(2) * p.N1 * U4;
-         i += size_t(gridDim.x) * blockDim.x)
-        p.gkey[i] = kKeyMin;
+    {   // this sweep's per-frame maxima
+        int* keys = p.gkey + size_t(PHASE) * p.N1 * U4;
+        for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < size_t(p.N1) * U4;
+             i += size_t(gridDim.x) * blockDim.x)
+            keys[i] = kKeyMin;
+    }
     for (int u = threadIdx.x; u < U4; u += blockDim.x) {
         s_C[u] = 0.0; s_lz[u] = 0.0; s_shift[u] = T(0); s_g[u] = T(0); s_z[u] = T(0); s_key[u] = kKeyMin;
     }
     grid_sync(p.barrier, bar_target);
 
     // ---------------------------------------------------------------- forward (αrecursion)
-    if (p.do_fwd) {
+    if (PHASE == 0) {
         const int c0 = p.fwd.cta_chunks[blockIdx.x], c1 = p.fwd.cta_chunks[blockIdx.x + 1];
         const int work1 = c0 + (c1 - c0) * p.ntiles;  // (chunk, tile) pairs
         for (int n = 0; n < p.N1; ++n) {
@@ -717,26 +847,30 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
                 const int4 ch = __ldg(p.fwd.chunks + c0 + (wk - c0) / p.ntiles);
                 const int uoff = ((wk - c0) % p.ntiles) * kTileUtts + lane * 4;
                 if (uoff < U4) {  // (lanes beyond the batch stay converged for the next pull)
-                    FwdFin<T, SR> fin{p, p.alpha + size_t(n > 0 ? n - 1 : 0) * frame, p.alpha + size_t(n) * frame,
+                    FwdFin<T, SR> fin{p, p.alpha + size_t(n > 0 ? n - 1 : 0) * frame_q, p.alpha + size_t(n) * frame_q,
                                       p.part + size_t(n & 1) * p.n_slots * U4, p.E + size_t(n) * p.Dh * U4, uoff,
-                                      s_shift, s_key};
+                                      s_shift};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) fin.mx[j] = neg_inf<T>();
                     if (n == 0) {
                         for (int i = ch.z; i < ch.w; ++i) {
-                            const int4 it = __ldg(p.fwd.items + i);
-                            if (it.z >= 0) continue;
-                            V4<T> e = ld4_nc<T>(fin.En + size_t(it.y) * U4 + uoff);
-                            const T a0 = __ldg(p.init_dense + it.x);  // A[:,1] = α̂ ⊗ e₁  (:68)
+                            fin.prefetch(fwd_src, i);
+                            if (fin.it.z >= 0) continue;
+                            const T a0 = __ldg(p.init_dense + fin.it.x);  // A[:,1] = α̂ ⊗ e₁  (:68)
                             V4<T> acc;
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                acc.v[j] = a0 + e.v[j];
-                                atomicMax(&s_key[uoff + j], fkey(float(acc.v[j])));
+                                acc.v[j] = a0 + fin.e.v[j];
+                                fin.mx[j] = max_(fin.mx[j], acc.v[j]);
                             }
-                            st4_cg(fin.cur + size_t(it.x) * U4 + uoff, acc);
+                            st4_cg(fin.cur + size_t(fin.it.x) * U4 + uoff, acc);
+                            fin.emit_q(acc);
                         }
                     } else {
-                        stream_chunk<T, SR, SA>(fwd_src, ch, fin.prev + uoff, queue, fin);
+                        stream_chunk<T, SR, SA>(fwd_src, ch, fin.prev + uoff, ring, queue, fin);
                     }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) atomicMax(&s_key[uoff + j], fkey(float(fin.mx[j])));
                 }
                 __syncwarp();
             }
@@ -753,20 +887,24 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
             __syncthreads();
         }
         // log Z = α_{N̂}[phony final] = a + Ca   (kernel units inside, natural log out)
-        const T* last = p.alpha + size_t(p.N1 - 1) * frame + size_t(S - 1) * U4;
+        const T* last = p.alpha + size_t(p.N1 - 1) * frame_q + size_t(S - 1) * U4;
         for (int u = threadIdx.x; u < U4; u += blockDim.x) {
             T a = __ldcg(last + u);
             double z = (a == neg_inf<T>()) ? double(a) : double(a) + s_C[u];
-            s_lz[u] = z;
             int b = p.utt_b[u];
-            if (blockIdx.x == 0 && b >= 0) p.lz[b] = T(SR == SR_LOG ? z * 0.6931471805599453 : z);
+            if (blockIdx.x == 0) {
+                p.lz2[u] = z;
+                if (b >= 0) p.lz[b] = T(SR == SR_LOG ? z * 0.6931471805599453 : z);
+            }
         }
-        __syncthreads();
+        return;
     }
-    if (!p.do_bwd) return;
 
     // ---------------------------------------------------------------- backward (βrecursion + γ)
-    for (int u = threadIdx.x; u < U4; u += blockDim.x) { s_C[u] = 0.0; s_key[u] = kKeyMin; s_z[u] = T(0); }
+    for (int u = threadIdx.x; u < U4; u += blockDim.x) {
+        s_C[u] = 0.0; s_key[u] = kKeyMin; s_z[u] = T(0);
+        s_lz[u] = p.do_post ? p.lz2[u] : 0.0;
+    }
     __syncthreads();
     const int c0 = p.bwd.cta_chunks[blockIdx.x], c1 = p.bwd.cta_chunks[blockIdx.x + 1];
     const int work1 = c0 + (c1 - c0) * p.ntiles;
@@ -797,18 +935,28 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
             const int uoff = ((wk - c0) % p.ntiles) * kTileUtts + lane * 4;
             if (uoff < U4) {
                 BwdFin<T, SR> fin{p, p.bt + size_t((n + 1) & 1) * frame, p.bt + size_t(n & 1) * frame,
-                                  p.E + size_t(n) * p.Dh * U4, p.alpha + size_t(n) * frame, n, uoff,
-                                  s_shift, s_g, s_z, s_key};
+                                  p.E + size_t(n) * p.Dh * U4, p.alpha + size_t(n) * frame_q, n, uoff,
+                                  s_shift, s_g};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { fin.mx[j] = neg_inf<T>(); fin.zs[j] = T(0); }
                 if (n == p.N1 - 1) {
                     for (int i = ch.z; i < ch.w; ++i) {
-                        fin.prefetch(i);
+                        fin.prefetch(bwd_src, i);
                         V4<T> beta;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) beta.v[j] = T(0);  // B[:,end] = 1̄  (:104)
                         fin.finish(beta);
                     }
                 } else {
-                    stream_chunk<T, SR, SA>(bwd_src, ch, fin.bt_next + uoff, queue, fin);
+                    stream_chunk<T, SR, SA>(bwd_src, ch, fin.bt_next + uoff, ring, queue, fin);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (n > 0) atomicMax(&s_key[uoff + j], fkey(float(fin.mx[j])));
+                    if (p.do_post && fin.zs[j] > T(0)) {
+                        if (SR == SR_LOG) atomicAdd(&s_z[uoff + j], fin.zs[j]);
+                        else red_max1(&s_z[uoff + j], fin.zs[j]);
+                    }
                 }
             }
             __syncwarp();
@@ -1081,14 +1229,14 @@ template <typename T> __global__ void total_kernel(const T* zsum, const T* lz, T
 // grid (ceil(S/32), ceil(U4/32), N1), block (32, 8)
 // ================================================================================================
 template <typename T>
-__global__ void unpack_states_kernel(const T* src, int S, int U4, const int* utt_b,
+__global__ void unpack_states_kernel(const T* src, int S, int S_src /* rows per source frame */, int U4, const int* utt_b,
                                      const long long* utt_off, const double* C /* [N1][U4] */, double unit, T* dst,
                                      long long total) {
     __shared__ T tile[32][33];
     const int n = blockIdx.z, s0 = blockIdx.x * 32, u0 = blockIdx.y * 32;
     for (int k = threadIdx.y; k < 32; k += 8) {
         int s = s0 + k, u = u0 + threadIdx.x;
-        if (s < S && u < U4) tile[k][threadIdx.x] = src[(size_t(n) * S + s) * U4 + u];
+        if (s < S && u < U4) tile[k][threadIdx.x] = src[(size_t(n) * S_src + s) * U4 + u];
     }
     __syncthreads();
     for (int k = threadIdx.y; k < 32; k += 8) {

@@ -104,6 +104,7 @@ struct DirDev {
     void *pw = nullptr, *arcs = nullptr;  // arcs: un-padded Arc<T> holding w - R in kernel units
     unsigned char* qflags = nullptr;
     int cache_cap = 0;  // largest per-CTA range of padded arcs (multiple of 4)
+    int cache_items = 0;  // largest per-CTA number of items
     double R = 0;       // bound on the ⊕ exponents, kernel units
     void release() {
         cudaFree(items); cudaFree(chunks); cudaFree(item_arcs); cudaFree(cta_chunks); cudaFree(pidx);
@@ -123,6 +124,7 @@ struct mk_graph {
     int4* d_fwd_long = nullptr;
     void *d_fwd_long_arcs = nullptr, *d_init_dense_s = nullptr;
     int n_long = 0, n_slots = 0;
+    int n_runs = 0;  // merged runs: the forward vector has Ŝ + n_runs rows
     size_t bytes = 0;
     ~mk_graph() {
         cudaFree(d_in_ptr); cudaFree(d_out_ptr); cudaFree(d_pdf);
@@ -154,19 +156,28 @@ template <typename T> struct DirHost {
     std::vector<int> cta_chunks, pidx;
     std::vector<T> pw;
     std::vector<unsigned char> qflags;
-    int cache_cap = 0;
+    int cache_cap = 0, cache_items = 0;
 };
 
+// gflags[r] (kernels.cuh, item.w): run bookkeeping of row merging.  `tied[r]` = row r must stay in the
+// same chunk as row r-1 (a non-first member of a run).  Backward (`reuse` rows): a tied row owns no
+// arcs, it reuses the ⊕ of the run's first row.
 template <typename T>
 static void build_plan(const std::vector<int>& ptr, const std::vector<Arc<T>>& arcs, const std::vector<int>& pdf,
-                       int S, int n_ctas, bool split, DirHost<T>& d, std::vector<int4>& long_rows,
-                       std::vector<Arc<T>>& long_arcs, int& n_slots) {
+                       int S, int n_ctas, bool split, const std::vector<int>& gflags, const std::vector<char>& tied,
+                       bool reuse, DirHost<T>& d, std::vector<int4>& long_rows, std::vector<Arc<T>>& long_arcs,
+                       int& n_slots) {
     const T ninf = -std::numeric_limits<T>::infinity();
     n_slots = 0;
     for (int r = 0; r < S; ++r) {
         const int beg = ptr[r], end = ptr[r + 1], deg = end - beg;
+        if (reuse && tied[r]) {  // β of this row = β of the run's first row
+            d.items.push_back(make_int4(r, pdf[r], -1, gflags[r]));
+            d.item_arcs.push_back(make_int2(beg, beg));
+            continue;
+        }
         if (!split || deg <= kLongRow) {
-            d.items.push_back(make_int4(r, pdf[r], -1, 0));
+            d.items.push_back(make_int4(r, pdf[r], -1, gflags[r]));
             d.item_arcs.push_back(make_int2(beg, end));
             continue;
         }
@@ -199,6 +210,7 @@ static void build_plan(const std::vector<int>& ptr, const std::vector<Arc<T>>& a
             acc += c;
             ++i;
         }
+        while (i < n_items && tied[d.items[i].x] && d.items[i].z < 0) ++i;  // never cut a run
         cta_items[k] = i;
     }
     d.cta_chunks.assign(n_ctas + 1, 0);
@@ -208,15 +220,26 @@ static void build_plan(const std::vector<int>& ptr, const std::vector<Arc<T>>& a
         const size_t first = d.chunks.size();
         const int cta_arc0 = int(d.pidx.size());
         int cb = cta_items[k], n_arcs = 0, pb = int(d.pidx.size());
+        // guided self-scheduling: chunks shrink from ~2x the target to 1/4 of it along the CTA's work, so
+        // that the last chunks pulled (they are sorted largest first) are small and the frame ends evenly
+        double cta_total = 0, done = 0;
+        for (int it = cta_items[k]; it < cta_items[k + 1]; ++it) cta_total += std::max(1, d.item_arcs[it].y - d.item_arcs[it].x);
         for (int it = cta_items[k]; it < cta_items[k + 1]; ++it) {
             const int2 ar = d.item_arcs[it];
-            for (int a = ar.x; a < ar.y; ++a) emit(arcs[a].idx, arcs[a].w);
-            if (ar.y == ar.x) emit(0, ninf);  // an empty row still owns one (pad) arc
-            const size_t last = d.pidx.size() - 1;
-            if (d.qflags.size() <= last / 4) d.qflags.resize(last / 4 + 1, 0);
-            d.qflags[last / 4] |= (unsigned char)(1u << (last % 4));
-            n_arcs += std::max(1, ar.y - ar.x);
-            if (n_arcs >= chunk_target || it + 1 == cta_items[k + 1]) {
+            const bool owns_arcs = !(reuse && tied[d.items[it].x]);
+            if (owns_arcs) {
+                for (int a = ar.x; a < ar.y; ++a) emit(arcs[a].idx, arcs[a].w);
+                if (ar.y == ar.x) emit(0, ninf);  // an empty row still owns one (pad) arc
+                const size_t last = d.pidx.size() - 1;
+                if (d.qflags.size() <= last / 4) d.qflags.resize(last / 4 + 1, 0);
+                d.qflags[last / 4] |= (unsigned char)(1u << (last % 4));
+                n_arcs += std::max(1, ar.y - ar.x);
+            }
+            const bool next_tied = it + 1 < cta_items[k + 1] && tied[d.items[it + 1].x] && d.items[it + 1].z < 0;
+            const double frac = cta_total > 0 ? done / cta_total : 1.0;
+            const int target = std::max(8, int(chunk_target * (2.0 - 1.75 * frac)));
+            if ((n_arcs >= target && !next_tied) || it + 1 == cta_items[k + 1]) {
+                done += n_arcs;
                 while (d.pidx.size() % 4) emit(0, ninf);
                 d.chunks.push_back(make_int4(pb, int(d.pidx.size()), cb, it + 1));
                 cb = it + 1;
@@ -228,6 +251,7 @@ static void build_plan(const std::vector<int>& ptr, const std::vector<Arc<T>>& a
                          [](const int4& x, const int4& y) { return x.y - x.x > y.y - y.x; });
         d.cta_chunks[k + 1] = int(d.chunks.size());
         d.cache_cap = std::max(d.cache_cap, int(d.pidx.size()) - cta_arc0);
+        d.cache_items = std::max(d.cache_items, cta_items[k + 1] - cta_items[k]);
     }
     d.qflags.resize(d.pidx.size() / 4 + 1, 0);
 }
@@ -242,6 +266,7 @@ template <typename T> static int upload_plan(const DirHost<T>& hst, const std::v
     TRY(upload(hst.qflags, (void**)&dev.qflags));
     TRY(upload(arcs, &dev.arcs));
     dev.cache_cap = hst.cache_cap;
+    dev.cache_items = hst.cache_items;
     return MK_OK;
 }
 
@@ -325,6 +350,55 @@ static int build_graph(mk_graph* g, const int64_t* colptr, const int64_t* rowval
         if (s < 0 || s >= S) return fail(MK_EINVAL, "init_idx[%lld] out of range", (long long)k);
         init[s] = init_w[k];
     }
+    // Row merging: runs of adjacent states with bit-identical out-arc lists (the A/B state pairs of
+    // the chain topology: same successors, same weights).  Backward: β is computed once per run and
+    // reused by the other members.  Forward: the members' mass reaches their common successors through
+    // ONE virtual source q_g = ⊕_{i in run} a[i] (row Ŝ + g of the forward vector), produced by the warp
+    // that finalises the run — so every such successor row loses |run| - 1 in-arcs.  MK_NO_MERGE=1 disables.
+    std::vector<int> grp(S, -1);
+    std::vector<char> tied(S, 0), run_last(S, 0);
+    int n_runs = 0, max_run = 1;
+    if (!(getenv("MK_NO_MERGE") && atoi(getenv("MK_NO_MERGE")))) {
+        auto same_row = [&](int x, int y) {
+            const int n = out_ptr[x + 1] - out_ptr[x];
+            if (n == 0 || n != out_ptr[y + 1] - out_ptr[y]) return false;
+            return std::memcmp(&out_arcs[out_ptr[x]], &out_arcs[out_ptr[y]], size_t(n) * sizeof(Arc<T>)) == 0;
+        };
+        for (int i = 0; i + 1 < S;) {
+            int j = i + 1;
+            while (j < S && j - i < 8 && same_row(i, j)) ++j;
+            bool ok = j - i >= 2;
+            for (int k = i; ok && k < j; ++k) ok = in_ptr[k + 1] - in_ptr[k] <= kLongRow;  // segments cannot join a run
+            if (!ok) { ++i; continue; }
+            for (int k = i; k < j; ++k) { grp[k] = n_runs; tied[k] = k > i; }
+            run_last[j - 1] = 1;
+            max_run = std::max(max_run, j - i);
+            ++n_runs;
+            i = j;
+        }
+    }
+    g->n_runs = n_runs;
+    // forward in-arcs with the runs' members replaced by their virtual source
+    std::vector<int> in_ptr_m(S + 1, 0);
+    std::vector<Arc<T>> in_arcs_m;
+    in_arcs_m.reserve(nnz);
+    for (int j = 0; j < S; ++j) {
+        for (int a = in_ptr[j]; a < in_ptr[j + 1]; ++a) {
+            const int i = in_arcs[a].idx;
+            if (grp[i] < 0) in_arcs_m.push_back(in_arcs[a]);
+            else if (!tied[i]) { Arc<T> m = in_arcs[a]; m.idx = S + grp[i]; in_arcs_m.push_back(m); }
+        }
+        in_ptr_m[j + 1] = int(in_arcs_m.size());
+    }
+    // item flags (kernels.cuh): forward  bit0 = run member, bit1 = first, bit2 = last, bits 4.. = run index;
+    //                           backward bit0 = reuse the previous item's ⊕
+    std::vector<int> gf_fwd(S, 0), gf_bwd(S, 0);
+    for (int s = 0; s < S; ++s)
+        if (grp[s] >= 0) {
+            gf_fwd[s] = 1 | (tied[s] ? 0 : 2) | (run_last[s] ? 4 : 0) | (grp[s] << 4);
+            gf_bwd[s] = tied[s] ? 1 : 0;
+        }
+
     // Bounds for the single-pass ⊕ (kernels.cuh): stored a_n <= max(log max column-sum, max α̂),
     // stored b_n ⊗ e' <= max(log max row-sum, 0); every exponent v + (w - R) is then <= 0.
     double R_f = 0, R_b = 0;
@@ -334,7 +408,7 @@ static int build_graph(mk_graph* g, const int64_t* colptr, const int64_t* rowval
         for (int64_t a = 0; a < nnz; ++a) wmax = std::max(wmax, double(in_arcs[a].w));
         for (int64_t k = 0; k < n_init; ++k) li = std::max(li, double(init_w[k]));
         if (wmax > ninf_d && wmax < std::numeric_limits<double>::infinity()) {
-            double vf = std::max(max_row_logsum<T>(in_ptr, in_arcs, S), li);
+            double vf = std::max(max_row_logsum<T>(in_ptr, in_arcs, S), li) + std::log(double(max_run));  // q_g <= max + log|run|
             double vb = std::max(max_row_logsum<T>(out_ptr, out_arcs, S), 0.0);
             if (!(vf > ninf_d)) vf = 0;
             R_f = vf + wmax;
@@ -343,7 +417,7 @@ static int build_graph(mk_graph* g, const int64_t* colptr, const int64_t* rowval
     }
     // the shared-graph kernel works in log2 units for the Log semiring
     const double unit = g->semiring == MK_LOG ? 1.4426950408889634 : 1.0;
-    std::vector<Arc<T>> in_s(in_arcs), out_s(out_arcs);
+    std::vector<Arc<T>> in_s(in_arcs_m), out_s(out_arcs);
     for (auto& a : in_s) a.w = T((double(a.w) - R_f) * unit);
     for (auto& a : out_s) a.w = T((double(a.w) - R_b) * unit);
     std::vector<T> init_s(init);
@@ -355,8 +429,9 @@ static int build_graph(mk_graph* g, const int64_t* colptr, const int64_t* rowval
     std::vector<int4> fwd_long, no_long;
     std::vector<Arc<T>> fwd_long_arcs, no_arcs;
     int no_slots = 0;
-    build_plan<T>(in_ptr, in_s, pdf, S, g->n_sms, true, fwd, fwd_long, fwd_long_arcs, g->n_slots);
-    build_plan<T>(out_ptr, out_s, pdf, S, g->n_sms, false, bwd, no_long, no_arcs, no_slots);
+    build_plan<T>(in_ptr_m, in_s, pdf, S, g->n_sms, true, gf_fwd, tied, false, fwd, fwd_long, fwd_long_arcs,
+                  g->n_slots);
+    build_plan<T>(out_ptr, out_s, pdf, S, g->n_sms, false, gf_bwd, tied, true, bwd, no_long, no_arcs, no_slots);
     g->n_long = int(fwd_long.size());
 
     TRY(upload(in_ptr, (void**)&g->d_in_ptr));
@@ -385,7 +460,7 @@ struct Group {  // utterances sharing one graph, run by shared_fb_kernel
     bool vec4 = false;
     int* d_utt_b = nullptr;
     long long* d_utt_off = nullptr;
-    DevBuf E, emax, alpha, bt, part, gkey, coff;
+    DevBuf E, emax, alpha, bt, part, gkey, coff, lz2;
 };
 
 struct mk_batch {
@@ -411,7 +486,7 @@ struct mk_batch {
         for (auto& gr : groups) {
             cudaFree(gr.d_utt_b); cudaFree(gr.d_utt_off);
             gr.E.release(); gr.alpha.release(); gr.bt.release();
-            gr.part.release(); gr.gkey.release(); gr.coff.release(); gr.emax.release();
+            gr.part.release(); gr.gkey.release(); gr.coff.release(); gr.emax.release(); gr.lz2.release();
         }
         DevBuf* all[] = {&small_descs, &small_alpha, &small_ca, &zsum, &lz, &seqlens, &barrier, &trace,
                          &h_ll, &h_post, &h_logz, &h_path};
@@ -450,14 +525,16 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
                          int Dout, int Tout, const int* d_seqlens) {
     mk_graph* g = gr.g;
     const int S = int(g->S), U4 = gr.U4;
-    const size_t frame = size_t(S) * U4 * sizeof(T);
-    if (size_t(S) * U4 >= (size_t(1) << 31)) return fail(MK_ENOTSUP, "Ŝ*U exceeds 2^31 in one group");
+    const int Sq = S + g->n_runs;  // rows of the forward vector: states + merged-run sources
+    const size_t frame = size_t(S) * U4 * sizeof(T), frame_q = size_t(Sq) * U4 * sizeof(T);
+    if (size_t(Sq) * U4 >= (size_t(1) << 31)) return fail(MK_ENOTSUP, "Ŝ*U exceeds 2^31 in one group");
     TRY(gr.E.ensure(size_t(N1) * Dh * U4 * sizeof(T)));
-    TRY(gr.alpha.ensure(size_t(N1) * frame));
+    TRY(gr.alpha.ensure(size_t(N1) * frame_q));
     if (mode == MODE_POST || mode == MODE_BETA) TRY(gr.bt.ensure(2 * frame));
     TRY(gr.part.ensure(2 * size_t(std::max(g->n_slots, 1)) * U4 * sizeof(T)));
     TRY(gr.gkey.ensure(2 * size_t(N1) * U4 * sizeof(int)));
     TRY(gr.emax.ensure(size_t(N1) * U4 * sizeof(T)));
+    TRY(gr.lz2.ensure(size_t(U4) * sizeof(double)));
     TRY(gr.coff.ensure(2 * size_t(N1) * U4 * sizeof(double)));
 
     EmisParams<T> ep;
@@ -478,7 +555,7 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     }
 
     SharedParams<T> p;
-    p.S = S; p.Dh = Dh; p.N1 = N1; p.U4 = U4; p.ntiles = (U4 + kTileUtts - 1) / kTileUtts;
+    p.S = S; p.Sq = Sq; p.Dh = Dh; p.N1 = N1; p.U4 = U4; p.ntiles = (U4 + kTileUtts - 1) / kTileUtts;
     auto plan = [](const DirDev& d) {
         DirPlan<T> q;
         q.items = d.items; q.item_arcs = d.item_arcs; q.chunks = d.chunks; q.cta_chunks = d.cta_chunks;
@@ -492,6 +569,7 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     p.n_slots = g->n_slots; p.part = static_cast<T*>(gr.part.p);
     p.init_dense = static_cast<const T*>(g->d_init_dense_s);
     p.emax = static_cast<const T*>(gr.emax.p);
+    p.lz2 = static_cast<double*>(gr.lz2.p);
     p.gkey = static_cast<int*>(gr.gkey.p); p.Coff = static_cast<double*>(gr.coff.p);
     p.E = static_cast<const T*>(gr.E.p);
     p.alpha = static_cast<T*>(gr.alpha.p);
@@ -511,33 +589,39 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
             p.post_vec4 = (gr.vec4 && bt->B % 4 == 0 && (reinterpret_cast<uintptr_t>(c.out0) & 15) == 0) ? 1 : 0;
             break;
     }
-    CK(cudaMemsetAsync(bt->barrier.p, 0, sizeof(unsigned), c.stream));
     void* args[] = {&p};
-    size_t smem = shared_scalars_bytes(U4, sizeof(T)) + size_t(kSharedWarps) * kQueue * 128 * sizeof(T);
-    // shared-memory arc caches (both directions) when they fit next to the scalars and queues
-    p.cache_f = p.cache_b = 0;
-    {
-        size_t need = arc_cache_bytes(g->fwd.cache_cap, sizeof(T)) + arc_cache_bytes(g->bwd.cache_cap, sizeof(T));
-        if (smem + need <= bt->max_smem_optin) {
-            p.cache_f = g->fwd.cache_cap;
-            p.cache_b = g->bwd.cache_cap;
-            smem += need;
-        }
-    }
-    void (*kern)(SharedParams<T>) = shared_fb_kernel<T, SR, false>;
-    if (p.cache_f > 0) kern = shared_fb_kernel<T, SR, true>;
+    const size_t scal = shared_scalars_bytes(U4, sizeof(T)) + size_t(kSharedWarps) * (kQueue + RingOf<T>::rows) * 128 * sizeof(T);
     const int slot = bt->prof_n % mk_batch::kProfRing;
     if (bt->profile) CK(cudaEventRecord(bt->ev0[slot], c.stream));
-    if (smem > 48 * 1024)
-        CK(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    CK(cudaLaunchCooperativeKernel((void*)kern, dim3(g->n_sms), dim3(kSharedThreads), args, smem, c.stream));
-    ++g_launches;
+    for (int phase = 0; phase < 2; ++phase) {
+        if (phase == 0 ? !p.do_fwd : !p.do_bwd) continue;
+        const DirDev& dd = phase == 0 ? g->fwd : g->bwd;
+        // shared-memory arc cache of this sweep when it fits next to the scalars, queues and rings
+        size_t smem = scal;
+        const size_t need = arc_cache_bytes(dd.cache_cap, dd.cache_items, sizeof(T));
+        const bool sa = smem + need <= bt->max_smem_optin;
+        p.cache_f = p.cache_b = p.cache_items_f = p.cache_items_b = 0;
+        if (sa) {
+            smem += need;
+            if (phase == 0) { p.cache_f = dd.cache_cap; p.cache_items_f = dd.cache_items; }
+            else { p.cache_b = dd.cache_cap; p.cache_items_b = dd.cache_items; }
+        }
+        void (*kern)(SharedParams<T>) =
+            phase == 0 ? (sa ? shared_fb_kernel<T, SR, true, 0> : shared_fb_kernel<T, SR, false, 0>)
+                       : (sa ? shared_fb_kernel<T, SR, true, 1> : shared_fb_kernel<T, SR, false, 1>);
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        CK(cudaMemsetAsync(bt->barrier.p, 0, sizeof(unsigned), c.stream));
+        CK(cudaLaunchCooperativeKernel((void*)kern, dim3(g->n_sms), dim3(kSharedThreads), args, smem, c.stream));
+        ++g_launches;
+    }
     if (bt->profile) { CK(cudaEventRecord(bt->ev1[slot], c.stream)); ++bt->prof_n; }
 
     if (mode == MODE_ALPHA || mode == MODE_BETA) {
         dim3 ug((S + 31) / 32, (U4 + 31) / 32, N1), ub(32, 8);
         const double* C = static_cast<const double*>(gr.coff.p) + (mode == MODE_BETA ? size_t(N1) * U4 : 0);
-        unpack_states_kernel<T><<<ug, ub, 0, c.stream>>>(static_cast<const T*>(gr.alpha.p), S, U4, gr.d_utt_b,
+        unpack_states_kernel<T><<<ug, ub, 0, c.stream>>>(static_cast<const T*>(gr.alpha.p), S,
+                                                        mode == MODE_BETA ? S : Sq, U4, gr.d_utt_b,
                                                         gr.d_utt_off, C, SR == SR_LOG ? 0.6931471805599453 : 1.0,
                                                         static_cast<T*>(c.out0), bt->total);
         CK(cudaGetLastError());
@@ -659,7 +743,7 @@ template <typename T, int SR> static int run(mk_batch* bt, Mode mode, const Call
             for (size_t k = 0; k < gr.utts.size(); ++k) {
                 TraceDesc<T> d;
                 d.in_ptr = gr.g->d_in_ptr; d.in_arcs = static_cast<const Arc<T>*>(gr.g->d_in_arcs);
-                d.base = (long long)k; d.sn = (long long)gr.g->S * gr.U4; d.ss = gr.U4;
+                d.base = (long long)k; d.sn = (long long)(gr.g->S + gr.g->n_runs) * gr.U4; d.ss = gr.U4;
                 d.S = int(gr.g->S); d.b = gr.utts[k];
                 descs.push_back(d);
             }
@@ -871,6 +955,17 @@ int mk_batch_info(const mk_batch* b, int64_t* B, int64_t* total_states_hat) {
 }
 
 int64_t mk_batch_workspace_bytes(const mk_batch* b) { return b ? int64_t(b->ws_bytes()) : 0; }
+
+#ifdef MK_PROFILE_BARRIER
+// debug: per-CTA cycle counters of grid_sync (work, CTA wait, grid wait); resets after reading
+int mk_debug_barrier_profile(unsigned long long* out /* [148*4] */) {
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(out, g_prof, sizeof(unsigned long long) * 148 * 4));
+    static unsigned long long zeros[148 * 4];
+    CK(cudaMemcpyToSymbol(g_prof, zeros, sizeof zeros));
+    return MK_OK;
+}
+#endif
 
 int mk_batch_profile(mk_batch* b, int enable) {
     if (!b) return fail(MK_EINVAL, "null batch");

@@ -218,6 +218,49 @@ def test_denominator_vs_oracle(torch, mm, orc, dtype, force):
     check_posteriors(mm, orc, [g] * B, D, V, lens, post, ttl, dtype)
 
 
+def test_row_merging_is_transparent(torch, mm, orc):
+    """The graph compiler merges runs of adjacent states with identical out-arc lists (the A/B pairs of
+    the chain topology).  With and without merging (MK_NO_MERGE=1) the results agree with each other
+    and with the oracle — posteriors, α, β and the tropical best path (bit-exact)."""
+    rng = np.random.default_rng(77)
+    B, T, D = 9, 35, 200
+    V = (rng.standard_normal((B, T, D)) * 2).astype(np.float32)
+    lens = rng.integers(T // 2, T + 1, B).astype(np.int32)
+    out = {}
+    for merge in (True, False):
+        old = os.environ.get("MK_NO_MERGE")
+        os.environ["MK_NO_MERGE"] = "0" if merge else "1"
+        try:
+            K = mm.LogSemiring[np.float32]
+            g = mm.graphs.denominator(K, n_tokens=1300, n_pdf=D, seed=11)
+            b = gpu_batch(mm, [g] * B, D, "shared")
+            post, ttl = mm.pdfposteriors(b, dev(torch, V), seqlengths=lens)
+            check_posteriors(mm, orc, [g] * B, D, V, lens, post, ttl, np.float32)
+            A = mm.αrecursion(b, dev(torch, V), seqlengths=lens).cpu().numpy()
+            Bm = mm.βrecursion(b, dev(torch, V), seqlengths=lens).cpu().numpy()
+            Kt = mm.TropicalSemiring[np.float32]
+            gt = (g[0].astype(Kt), g[1])
+            bt = gpu_batch(mm, [gt] * B, D, "shared")
+            path, score = mm.bestpath(bt, dev(torch, V), seqlengths=lens)
+            opath, oscore = orc.bestpath(orc_graphs(orc, [gt] * B, D), V, lens)
+            np.testing.assert_array_equal(path.cpu().numpy(), opath)
+            np.testing.assert_array_equal(score.cpu().numpy(), oscore)
+            out[merge] = (post.cpu().numpy(), ttl.cpu().numpy(), A, Bm)
+        finally:
+            if old is None:
+                os.environ.pop("MK_NO_MERGE", None)
+            else:
+                os.environ["MK_NO_MERGE"] = old
+    np.testing.assert_allclose(out[True][1], out[False][1], rtol=1e-6)
+    np.testing.assert_allclose(out[True][0], out[False][0], rtol=1e-4, atol=1e-7)
+    assert_states_close(out[True][2], out[False][2], np.float32)
+    assert_states_close(out[True][3], out[False][3], np.float32)
+    og = orc_graphs(orc, [g], D)[0]
+    oA, oB = orc.alpha_beta(og, V[0], lens[0])
+    assert_states_close(out[True][2][:g[0].nstates_hat], oA, np.float32)
+    assert_states_close(out[True][3][:g[0].nstates_hat], oB, np.float32)
+
+
 def test_mixed_batch_vs_oracle(torch, mm, orc):
     """One batch holding the replicated denominator (shared-graph kernel, interleaved utterance
     indices) and distinct small graphs (per-utterance kernel)."""

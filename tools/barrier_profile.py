@@ -1,0 +1,29 @@
+# SPDX-License-Identifier: MIT
+"""Debug (library built with MK_PROFILE_BARRIER=1): where do CTAs spend a frame — working, waiting for
+their own warps, or waiting for the grid?"""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import markov_b200 as mm
+B, T, D = 128, 150, 3000
+K = mm.LogSemiring[np.float32]
+fsm, pdf = mm.graphs.denominator(K)
+c = mm.compile(fsm, mm.statemap(fsm, D, pdf)); b = mm.batch(*[c] * B)
+V = (torch.randn((B, T, D), device="cuda") * 2).permute(0, 2, 1)
+post = torch.empty((T, D, B), device="cuda"); ttl = torch.empty((B,), device="cuda")
+lib = C.CDLL(mm._lib.LIB_PATH)
+buf = (C.c_ulonglong * (148 * 4))()
+mm.pdfposteriors(b, V, out=(post, ttl)); lib.mk_debug_barrier_profile(buf)
+mm.pdfposteriors(b, V, out=(post, ttl)); lib.mk_debug_barrier_profile(buf)
+a = np.array(buf[:], np.float64).reshape(148, 4)
+nb = 2 * (T + 1)
+print("per barrier interval, cycles (mean over CTAs / min / max):")
+for k, name in enumerate(["thread0 work since last barrier", "thread0 waits for its CTA", "CTA waits for the grid"]):
+    x = a[:, k] / nb
+    print(f"  {name:34s} {x.mean():9.0f} {x.min():9.0f} {x.max():9.0f}")
+tot = a[:, :3].sum(1) / nb
+print("  total per frame", tot.mean(), "cycles =", tot.mean() / 1.965e3, "us")
+x = a[:, 3] / nb / 12
+print(f"  drain/finalise cycles per warp per frame  {x.mean():9.0f} {x.min():9.0f} {x.max():9.0f}")
+w = a[:, 0] + a[:, 1]
+print("  busy (work + CTA wait) spread: min %.0f max %.0f  (max/mean %.2f)" % ((w / nb).min(), (w / nb).max(), w.max() / w.mean()))
