@@ -175,7 +175,8 @@ template <int SR, typename T> __device__ __forceinline__ T lin_add(T a, T b) {
 // stores are ordered by bar.sync + fence + the atomic; the waiting thread uses an acquire load
 // and every consumer then reads other CTAs' data with L1-bypassing loads only (ld4_cg).
 #ifdef MK_PROFILE_BARRIER
-__device__ unsigned long long g_prof[148 * 4];  // per CTA: cycles before arriving, cycles waiting, ...
+__device__ unsigned long long g_prof[148 * 4];
+__device__ unsigned long long g_redo;  // exact-fallback events  // per CTA: cycles before arriving, cycles waiting, ...
 #endif
 __device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& target) {
 #ifdef MK_PROFILE_BARRIER
@@ -323,18 +324,21 @@ __device__ __noinline__ void row_reduce_slow(const Arc<T>* arcs, int beg, int en
 // for an utterance whose emission is alive is redone with the exact two-pass row_reduce (which
 // also recognises a genuinely dead row).
 template <typename T, int SR>
-__device__ __forceinline__ V4<T> resolve_sum(const V4<T>& acc, const V4<T>& e, bool need_all, const DirPlan<T>& pl,
-                                             int item, const T* vec, int U4, int uoff) {
+__device__ __forceinline__ V4<T> resolve_sum(const V4<T>& acc, const V4<T>& e, bool need_all, bool dead,
+                                             const DirPlan<T>& pl, int item, const T* vec, int U4, int uoff) {
     V4<T> val;
     if (SR == SR_TROP) return acc;
-    const T tiny = T(1e-30);
+    const T tiny = sizeof(T) == 4 ? T(1e-30) : T(1e-280);  // (the bound sits at 2^100 / 2^900, see build_graph)
     bool redo = false;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         val.v[j] = lg2_(acc.v[j]) + pl.R;  // acc == 0 -> -Inf
         redo |= (acc.v[j] < tiny) && (need_all || e.v[j] != neg_inf<T>());
     }
-    if (redo) {
+    if (redo && !dead) {  // (a statically dead row: the all-zero sum is exact)
+#ifdef MK_PROFILE_BARRIER
+        if ((threadIdx.x & 31) == 0) atomicAdd(&g_redo, 1ull);
+#endif
         const int2 ar = __ldg(pl.item_arcs + item);
         if (ar.y > ar.x) {
             T ex[4];
@@ -465,6 +469,10 @@ __device__ __forceinline__ void stream_chunk(const ArcSrc<T, SA>& src, const int
     int item = ch.z;
     fin.warm(src, ch.z, ch.w);
     fin.prefetch(src, item);
+    while (item < ch.w && fin.is_passive()) {  // leading items without arcs
+        fin.passive();
+        if (++item < ch.w) fin.prefetch(src, item);
+    }
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
         if (g < nq) quad_issue<T, SA>(ring + g * 4 * SLOT, src, ch.x + g * 4, vec_lane);
@@ -506,8 +514,8 @@ __device__ __forceinline__ void stream_chunk(const ArcSrc<T, SA>& src, const int
             const V4<T> r = lds_row(queue + unsigned(k) * SLOT, T());
             fin(item, r);
             if (++item < ch.w) fin.prefetch(src, item);
-            while (item < ch.w && fin.is_reuse()) {  // rows of a merged run reuse the ⊕ just resolved
-                fin.reuse();
+            while (item < ch.w && fin.is_passive()) {  // items without arcs (merged-run members, dead rows)
+                fin.passive();
                 if (++item < ch.w) fin.prefetch(src, item);
             }
         }
@@ -565,6 +573,7 @@ template <typename T> struct SharedParams {
     double* lz2;       // [U4] the same in kernel units, handed from the forward to the backward launch
     unsigned* barrier;
     int do_fwd, do_bwd, do_post;
+    int bwd_dead_ok;   // the library applied `expand`: co-unreachable rows have β = 0̄ before the last frame
 };
 
 template <typename T> __device__ __forceinline__ V4<T> ld4_nc(const T* p);
@@ -631,9 +640,9 @@ template <typename T, int SR> struct FwdFin {
     template <class Src> __device__ __forceinline__ void warm(const Src& src, int i0, int i1) {
         for (int i = i0; i < i1; ++i) prefetch_l1(En + size_t(src.item(i).y) * p.U4 + uoff);
     }
-    __device__ __forceinline__ bool is_reuse() const { return false; }
-    __device__ __forceinline__ void reuse() {}
-    // Row merging: item.w bit0 = member of a run, bit1 = first, bit2 = last, bits 4.. = run index g.  The
+    __device__ __forceinline__ bool is_passive() const { return false; }
+    __device__ __forceinline__ void passive() {}
+    // Row merging: item.w bit0 = member of a run, bit1 = first, bit2 = last, bits 8.. = run index g.  The
     // run's virtual source q_g = ⊕_members a (row Ŝ + g of this frame's vector) feeds the members' common
     // successors in the next frame.
     __device__ __forceinline__ void emit_q(const V4<T>& val) {
@@ -649,10 +658,11 @@ template <typename T, int SR> struct FwdFin {
                 qacc.v[j] = (m == neg_inf<T>()) ? m : m + lg2_(T(1) + ex2_(d));
             }
         }
-        if (it.w & 4) st4_cg(cur + size_t(p.S + (it.w >> 4)) * p.U4 + uoff, qacc);
+        if (it.w & 4) st4_cg(cur + size_t(p.S + (it.w >> 8)) * p.U4 + uoff, qacc);
     }
     __device__ __forceinline__ void operator()(int item, const V4<T>& acc) {
-        V4<T> val = resolve_sum<T, SR>(acc, e, false, p.fwd, item, prev, p.U4, uoff);  // T̂ᵀ A[:,n-1] (:70)
+        // item.w bit3: no initial state reaches this row — α = 0̄ in every frame; bit4: the row has no arcs
+        V4<T> val = resolve_sum<T, SR>(acc, e, false, it.w & 24, p.fwd, item, prev, p.U4, uoff);  // T̂ᵀ A[:,n-1] (:70)
         if (it.z >= 0) {  // segment of a long row: partial ⊕ only
             st4_cg(part + size_t(it.z) * p.U4 + uoff, val);
             return;
@@ -676,8 +686,9 @@ template <typename T, int SR> struct BwdFin {
     int4 it;     // the item being streamed, its emissions and α, requested when the item starts
     V4<T> e, a;
     V4<T> last;  // b_n of the last item that owned arcs: rows of a merged run share it (item.w bit0)
-    __device__ __forceinline__ bool is_reuse() const { return it.w & 1; }
-    __device__ __forceinline__ void reuse() { finish(last); }
+    // items without arcs: rows of a merged run reuse the ⊕ just resolved (item.w bit0)
+    __device__ __forceinline__ bool is_passive() const { return it.w & 1; }
+    __device__ __forceinline__ void passive() { finish(last); }
     template <class Src> __device__ __forceinline__ void prefetch(const Src& src, int item) {
         it = src.item(item);
         e = ld4_nc<T>(En + size_t(it.y) * p.U4 + uoff);
@@ -727,7 +738,9 @@ template <typename T, int SR> struct BwdFin {
     }
     __device__ __forceinline__ void operator()(int item, const V4<T>& acc) {
         // an explicit β output needs β_n even where e_n = 0̄ kills α_n and b_n ⊗ e_n
-        V4<T> beta = resolve_sum<T, SR>(acc, e, p.beta_out != nullptr, p.bwd, item, bt_next, p.U4, uoff);  // (:106-107)
+        // item.w bit3: the phony final state is unreachable from this row — β = 0̄ (under `expand` emissions)
+        V4<T> beta = resolve_sum<T, SR>(acc, e, p.beta_out != nullptr, ((it.w & 8) && p.bwd_dead_ok) || (it.w & 16), p.bwd, item,
+                                        bt_next, p.U4, uoff);  // (:106-107)
 #pragma unroll
         for (int j = 0; j < 4; ++j) beta.v[j] -= s_shift[uoff + j];
         last = beta;

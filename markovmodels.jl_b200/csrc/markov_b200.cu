@@ -141,13 +141,19 @@ struct mk_graph {
 // balanced by arcs, and inside a CTA into chunks of ~kChunkArcs arcs that the warps pull
 // dynamically, largest first.  The arcs are re-laid out chunk by chunk into padded arrays (see
 // kernels.cuh DirPlan): every chunk spans a multiple of four arcs, every item owns >= 1 arc.
+constexpr int kItemDead = 8;    // item.w bit3 (both sweeps): statically dead row, see kernels.cuh
+constexpr int kItemEmpty = 16;  // item.w bit4 (both sweeps): the row has no arcs
+constexpr double kItemCost = 12.0;
 constexpr int kLongRow = 128;
 constexpr int kMinSegment = 64;
 constexpr int kMaxSlotsPerRow = 160;
-static int chunk_arcs() {  // target arcs per dynamically scheduled chunk (MK_CHUNK_ARCS overrides, for tuning)
+// Target cost (arcs + kItemCost per item) of a dynamically scheduled chunk: about three chunks per warp of
+// the CTA, between 48 and 160 (measured optimum for the 30k-state denominator: 160-190; small graphs want
+// more, smaller chunks).  MK_CHUNK_ARCS overrides, for tuning.
+static double chunk_cost_target(double cta_total) {
     const char* e = getenv("MK_CHUNK_ARCS");
-    int v = e ? atoi(e) : 64;
-    return v >= 4 ? v : 64;
+    if (e && atoi(e) >= 4) return atoi(e);
+    return std::min(160.0, std::max(48.0, cta_total / (3.0 * kSharedWarps)));
 }
 
 template <typename T> struct DirHost {
@@ -171,7 +177,8 @@ static void build_plan(const std::vector<int>& ptr, const std::vector<Arc<T>>& a
     n_slots = 0;
     for (int r = 0; r < S; ++r) {
         const int beg = ptr[r], end = ptr[r + 1], deg = end - beg;
-        if (reuse && tied[r]) {  // β of this row = β of the run's first row
+        if (reuse && tied[r]) {
+            // β of this row = β of the run's first row: no arcs
             d.items.push_back(make_int4(r, pdf[r], -1, gflags[r]));
             d.item_arcs.push_back(make_int2(beg, beg));
             continue;
@@ -195,7 +202,8 @@ static void build_plan(const std::vector<int>& ptr, const std::vector<Arc<T>>& a
         long_rows.push_back(make_int4(r, pseudo_beg, int(long_arcs.size()), pdf[r]));
     }
     const int n_items = int(d.items.size());
-    auto cost = [&](int i) { return double(d.item_arcs[i].y - d.item_arcs[i].x) + 2.0; };
+    // cost of an item in arc units: its arcs plus the finalise (measured ≈ 12 arcs' worth of warp time)
+    auto cost = [&](int i) { return double(d.item_arcs[i].y - d.item_arcs[i].x) + kItemCost; };
     double total = 0;
     for (int i = 0; i < n_items; ++i) total += cost(i);
     std::vector<int> cta_items(n_ctas + 1, n_items);
@@ -214,7 +222,6 @@ static void build_plan(const std::vector<int>& ptr, const std::vector<Arc<T>>& a
         cta_items[k] = i;
     }
     d.cta_chunks.assign(n_ctas + 1, 0);
-    const int chunk_target = chunk_arcs();
     auto emit = [&](int idx, T w) { d.pidx.push_back(idx); d.pw.push_back(w); };
     for (int k = 0; k < n_ctas; ++k) {
         const size_t first = d.chunks.size();
@@ -222,8 +229,9 @@ static void build_plan(const std::vector<int>& ptr, const std::vector<Arc<T>>& a
         int cb = cta_items[k], n_arcs = 0, pb = int(d.pidx.size());
         // guided self-scheduling: chunks shrink from ~2x the target to 1/4 of it along the CTA's work, so
         // that the last chunks pulled (they are sorted largest first) are small and the frame ends evenly
-        double cta_total = 0, done = 0;
-        for (int it = cta_items[k]; it < cta_items[k + 1]; ++it) cta_total += std::max(1, d.item_arcs[it].y - d.item_arcs[it].x);
+        double cta_total = 0, done = 0, n_cost = 0;
+        for (int it = cta_items[k]; it < cta_items[k + 1]; ++it) cta_total += cost(it);
+        const double chunk_target = chunk_cost_target(cta_total);
         for (int it = cta_items[k]; it < cta_items[k + 1]; ++it) {
             const int2 ar = d.item_arcs[it];
             const bool owns_arcs = !(reuse && tied[d.items[it].x]);
@@ -235,11 +243,13 @@ static void build_plan(const std::vector<int>& ptr, const std::vector<Arc<T>>& a
                 d.qflags[last / 4] |= (unsigned char)(1u << (last % 4));
                 n_arcs += std::max(1, ar.y - ar.x);
             }
+            n_cost += cost(it);
             const bool next_tied = it + 1 < cta_items[k + 1] && tied[d.items[it + 1].x] && d.items[it + 1].z < 0;
             const double frac = cta_total > 0 ? done / cta_total : 1.0;
-            const int target = std::max(8, int(chunk_target * (2.0 - 1.75 * frac)));
-            if ((n_arcs >= target && !next_tied) || it + 1 == cta_items[k + 1]) {
-                done += n_arcs;
+            const double target = std::max(2.0 * kItemCost, chunk_target * (2.0 - 1.75 * frac));
+            if ((n_cost >= target && !next_tied) || it + 1 == cta_items[k + 1]) {
+                done += n_cost;
+                n_cost = 0;
                 while (d.pidx.size() % 4) emit(0, ninf);
                 d.chunks.push_back(make_int4(pb, int(d.pidx.size()), cb, it + 1));
                 cb = it + 1;
@@ -390,14 +400,45 @@ static int build_graph(mk_graph* g, const int64_t* colptr, const int64_t* rowval
         }
         in_ptr_m[j + 1] = int(in_arcs_m.size());
     }
-    // item flags (kernels.cuh): forward  bit0 = run member, bit1 = first, bit2 = last, bits 4.. = run index;
-    //                           backward bit0 = reuse the previous item's ⊕
+    // Static trimming: a state that no initial state reaches has α = 0̄ in every frame; a state from which
+    // the phony final state cannot be reached has β = 0̄ in every frame before the last (when `expand`
+    // builds the emissions: the phony frame kills every real state).  Such rows are flagged DEAD: their
+    // all-zero ⊕ is taken at face value instead of going through the exact-fallback path every frame.
+    std::vector<char> fwd_live(S, 0), bwd_live(S, 0);
+    {
+        std::vector<int> stack;
+        for (int s = 0; s < S; ++s) if (init[s] > ninf) { fwd_live[s] = 1; stack.push_back(s); }
+        while (!stack.empty()) {
+            int s = stack.back(); stack.pop_back();
+            for (int a = out_ptr[s]; a < out_ptr[s + 1]; ++a) {
+                int t = out_arcs[a].idx;
+                if (!fwd_live[t] && out_arcs[a].w > ninf) { fwd_live[t] = 1; stack.push_back(t); }
+            }
+        }
+        bwd_live[S - 1] = 1; stack.push_back(S - 1);
+        while (!stack.empty()) {
+            int s = stack.back(); stack.pop_back();
+            for (int a = in_ptr[s]; a < in_ptr[s + 1]; ++a) {
+                int t = in_arcs[a].idx;
+                if (!bwd_live[t] && in_arcs[a].w > ninf) { bwd_live[t] = 1; stack.push_back(t); }
+            }
+        }
+    }
+    // item flags (kernels.cuh): forward  bit0 = run member, bit1 = first, bit2 = last, bits 8.. = run index;
+    //                           backward bit0 = reuse the previous item's ⊕;  both: bit3 = dead row, bit4 = no arcs
     std::vector<int> gf_fwd(S, 0), gf_bwd(S, 0);
     for (int s = 0; s < S; ++s)
         if (grp[s] >= 0) {
-            gf_fwd[s] = 1 | (tied[s] ? 0 : 2) | (run_last[s] ? 4 : 0) | (grp[s] << 4);
+            gf_fwd[s] = 1 | (tied[s] ? 0 : 2) | (run_last[s] ? 4 : 0) | (grp[s] << 8);
             gf_bwd[s] = tied[s] ? 1 : 0;
         }
+    for (int s = 0; s < S; ++s) {
+        if (!fwd_live[s]) gf_fwd[s] |= kItemDead;
+        if (!bwd_live[s]) gf_bwd[s] |= kItemDead;
+        // a row without arcs sums to 0̄ whatever the emissions are
+        if (in_ptr_m[s + 1] == in_ptr_m[s]) gf_fwd[s] |= kItemEmpty;
+        if (out_ptr[s + 1] == out_ptr[s]) gf_bwd[s] |= kItemEmpty;
+    }
 
     // Bounds for the single-pass ⊕ (kernels.cuh): stored a_n <= max(log max column-sum, max α̂),
     // stored b_n ⊗ e' <= max(log max row-sum, 0); every exponent v + (w - R) is then <= 0.
@@ -415,8 +456,13 @@ static int build_graph(mk_graph* g, const int64_t* colptr, const int64_t* rowval
             R_b = vb + wmax;
         }
     }
-    // the shared-graph kernel works in log2 units for the Log semiring
+    // the shared-graph kernel works in log2 units for the Log semiring.  The bound is placed at 2^kHeadroom
+    // rather than at 1 so that the linear sums use the whole float range: terms may be as small as
+    // 2^-100 (the underflow threshold of resolve_sum) and a row of up to 2^20 arcs still cannot overflow.
     const double unit = g->semiring == MK_LOG ? 1.4426950408889634 : 1.0;
+    const double headroom = g->semiring == MK_LOG ? (sizeof(T) == 4 ? 100.0 : 900.0) : 0.0;  // log2 units
+    R_f -= headroom / unit;
+    R_b -= headroom / unit;
     std::vector<Arc<T>> in_s(in_arcs_m), out_s(out_arcs);
     for (auto& a : in_s) a.w = T((double(a.w) - R_f) * unit);
     for (auto& a : out_s) a.w = T((double(a.w) - R_b) * unit);
@@ -580,6 +626,7 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     p.zsum = static_cast<T*>(bt->zsum.p); p.lz = static_cast<T*>(bt->lz.p);
     p.barrier = static_cast<unsigned*>(bt->barrier.p);
     p.do_fwd = p.do_bwd = p.do_post = 0;
+    p.bwd_dead_ok = c.expanded ? 0 : 1;
     switch (mode) {
         case MODE_ALPHA: case MODE_BEST: p.do_fwd = 1; break;
         case MODE_BETA: p.do_bwd = 1; p.beta_out = static_cast<T*>(gr.alpha.p); break;
@@ -963,6 +1010,8 @@ int mk_debug_barrier_profile(unsigned long long* out /* [148*4] */) {
     CK(cudaMemcpyFromSymbol(out, g_prof, sizeof(unsigned long long) * 148 * 4));
     static unsigned long long zeros[148 * 4];
     CK(cudaMemcpyToSymbol(g_prof, zeros, sizeof zeros));
+    CK(cudaMemcpyFromSymbol(out + 148 * 4, g_redo, sizeof(unsigned long long)));
+    CK(cudaMemcpyToSymbol(g_redo, zeros, sizeof(unsigned long long)));
     return MK_OK;
 }
 #endif
