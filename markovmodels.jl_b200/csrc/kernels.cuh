@@ -438,6 +438,7 @@ __device__ __forceinline__ V4<double> lds_row(unsigned saddr, double) {
 constexpr int kRingF32 = MK_RING;  // rows in flight per warp for 4-byte payloads (power of two, multiple of 4)
 template <typename T> struct RingOf { static constexpr int rows = sizeof(T) == 4 ? kRingF32 : (kRingF32 / 2 >= 8 ? kRingF32 / 2 : 8); };
 constexpr int kQueue = 4;        // finished items per drain: one quad
+constexpr int kWarmAhead = 3;    // items whose emission/α rows are prefetched into L1 ahead of their finalise
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -467,7 +468,7 @@ __device__ __forceinline__ void stream_chunk(const ArcSrc<T, SA>& src, const int
     static_assert((NG & (NG - 1)) == 0 && NG >= 2, "ring depth");
     const int nq = (ch.y - ch.x) >> 2;
     int item = ch.z;
-    fin.warm(src, ch.z, ch.w);
+    fin.warm(src, ch.z, min(ch.w, ch.z + kWarmAhead));  // L1 prefetch of the next items' emission (and α) rows
     fin.prefetch(src, item);
     while (item < ch.w && fin.is_passive()) {  // leading items without arcs
         fin.passive();
@@ -513,9 +514,11 @@ __device__ __forceinline__ void stream_chunk(const ArcSrc<T, SA>& src, const int
         for (int k = 0; k < npush; ++k) {  // the only finalise site
             const V4<T> r = lds_row(queue + unsigned(k) * SLOT, T());
             fin(item, r);
+            if (item + kWarmAhead < ch.w) fin.warm(src, item + kWarmAhead, item + kWarmAhead + 1);
             if (++item < ch.w) fin.prefetch(src, item);
-            while (item < ch.w && fin.is_passive()) {  // items without arcs (merged-run members, dead rows)
+            while (item < ch.w && fin.is_passive()) {  // items without arcs (merged-run members)
                 fin.passive();
+                if (item + kWarmAhead < ch.w) fin.warm(src, item + kWarmAhead, item + kWarmAhead + 1);
                 if (++item < ch.w) fin.prefetch(src, item);
             }
         }

@@ -147,13 +147,13 @@ constexpr double kItemCost = 12.0;
 constexpr int kLongRow = 128;
 constexpr int kMinSegment = 64;
 constexpr int kMaxSlotsPerRow = 160;
-// Target cost (arcs + kItemCost per item) of a dynamically scheduled chunk: about three chunks per warp of
-// the CTA, between 48 and 160 (measured optimum for the 30k-state denominator: 160-190; small graphs want
+// Target cost (arcs + kItemCost per item) of a dynamically scheduled chunk: about two chunks per warp of
+// the CTA, between 48 and 192 (measured optimum for the 30k-state denominator: 160-190; small graphs want
 // more, smaller chunks).  MK_CHUNK_ARCS overrides, for tuning.
 static double chunk_cost_target(double cta_total) {
     const char* e = getenv("MK_CHUNK_ARCS");
     if (e && atoi(e) >= 4) return atoi(e);
-    return std::min(160.0, std::max(48.0, cta_total / (3.0 * kSharedWarps)));
+    return std::min(192.0, std::max(48.0, cta_total / (2.0 * kSharedWarps)));
 }
 
 template <typename T> struct DirHost {
