@@ -35,9 +35,9 @@ namespace mk {
 enum { SR_LOG = 0, SR_TROP = 1 };
 
 #ifndef MK_THREADS
-#define MK_THREADS 384
+#define MK_THREADS 512
 #endif
-constexpr int kSharedThreads = MK_THREADS;  // 12 warps / CTA, 1 CTA / SM (170 registers per thread: the quad buffers must not spill)
+constexpr int kSharedThreads = MK_THREADS;  // 16 warps / CTA, 1 CTA / SM (128 registers per thread: one pass of gathers must not spill)
 constexpr int kSharedWarps = kSharedThreads / 32;
 constexpr int kChunk = 8;       // arcs cached in registers per ⊕ chunk
 constexpr int kTileUtts = 128;  // utterances covered by one warp pass (32 lanes x 4)
@@ -76,6 +76,8 @@ __device__ __forceinline__ float ex2_(float x) { return ex2_approx(x); }
 __device__ __forceinline__ double ex2_(double x) { return exp2(x); }
 __device__ __forceinline__ float lg2_(float x) { return lg2_approx(x); }
 __device__ __forceinline__ double lg2_(double x) { return log2(x); }
+__device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
 __device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
 
@@ -294,72 +296,90 @@ template <typename T> __device__ __forceinline__ bool all_zero_bar(const V4<T>& 
 
 // ---- work plan of one direction ---------------------------------------------------------------
 // Built by the host (markov_b200.cu, build_plan).  Items are rows (or segments of long forward
-// rows) in row order.  Their arcs are re-laid out chunk by chunk into PADDED arrays: every chunk
-// starts and ends on a multiple of four arcs (pads: weight 0̄), every item owns at least one arc
-// (an empty row gets one pad arc), and a per-quad flag byte marks the arcs that end an item — so
-// the streaming loop needs no per-arc bookkeeping beyond one flag test.
+// rows) in row order.  Their arcs are re-laid out item by item into PADDED arrays: every item
+// starts on a multiple of four arcs (pads: weight 0 / 0̄, never loaded), so that the streaming loop
+// fetches four neighbour offsets and four weights with one 16-byte shared-memory load each.
 template <typename T> struct DirPlan {
     const int4* items;           // {row, pdf, slot or -1, run flags (see FwdFin / BwdFin)}
+    const int2* item_pa;         // {first padded arc (multiple of 4), number of arcs}
     const int2* item_arcs;       // {beg, end} in the un-padded arc array (exact fallback only)
     const int4* chunks;          // {parc_begin, parc_end, item_begin, item_end}
     const int* cta_chunks;       // [grid + 1]: CTA c pulls chunks [cta_chunks[c], cta_chunks[c+1])
     const int* pidx;             // padded arcs: neighbour state
-    const T* pw;                 // padded arcs: (w - R) in kernel units, 0̄ on pads
-    const unsigned char* qflags; // per quad of padded arcs: bit k set = arc 4q+k ends an item
+    const T* pw;                 // padded arcs: Log: linear weight 2^(w - R - H); Tropical: w
     const Arc<T>* arcs;          // un-padded arcs (w - R, kernel units) for the exact fallback
     T R;                         // bound on the ⊕ exponents (0 for Tropical)
+    T H;                         // Log: the linear copy of a stored value v is 2^(v + H) (<= 2^headroom)
 };
 
-// out-of-line: the rare exact path must not bloat (or take registers from) the streaming loop
-template <typename T, int SR>
-__device__ __noinline__ void row_reduce_slow(const Arc<T>* arcs, int beg, int end, const T* vec, int U4, int uoff,
-                                             T* out4) {
-    V4<T> r = row_reduce<T, SR>(arcs, beg, end, vec, U4, uoff);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) out4[j] = r.v[j];
+// Single-pass ⊕ of an item's arcs, resolved to log2 Σ 2^(v + w) for 4 utterances.  acc is the
+// linear sum Σ lin·W (Log) or the running maximum (Tropical).  A sum that underflowed for an
+// utterance whose emission is alive is redone with the exact two-pass row_reduce over the log2
+// copies (which also recognises a genuinely dead row).  `live`: bit j set = utterance j needs its value.
+template <typename T> __device__ __forceinline__ T tiny_sum() { return sizeof(T) == 4 ? T(1e-30) : T(1e-280); }  // (the bound sits at 2^100 / 2^900, see build_graph)
+template <typename T> __device__ __forceinline__ T min4(const V4<T>& x) {
+    return fmin(fmin(x.v[0], x.v[1]), fmin(x.v[2], x.v[3]));
 }
-
-// single-pass ⊕ of an item's arcs, resolved to log2 Σ 2^(v + w) for 4 utterances.  acc is the
-// linear sum against the bound R (Log) or the running maximum (Tropical).  A sum that underflowed
-// for an utterance whose emission is alive is redone with the exact two-pass row_reduce (which
-// also recognises a genuinely dead row).
+template <typename T, int SR>
+__device__ __noinline__ void redo_row(const DirPlan<T>* pl, int item, const T* vec, int U4, int uoff, const T* acc4,
+                                      unsigned live, T* val4) {
+#ifdef MK_PROFILE_BARRIER
+    if ((threadIdx.x & 31) == 0) atomicAdd(&g_redo, 1ull);
+#endif
+    const T tiny = tiny_sum<T>();
+    bool need = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) need |= (acc4[j] < tiny) && ((live >> j) & 1u);
+    if (!need) return;
+    const int2 ar = __ldg(pl->item_arcs + item);
+    if (ar.y <= ar.x) return;
+    V4<T> r = row_reduce<T, SR>(pl->arcs, ar.x, ar.y, vec, U4, uoff);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (acc4[j] < tiny) val4[j] = r.v[j] + pl->R;
+}
+template <typename T> __device__ __forceinline__ unsigned live_mask(const V4<T>& e) {
+    unsigned m = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m |= (e.v[j] != neg_inf<T>()) ? (1u << j) : 0u;
+    return m;
+}
 template <typename T, int SR>
 __device__ __forceinline__ V4<T> resolve_sum(const V4<T>& acc, const V4<T>& e, bool need_all, bool dead,
                                              const DirPlan<T>& pl, int item, const T* vec, int U4, int uoff) {
-    V4<T> val;
     if (SR == SR_TROP) return acc;
-    const T tiny = sizeof(T) == 4 ? T(1e-30) : T(1e-280);  // (the bound sits at 2^100 / 2^900, see build_graph)
-    bool redo = false;
+    V4<T> val;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        val.v[j] = lg2_(acc.v[j]) + pl.R;  // acc == 0 -> -Inf
-        redo |= (acc.v[j] < tiny) && (need_all || e.v[j] != neg_inf<T>());
-    }
-    if (redo && !dead) {  // (a statically dead row: the all-zero sum is exact)
-#ifdef MK_PROFILE_BARRIER
-        if ((threadIdx.x & 31) == 0) atomicAdd(&g_redo, 1ull);
-#endif
-        const int2 ar = __ldg(pl.item_arcs + item);
-        if (ar.y > ar.x) {
-            T ex[4];
-            row_reduce_slow<T, SR>(pl.arcs, ar.x, ar.y, vec, U4, uoff, ex);
+    for (int j = 0; j < 4; ++j) val.v[j] = lg2_(acc.v[j]) + pl.R;  // acc == 0 -> -Inf
+    if (min4(acc) < tiny_sum<T>() && !dead) {  // rare (a statically dead row: the all-zero sum is exact)
+        T a4[4], v4[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (acc.v[j] < tiny) val.v[j] = ex[j] + pl.R;
-        }
+        for (int j = 0; j < 4; ++j) { a4[j] = acc.v[j]; v4[j] = val.v[j]; }
+        redo_row<T, SR>(&pl, item, vec, U4, uoff, a4, need_all ? 15u : live_mask(e), v4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) val.v[j] = v4[j];
     }
     return val;
 }
 
 // ---- arc source: the CTA's shared-memory cache (SA) or the global padded arrays ---------------------
 // The cache holds, per padded arc, the row offset pre-multiplied (idx * U4/4, in units of one
-// lane's 4 utterances) and the weight; per quad the flag byte.
+// lane's 4 utterances) and the weight; per item its two records.
 
 template <typename T, bool SA> struct ArcSrc {
-    const int* gidx; const T* gw; const unsigned char* gqf;  // global
-    unsigned soff, sw, sqf;  // shared addresses of (virtual) padded arc 0 / quad 0
-    const int4* gitems; unsigned sitems;  // item records: global array / shared address of (virtual) item 0
-    int U4q;                 // U4 / 4
+    const int* gidx; const T* gw;  // global
+    unsigned soff, sw;             // shared addresses of (virtual) padded arc 0
+    const int4* gitems; const int2* gpa;
+    unsigned sitems, spa;          // shared addresses of (virtual) item 0
+    int U4q;                       // U4 / 4
+    int zpdf;                      // backward sweep: item.z carries the pdf index (no slots there)
+    // item record with pre-multiplied offsets: {row * U4/4, pdf * U4/4, slot (forward) or pdf (backward), flags}
+    __device__ __forceinline__ static int4 cook(int4 r, int U4q, int zpdf) {
+        if (zpdf) r.z = r.y;
+        r.x *= U4q;
+        r.y *= U4q;
+        return r;
+    }
     __device__ __forceinline__ int4 item(int i) const {
         if (SA) {
             int4 r;
@@ -367,7 +387,15 @@ template <typename T, bool SA> struct ArcSrc {
                          : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(sitems + unsigned(i) * 16u));
             return r;
         }
-        return __ldg(gitems + i);
+        return cook(__ldg(gitems + i), U4q, zpdf);
+    }
+    __device__ __forceinline__ int2 item_pa(int i) const {
+        if (SA) {
+            int2 r;
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(spa + unsigned(i) * 8u));
+            return r;
+        }
+        return __ldg(gpa + i);
     }
     // row offsets of the quad's four arcs, in units of one lane's 4 utterances
     __device__ __forceinline__ void offsets(int aq, unsigned (&off)[4]) const {
@@ -380,7 +408,7 @@ template <typename T, bool SA> struct ArcSrc {
             off[2] = unsigned(ix.z) * U4q; off[3] = unsigned(ix.w) * U4q;
         }
     }
-    __device__ __forceinline__ void weights(int aq, T (&w)[4], unsigned& flags) const;
+    __device__ __forceinline__ void weights(int aq, T (&w)[4]) const;
 };
 __device__ __forceinline__ void lds_w4(unsigned a, float (&w)[4]) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w[0]), "=f"(w[1]), "=f"(w[2]), "=f"(w[3]) : "r"(a));
@@ -390,143 +418,86 @@ __device__ __forceinline__ void lds_w4(unsigned a, double (&w)[4]) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(w[2]), "=d"(w[3]) : "r"(a + 16u));
 }
 template <typename T, bool SA>
-__device__ __forceinline__ void ArcSrc<T, SA>::weights(int aq, T (&w)[4], unsigned& flags) const {
+__device__ __forceinline__ void ArcSrc<T, SA>::weights(int aq, T (&w)[4]) const {
     if (SA) {
         lds_w4(sw + unsigned(aq) * unsigned(sizeof(T)), w);
-        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(flags) : "r"(sqf + (unsigned(aq) >> 2)));
     } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k) w[k] = __ldg(gw + aq + k);
-        flags = __ldg(gqf + (aq >> 2));
     }
-}
-
-__device__ __forceinline__ void sts_row(unsigned saddr, const V4<float>& x) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(x.v[0]), "f"(x.v[1]), "f"(x.v[2]),
-                 "f"(x.v[3]) : "memory");
-}
-__device__ __forceinline__ void sts_row(unsigned saddr, const V4<double>& x) {
-    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(saddr), "d"(x.v[0]), "d"(x.v[1]) : "memory");
-    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(saddr + 16), "d"(x.v[2]), "d"(x.v[3]) : "memory");
-}
-__device__ __forceinline__ V4<float> lds_row(unsigned saddr, float) {
-    V4<float> r;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "r"(saddr) : "memory");
-    return r;
-}
-__device__ __forceinline__ V4<double> lds_row(unsigned saddr, double) {
-    V4<double> r;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "r"(saddr) : "memory");
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.v[2]), "=d"(r.v[3]) : "r"(saddr + 16) : "memory");
-    return r;
 }
 
 // ---- streaming loop ----------------------------------------------------------------------------------
-// Register-destination loads cannot form a rolling window here: the 6 scoreboard slots are shared
-// with the MUFU results, ptxas puts every gather on the same slot and each consume then waits for
-// ALL outstanding gathers (measured: depth 2..6 made no difference).  Asynchronous copies do not
-// use register scoreboards: each warp owns a ring of kRing rows in shared memory, lane l copies its
-// own 4 utterances of every gathered row there with cp.async (16 B / 32 B) and reads them back
-// itself — no cross-lane traffic, no barrier.  Copies are committed per quad of arcs and
-// cp.async.wait_group gives exactly the rolling window: kRing/4 - 1 quads stay in flight while one
-// is consumed.  Per arc and utterance: one add, one ex2, one add.  A finished item's sum goes to a
-// small per-warp queue (lane-private columns) drained after every quad by the single finalise site.
-#ifndef MK_RING
-#define MK_RING 16
+// One warp streams the items of a chunk for 128 utterances (lane l: utterances 4l..4l+3).  Per pass
+// it gathers up to 4 * kPassQuads neighbour rows straight into registers (one 16-byte L2 load per
+// arc and lane: a warp reads one contiguous 512 B row) and then folds them with the arc weights:
+//   Log      acc += lin[neighbour] * W      (linear copies x linear weights: one FFMA per arc and utterance)
+//   Tropical acc  = max(acc, v[neighbour] + w)
+// Nothing passes through shared memory except the arc records themselves; the latency of a pass is
+// hidden by the other warps of the SM, each of which has its own pass in flight.
+#ifndef MK_PASS_QUADS
+#define MK_PASS_QUADS 2
 #endif
-constexpr int kRingF32 = MK_RING;  // rows in flight per warp for 4-byte payloads (power of two, multiple of 4)
-template <typename T> struct RingOf { static constexpr int rows = sizeof(T) == 4 ? kRingF32 : (kRingF32 / 2 >= 8 ? kRingF32 / 2 : 8); };
-constexpr int kQueue = 4;        // finished items per drain: one quad
-constexpr int kWarmAhead = 3;    // items whose emission/α rows are prefetched into L1 ahead of their finalise
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void cp_async_row(unsigned sdst, const float* g) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_row(unsigned sdst, const double* g) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(g) : "memory");
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + 16), "l"(g + 2) : "memory");
-}
-
-template <typename T, bool SA>
-__device__ __forceinline__ void quad_issue(unsigned slot0, const ArcSrc<T, SA>& src, int aq, const T* vec_lane) {
-    constexpr unsigned SLOT = 128 * sizeof(T);
-    unsigned off[4];
-    src.offsets(aq, off);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) cp_async_row(slot0 + k * SLOT, vec_lane + size_t(off[k]) * 4);
-}
+template <typename T> struct PassOf { static constexpr int quads = sizeof(T) == 4 ? MK_PASS_QUADS : (MK_PASS_QUADS + 1) / 2; };
 
 template <typename T, int SR, bool SA, class Fin>
-__device__ __forceinline__ void stream_chunk(const ArcSrc<T, SA>& src, const int4 ch, const T* vec_lane,
-                                             unsigned ring, unsigned queue, Fin& fin) {
-    constexpr unsigned SLOT = 128 * sizeof(T);  // bytes per ring / queue slot: 32 lanes x 4 utterances
-    constexpr int NG = RingOf<T>::rows / 4;     // quads in the ring
-    static_assert((NG & (NG - 1)) == 0 && NG >= 2, "ring depth");
-    const int nq = (ch.y - ch.x) >> 2;
-    int item = ch.z;
-    fin.warm(src, ch.z, min(ch.w, ch.z + kWarmAhead));  // L1 prefetch of the next items' emission (and α) rows
-    fin.prefetch(src, item);
-    while (item < ch.w && fin.is_passive()) {  // leading items without arcs
-        fin.passive();
-        if (++item < ch.w) fin.prefetch(src, item);
-    }
-#pragma unroll
-    for (int g = 0; g < NG; ++g) {
-        if (g < nq) quad_issue<T, SA>(ring + g * 4 * SLOT, src, ch.x + g * 4, vec_lane);
-        cp_async_commit();
-    }
-    V4<T> acc;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc.v[j] = SR == SR_LOG ? T(0) : neg_inf<T>();
-    for (int q = 0; q < nq; ++q) {
-        const int aq = ch.x + q * 4;
-        const unsigned slot0 = ring + unsigned(q & (NG - 1)) * 4 * SLOT;
-        T w[4];
-        unsigned flags;
-        src.weights(aq, w, flags);
-        cp_async_wait<NG - 1>();  // the oldest quad has landed
-        int npush = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const V4<T> v = lds_row(slot0 + k * SLOT, T());
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const T x = v.v[j] + w[k];
-                if (SR == SR_LOG) acc.v[j] += ex2_(x);
-                else acc.v[j] = max_(acc.v[j], x);
-            }
-            if (flags & (1u << k)) {  // this arc ends an item (warp-uniform)
-                sts_row(queue + unsigned(npush) * SLOT, acc);
-                ++npush;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc.v[j] = SR == SR_LOG ? T(0) : neg_inf<T>();
-            }
+__device__ __forceinline__ void stream_items(const ArcSrc<T, SA>& src, const int i0, const int i1,
+                                             const T* vec_lane, Fin& fin) {
+    constexpr int kPassQuads = PassOf<T>::quads;
+    for (int item = i0; item < i1; ++item) {
+        fin.prefetch(src, item);  // item record, emission (and α) rows: in flight together with the gathers
+        if (fin.is_passive()) {   // rows of a merged run that reuse the run's ⊕ (backward)
+            fin.passive();
+            continue;
         }
-        if (q + NG < nq) quad_issue<T, SA>(slot0, src, aq + NG * 4, vec_lane);
-        cp_async_commit();
-#ifdef MK_PROFILE_BARRIER
-        long long td0 = clock64();
-#endif
-        for (int k = 0; k < npush; ++k) {  // the only finalise site
-            const V4<T> r = lds_row(queue + unsigned(k) * SLOT, T());
-            fin(item, r);
-            if (item + kWarmAhead < ch.w) fin.warm(src, item + kWarmAhead, item + kWarmAhead + 1);
-            if (++item < ch.w) fin.prefetch(src, item);
-            while (item < ch.w && fin.is_passive()) {  // items without arcs (merged-run members)
-                fin.passive();
-                if (item + kWarmAhead < ch.w) fin.warm(src, item + kWarmAhead, item + kWarmAhead + 1);
-                if (++item < ch.w) fin.prefetch(src, item);
+        const int2 pa = src.item_pa(item);
+        V4<T> acc;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc.v[j] = SR == SR_LOG ? T(0) : neg_inf<T>();
+        int a = pa.x, rem = pa.y;
+        while (rem > 0) {
+            V4<T> v[kPassQuads * 4];
+#pragma unroll
+            for (int q = 0; q < kPassQuads; ++q) {
+                const int left = rem - q * 4;
+                if (left > 0) {  // warp-uniform
+                    unsigned off[4];
+                    src.offsets(a + q * 4, off);
+                    if (left >= 4) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) v[q * 4 + k] = ld4_cg(vec_lane + size_t(off[k]) * 4);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (k < left) {
+                                v[q * 4 + k] = ld4_cg(vec_lane + size_t(off[k]) * 4);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) v[q * 4 + k].v[j] = T(0);  // (pad weights are 0 / 0̄)
+                            }
+                        }
+                    }
+                }
             }
+#pragma unroll
+            for (int q = 0; q < kPassQuads; ++q) {
+                if (rem - q * 4 > 0) {
+                    T w[4];
+                    src.weights(a + q * 4, w);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (SR == SR_LOG) acc.v[j] = fma_(v[q * 4 + k].v[j], w[k], acc.v[j]);
+                            else acc.v[j] = max_(acc.v[j], v[q * 4 + k].v[j] + w[k]);
+                        }
+                }
+            }
+            a += kPassQuads * 4;
+            rem -= kPassQuads * 4;
         }
-#ifdef MK_PROFILE_BARRIER
-        if ((threadIdx.x & 31) == 0) atomicAdd(&g_prof[blockIdx.x * 4 + 3], (unsigned long long)(clock64() - td0));
-#endif
+        fin(item, acc);
     }
-    cp_async_wait<0>();
 }
 
 // ================================================================================================
@@ -564,6 +535,8 @@ template <typename T> struct SharedParams {
     const T* emax;   // [N1][U4]
     T* alpha;        // [N1][Sq][U4]  normalised a_n, then the merged-run sources q_g
     T* bt;           // [2][S][U4]    b_{n+1} ⊗ e'_{n+1} ping-pong
+    T* flin;         // [2][Sq][U4]   Log: linear copies 2^(a_n + H_f) of the forward vector (ping-pong), the gather source
+    T* blin;         // [2][S][U4]    Log: linear copies 2^(b_{n+1} ⊗ e'_{n+1} + H_b), the gather source
     T* beta_out;     // optional [N1][S][U4]  normalised b_n
     int* gkey;       // [2][N1][U4]   per-frame maxima (ordered keys): forward, backward
     double* Coff;    // [2][N1][U4]   Ca_n, Cb_n
@@ -588,6 +561,15 @@ template <> __device__ __forceinline__ V4<double> ld4_nc<double>(const double* p
     double2 a = __ldg(reinterpret_cast<const double2*>(p));
     double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
     V4<double> r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; return r;
+}
+
+// linear copy of a stored (log2) row: 2^(v + H); 0̄ -> 0, values below 2^-126 flush to 0 (the rows that
+// then sum to less than `tiny` are redone exactly from the log2 copies, see resolve_sum)
+template <typename T> __device__ __forceinline__ void st_lin(T* dst, const V4<T>& val, T H) {
+    V4<T> l;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) l.v[j] = ex2_(val.v[j] + H);
+    st4_cg(dst, l);
 }
 
 // combine the segment partials of the long rows into a_m (every CTA, identical result)
@@ -622,103 +604,176 @@ __device__ __forceinline__ void fwd_combine(const SharedParams<T>& p, int m, con
                 atomicMax(&s_key[uoff + j], fkey(float(val.v[j])));
             }
             st4_cg(p.alpha + size_t(m) * frame + size_t(r) * U4 + uoff, val);
+            if (SR == SR_LOG) st_lin(p.flin + size_t(m & 1) * frame + size_t(r) * U4 + uoff, val, p.fwd.H);
         }
     }
 }
 
+// exact ⊕ of the members of a merged run (rows first, first + step, .. last of `cur_lane`), for the lanes whose
+// linear sum underflowed
+template <typename T>
+__device__ __noinline__ void run_logsum_slow(const T* cur_lane, unsigned first, unsigned last, unsigned step, const T* qlin4,
+                                             T* ql4) {
+    const T tiny = tiny_sum<T>();
+    T m[4], sum[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { m[j] = neg_inf<T>(); sum[j] = T(0); }
+    for (unsigned r = first; r <= last; r += step) {
+        const V4<T> v = ld4_cg(cur_lane + size_t(r) * 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m[j] = max_(m[j], v.v[j]);
+    }
+    for (unsigned r = first; r <= last; r += step) {
+        const V4<T> v = ld4_cg(cur_lane + size_t(r) * 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sum[j] += (m[j] == neg_inf<T>()) ? T(0) : ex2_(v.v[j] - m[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (qlin4[j] < tiny) ql4[j] = (sum[j] > T(0)) ? m[j] + lg2_(sum[j]) : neg_inf<T>();
+}
+
+// Finalisers.  Item records arrive with pre-multiplied offsets (ArcSrc::item): it.x = row * U4/4,
+// it.y = pdf * U4/4 — in units of one lane's four utterances, so that every row address is one
+// IMAD.WIDE away from a lane base pointer.
 template <typename T, int SR> struct FwdFin {
     const SharedParams<T>& p;
-    const T* prev; T* cur; T* part; const T* En;
+    const T* prev;      // previous frame's log2 vector (exact fallback)
+    T* cur_l;           // lane bases (+ uoff): this frame's log2 vector,
+    T* lin_l;           //   its linear copies (Log; gathered by the next frame),
+    T* part_l;          //   the segment partials,
+    const T* En_l;      //   this frame's emissions
     int uoff;
-    const T* s_shift;  // per-utterance shift of this frame (shared memory)
-    T mx[4];           // running maxima of this chunk's a values, flushed once per chunk
-    int4 it;   // the item being streamed and its emissions, requested when the item starts
+    T c[4];             // -shift_n of the lane's utterances
+    T mx[4];            // running maxima of this chunk's a values, flushed once per chunk
+    int4 it;            // the item being streamed and its emissions, requested when the item starts
     V4<T> e;
-    V4<T> qacc;  // ⊕ of the a values of the current merged run
+    V4<T> qacc;         // merged run: Σ of the members' linear copies (Log) / their maximum (Tropical)
+    unsigned qfirst;    // row offset of the run's first member
+    __device__ __forceinline__ FwdFin(const SharedParams<T>& p_, const T* prev_, T* cur, T* lin, T* part, const T* En,
+                                      int uoff_, const T* s_shift)
+        : p(p_), prev(prev_), cur_l(cur + uoff_), lin_l(lin + uoff_), part_l(part + uoff_), En_l(En + uoff_), uoff(uoff_) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { c[j] = -s_shift[uoff_ + j]; mx[j] = neg_inf<T>(); qacc.v[j] = T(0); }
+        qfirst = 0;
+    }
     template <class Src> __device__ __forceinline__ void prefetch(const Src& src, int item) {
         it = src.item(item);
-        e = ld4_nc<T>(En + size_t(it.y) * p.U4 + uoff);
-    }
-    // bring the emission rows of a whole chunk into L1 ahead of the finalise chain
-    template <class Src> __device__ __forceinline__ void warm(const Src& src, int i0, int i1) {
-        for (int i = i0; i < i1; ++i) prefetch_l1(En + size_t(src.item(i).y) * p.U4 + uoff);
+        e = ld4_nc<T>(En_l + size_t(unsigned(it.y)) * 4);
     }
     __device__ __forceinline__ bool is_passive() const { return false; }
     __device__ __forceinline__ void passive() {}
     // Row merging: item.w bit0 = member of a run, bit1 = first, bit2 = last, bits 8.. = run index g.  The
     // run's virtual source q_g = ⊕_members a (row Ŝ + g of this frame's vector) feeds the members' common
-    // successors in the next frame.
-    __device__ __forceinline__ void emit_q(const V4<T>& val) {
-        if (!(it.w & 1)) return;
+    // successors in the next frame.  lin: the member's linear copy (Log) / its value (Tropical).
+    __device__ __forceinline__ void emit_q(const V4<T>& lin) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (it.w & 2) {
-                qacc.v[j] = val.v[j];
-            } else if (SR == SR_TROP) {
-                qacc.v[j] = max_(qacc.v[j], val.v[j]);
-            } else {
-                const T m = max_(qacc.v[j], val.v[j]), d = qacc.v[j] + val.v[j] - m - m;  // -|difference|
-                qacc.v[j] = (m == neg_inf<T>()) ? m : m + lg2_(T(1) + ex2_(d));
-            }
+            if (it.w & 2) qacc.v[j] = lin.v[j];
+            else qacc.v[j] = SR == SR_LOG ? qacc.v[j] + lin.v[j] : max_(qacc.v[j], lin.v[j]);
         }
-        if (it.w & 4) st4_cg(cur + size_t(p.S + (it.w >> 8)) * p.U4 + uoff, qacc);
+        if (it.w & 2) qfirst = unsigned(it.x);
+        if (it.w & 4) {
+            const unsigned qoff = unsigned(p.S + (it.w >> 8)) * unsigned(p.U4 >> 2);
+            if (SR == SR_TROP) {
+                st4_cg(cur_l + size_t(qoff) * 4, qacc);
+                return;
+            }
+            st4_cg(lin_l + size_t(qoff) * 4, qacc);
+            V4<T> ql;  // the log2 copy, for the exact fallback of the successors' rows
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ql.v[j] = lg2_(qacc.v[j]) - p.fwd.H;
+            if (min4(qacc) < tiny_sum<T>()) {  // rare
+                T q4[4], l4[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { q4[j] = qacc.v[j]; l4[j] = ql.v[j]; }
+                run_logsum_slow<T>(cur_l, qfirst, unsigned(it.x), unsigned(p.U4 >> 2), q4, l4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ql.v[j] = l4[j];
+            }
+            st4_cg(cur_l + size_t(qoff) * 4, ql);
+        }
+    }
+    // val: the row's normalised a_n (log2 / tropical)
+    __device__ __forceinline__ void store(V4<T>& val) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mx[j] = max_(mx[j], val.v[j]);
+        st4_cg(cur_l + size_t(unsigned(it.x)) * 4, val);
+        if (SR == SR_LOG) {
+            V4<T> lin;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) lin.v[j] = ex2_(val.v[j] + p.fwd.H);
+            // (rows of a merged run are only ever gathered through the run's virtual source)
+            if (!(it.w & 1)) st4_cg(lin_l + size_t(unsigned(it.x)) * 4, lin);
+            else emit_q(lin);
+        } else if (it.w & 1) {
+            emit_q(val);
+        }
     }
     __device__ __forceinline__ void operator()(int item, const V4<T>& acc) {
         // item.w bit3: no initial state reaches this row — α = 0̄ in every frame; bit4: the row has no arcs
         V4<T> val = resolve_sum<T, SR>(acc, e, false, it.w & 24, p.fwd, item, prev, p.U4, uoff);  // T̂ᵀ A[:,n-1] (:70)
         if (it.z >= 0) {  // segment of a long row: partial ⊕ only
-            st4_cg(part + size_t(it.z) * p.U4 + uoff, val);
+            st4_cg(part_l + size_t(it.z) * p.U4, val);
             return;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            val.v[j] = val.v[j] + e.v[j] - s_shift[uoff + j];  // ⊗ e_n (:71), normalised
-            mx[j] = max_(mx[j], val.v[j]);
-        }
-        st4_cg(cur + size_t(it.x) * p.U4 + uoff, val);
-        emit_q(val);
+        for (int j = 0; j < 4; ++j) val.v[j] += e.v[j] + c[j];  // ⊗ e_n (:71), normalised
+        store(val);
     }
 };
 
 template <typename T, int SR> struct BwdFin {
     const SharedParams<T>& p;
-    const T* bt_next; T* bt_cur; const T* En; const T* An;
+    const T* bt_next;   // b_{n+1} ⊗ e'_{n+1} (log2; exact fallback)
+    T* bt_l;            // lane bases (+ uoff): b_n ⊗ e'_n,
+    T* lin_l;           //   its linear copies (Log; gathered by the next frame of the sweep),
+    const T* En_l;      //   this frame's emissions,
+    const T* An_l;      //   this frame's a_n,
+    T* beta_l;          //   optional β output,
+    T* post_l;          //   posterior rows of this frame (pdf 0)
     int n, uoff;
-    const T* s_shift; const T* s_g;  // per-utterance scalars of this frame (shared memory)
-    T mx[4], zs[4];                  // running maxima of b ⊗ e and posterior mass, flushed once per chunk
-    int4 it;     // the item being streamed, its emissions and α, requested when the item starts
+    bool post_on;       // this frame and these utterances have posterior rows
+    T c[4], g[4];       // -shift_n and Ca_n + Cb_n - log Z of the lane's utterances
+    T mx[4], zs[4];     // running maxima of b ⊗ e and posterior mass, flushed once per chunk
+    int4 it;            // the item being streamed (it.z = pdf), its emissions and α, requested when the item starts
     V4<T> e, a;
-    V4<T> last;  // b_n of the last item that owned arcs: rows of a merged run share it (item.w bit0)
+    V4<T> last;         // b_n of the last item that owned arcs: rows of a merged run share it (item.w bit0)
+    __device__ __forceinline__ BwdFin(const SharedParams<T>& p_, const T* bt_next_, T* bt_cur, T* lin, const T* En,
+                                      const T* An, int n_, int uoff_, const T* s_shift, const T* s_g)
+        : p(p_), bt_next(bt_next_), bt_l(bt_cur + uoff_), lin_l(lin + uoff_), En_l(En + uoff_), An_l(An + uoff_), n(n_),
+          uoff(uoff_) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            c[j] = -s_shift[uoff_ + j]; g[j] = s_g[uoff_ + j];
+            mx[j] = neg_inf<T>(); zs[j] = T(0); last.v[j] = neg_inf<T>();
+        }
+        beta_l = p.beta_out ? p.beta_out + size_t(n_) * p.S * p.U4 + uoff_ : nullptr;
+        post_on = p.do_post && n_ < p.Tn;
+        post_l = post_on ? p.post + size_t(n_) * p.D * p.B : nullptr;
+    }
     // items without arcs: rows of a merged run reuse the ⊕ just resolved (item.w bit0)
     __device__ __forceinline__ bool is_passive() const { return it.w & 1; }
     __device__ __forceinline__ void passive() { finish(last); }
     template <class Src> __device__ __forceinline__ void prefetch(const Src& src, int item) {
         it = src.item(item);
-        e = ld4_nc<T>(En + size_t(it.y) * p.U4 + uoff);
-        if (p.do_post) a = ld4_ca(An + size_t(it.x) * p.U4 + uoff);
-    }
-    template <class Src> __device__ __forceinline__ void warm(const Src& src, int i0, int i1) {
-        for (int i = i0; i < i1; ++i) {
-            const int4 t = src.item(i);
-            prefetch_l1(En + size_t(t.y) * p.U4 + uoff);
-            if (p.do_post) prefetch_l1(An + size_t(t.x) * p.U4 + uoff);
-        }
+        e = ld4_nc<T>(En_l + size_t(unsigned(it.y)) * 4);
+        if (p.do_post) a = ld4_cs(An_l + size_t(unsigned(it.x)) * 4);
     }
     __device__ __forceinline__ void finish(V4<T> beta) {
-        const size_t frame = size_t(p.S) * p.U4;  // (β output frames hold Ŝ rows)
-        const int row = it.x, pdf = it.y;
-        if (p.beta_out) st4_cg(p.beta_out + size_t(n) * frame + size_t(row) * p.U4 + uoff, beta);
+        if (beta_l) st4_cg(beta_l + size_t(unsigned(it.x)) * 4, beta);
         if (p.do_post) {
             // γ = α ⊗ β ⊘ Z, exp, per-pdf ⊕  (:154-160)
             V4<T> pg;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const T x = a.v[j] + beta.v[j] + s_g[uoff + j];
+                const T x = a.v[j] + beta.v[j] + g[j];
                 pg.v[j] = SR == SR_LOG ? ex2_(x) : exp_(x);
                 zs[j] = lin_add<SR>(zs[j], pg.v[j]);
             }
-            if (n < p.Tn && pdf < p.D) {
-                T* dst = p.post + (size_t(n) * p.D + pdf) * p.B;
+            const int pdf = it.z;
+            if (post_on && pdf < p.D) {
+                T* dst = post_l + size_t(pdf) * p.B;
                 if (p.post_vec4 && SR == SR_LOG) {
                     red_add4(dst + p.utt_b[uoff], pg);
                 } else {
@@ -736,7 +791,13 @@ template <typename T, int SR> struct BwdFin {
                 beta.v[j] += e.v[j];
                 mx[j] = max_(mx[j], beta.v[j]);
             }
-            st4_cg(bt_cur + size_t(row) * p.U4 + uoff, beta);
+            st4_cg(bt_l + size_t(unsigned(it.x)) * 4, beta);
+            if (SR == SR_LOG) {
+                V4<T> lin;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) lin.v[j] = ex2_(beta.v[j] + p.bwd.H);
+                st4_cg(lin_l + size_t(unsigned(it.x)) * 4, lin);
+            }
         }
     }
     __device__ __forceinline__ void operator()(int item, const V4<T>& acc) {
@@ -745,7 +806,7 @@ template <typename T, int SR> struct BwdFin {
         V4<T> beta = resolve_sum<T, SR>(acc, e, p.beta_out != nullptr, ((it.w & 8) && p.bwd_dead_ok) || (it.w & 16), p.bwd, item,
                                         bt_next, p.U4, uoff);  // (:106-107)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) beta.v[j] -= s_shift[uoff + j];
+        for (int j = 0; j < 4; ++j) beta.v[j] += c[j];
         last = beta;
         finish(beta);
     }
@@ -753,13 +814,14 @@ template <typename T, int SR> struct BwdFin {
 
 // fill this CTA's shared-memory arc cache for one direction; returns the arc source
 template <typename T, bool SA>
-__device__ __forceinline__ ArcSrc<T, SA> make_arc_src(const DirPlan<T>& pl, int cap, unsigned char* smem, int U4q) {
+__device__ __forceinline__ ArcSrc<T, SA> make_arc_src(const DirPlan<T>& pl, int cap, int cap_items, unsigned char* smem,
+                                                      int U4q, int zpdf) {
     ArcSrc<T, SA> src;
-    src.gidx = pl.pidx; src.gw = pl.pw; src.gqf = pl.qflags; src.U4q = U4q;
-    src.gitems = pl.items;
-    src.soff = src.sw = src.sqf = src.sitems = 0;
-    if (SA && cap > 0) {  // (cap == 0: the other sweep's plan, unused in this launch)
-        // the CTA's chunks cover one contiguous range of padded arcs
+    src.gidx = pl.pidx; src.gw = pl.pw; src.U4q = U4q; src.zpdf = zpdf;
+    src.gitems = pl.items; src.gpa = pl.item_pa;
+    src.soff = src.sw = src.sitems = src.spa = 0;
+    if (SA && cap + cap_items > 0) {  // (both 0: the other sweep's plan, unused in this launch)
+        // the CTA's chunks cover one contiguous range of padded arcs and of items
         int a0 = 0x7fffffff, a1 = 0, i0 = 0x7fffffff, i1 = 0;
         for (int c = pl.cta_chunks[blockIdx.x]; c < pl.cta_chunks[blockIdx.x + 1]; ++c) {
             const int4 ch = pl.chunks[c];
@@ -772,24 +834,26 @@ __device__ __forceinline__ ArcSrc<T, SA> make_arc_src(const DirPlan<T>& pl, int 
         if (i0 > i1) i0 = i1 = 0;
         unsigned* s_off = reinterpret_cast<unsigned*>(smem);
         T* s_w = reinterpret_cast<T*>(smem + size_t(cap) * 4);
-        unsigned char* s_qf = smem + size_t(cap) * (4 + sizeof(T));
-        int4* s_items = reinterpret_cast<int4*>(smem + ((size_t(cap) * (4 + sizeof(T)) + size_t(cap) / 4 + 15) & ~size_t(15)));
-        for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) s_items[i - i0] = pl.items[i];
-        src.sitems = unsigned(__cvta_generic_to_shared(s_items)) - unsigned(i0) * 16u;
+        int4* s_items = reinterpret_cast<int4*>(smem + size_t(cap) * (4 + sizeof(T)));
+        int2* s_pa = reinterpret_cast<int2*>(smem + size_t(cap) * (4 + sizeof(T)) + size_t(cap_items) * 16);
+        for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+            s_items[i - i0] = ArcSrc<T, SA>::cook(pl.items[i], U4q, zpdf);
+            s_pa[i - i0] = pl.item_pa[i];
+        }
         for (int a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
             s_off[a - a0] = unsigned(pl.pidx[a]) * unsigned(U4q);
             s_w[a - a0] = pl.pw[a];
         }
-        for (int q = (a0 >> 2) + threadIdx.x; q < (a1 >> 2); q += blockDim.x) s_qf[q - (a0 >> 2)] = pl.qflags[q];
+        src.sitems = unsigned(__cvta_generic_to_shared(s_items)) - unsigned(i0) * 16u;
+        src.spa = unsigned(__cvta_generic_to_shared(s_pa)) - unsigned(i0) * 8u;
         src.soff = unsigned(__cvta_generic_to_shared(s_off)) - unsigned(a0) * 4u;
         src.sw = unsigned(__cvta_generic_to_shared(s_w)) - unsigned(a0) * unsigned(sizeof(T));
-        src.sqf = unsigned(__cvta_generic_to_shared(s_qf)) - (unsigned(a0) >> 2);
     }
     return src;
 }
-// padded arcs (offset, weight), quad flags, then the CTA's item records (at most one per arc)
+// padded arcs (offset, weight; cap is a multiple of 4), then the CTA's item records
 __host__ __device__ inline size_t arc_cache_bytes(int cap, int items, size_t tsize) {
-    return ((size_t(cap) * (4 + tsize) + size_t(cap) / 4 + 15) & ~size_t(15)) + size_t(items) * 16;
+    return size_t(cap) * (4 + tsize) + size_t(items) * 24;
 }
 __host__ __device__ inline size_t shared_scalars_bytes(int U4, size_t tsize) {
     return (size_t(U4) * (2 * sizeof(double) + 3 * tsize + sizeof(int)) + 16 + 15) & ~size_t(15);
@@ -813,17 +877,13 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
     const size_t frame_q = size_t(p.Sq) * U4;  // α store: Ŝ + merged-run rows
     unsigned bar_target = 0;
 
-    // per-warp queue of finished items (lane-private columns), then the arc caches
-    const size_t scalars_bytes = shared_scalars_bytes(U4, sizeof(T));
-    constexpr unsigned QSLOT = 128 * sizeof(T);
-    const unsigned warp_smem = unsigned(__cvta_generic_to_shared(smem_raw + scalars_bytes)) +
-                               warp * ((kQueue + RingOf<T>::rows) * QSLOT) + lane * 4 * unsigned(sizeof(T));
-    const unsigned queue = warp_smem, ring = warp_smem + kQueue * QSLOT;
-    unsigned char* cache = smem_raw + scalars_bytes + size_t(kSharedWarps) * (kQueue + RingOf<T>::rows) * QSLOT;
     // This CTA's arcs stay in shared memory for the whole launch: the per-frame fence of the grid
     // barrier invalidates L1, shared memory survives.
-    const ArcSrc<T, SA> fwd_src = make_arc_src<T, SA>(p.fwd, PHASE == 0 ? p.cache_f : 0, cache, U4 >> 2);
-    const ArcSrc<T, SA> bwd_src = make_arc_src<T, SA>(p.bwd, PHASE == 1 ? p.cache_b : 0, cache, U4 >> 2);
+    unsigned char* cache = smem_raw + shared_scalars_bytes(U4, sizeof(T));
+    const ArcSrc<T, SA> fwd_src = make_arc_src<T, SA>(p.fwd, PHASE == 0 ? p.cache_f : 0, PHASE == 0 ? p.cache_items_f : 0,
+                                                      cache, U4 >> 2, 0);
+    const ArcSrc<T, SA> bwd_src = make_arc_src<T, SA>(p.bwd, PHASE == 1 ? p.cache_b : 0, PHASE == 1 ? p.cache_items_b : 0,
+                                                      cache, U4 >> 2, 1);
 
     {   // this sweep's per-frame maxima
         int* keys = p.gkey + size_t(PHASE) * p.N1 * U4;
@@ -863,27 +923,23 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
                 const int4 ch = __ldg(p.fwd.chunks + c0 + (wk - c0) / p.ntiles);
                 const int uoff = ((wk - c0) % p.ntiles) * kTileUtts + lane * 4;
                 if (uoff < U4) {  // (lanes beyond the batch stay converged for the next pull)
-                    FwdFin<T, SR> fin{p, p.alpha + size_t(n > 0 ? n - 1 : 0) * frame_q, p.alpha + size_t(n) * frame_q,
-                                      p.part + size_t(n & 1) * p.n_slots * U4, p.E + size_t(n) * p.Dh * U4, uoff,
-                                      s_shift};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) fin.mx[j] = neg_inf<T>();
+                    FwdFin<T, SR> fin(p, p.alpha + size_t(n > 0 ? n - 1 : 0) * frame_q, p.alpha + size_t(n) * frame_q,
+                                      p.flin + size_t(n & 1) * frame_q, p.part + size_t(n & 1) * p.n_slots * U4,
+                                      p.E + size_t(n) * p.Dh * U4, uoff, s_shift);
                     if (n == 0) {
                         for (int i = ch.z; i < ch.w; ++i) {
                             fin.prefetch(fwd_src, i);
                             if (fin.it.z >= 0) continue;
-                            const T a0 = __ldg(p.init_dense + fin.it.x);  // A[:,1] = α̂ ⊗ e₁  (:68)
-                            V4<T> acc;
+                            const T a0 = __ldg(p.init_dense + unsigned(fin.it.x) / unsigned(U4 >> 2));  // A[:,1] = α̂ ⊗ e₁  (:68)
+                            V4<T> val;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                acc.v[j] = a0 + fin.e.v[j];
-                                fin.mx[j] = max_(fin.mx[j], acc.v[j]);
-                            }
-                            st4_cg(fin.cur + size_t(fin.it.x) * U4 + uoff, acc);
-                            fin.emit_q(acc);
+                            for (int j = 0; j < 4; ++j) val.v[j] = a0 + fin.e.v[j];
+                            fin.store(val);
                         }
                     } else {
-                        stream_chunk<T, SR, SA>(fwd_src, ch, fin.prev + uoff, ring, queue, fin);
+                        // gather source: the previous frame's linear copies (Log) / the vector itself (Tropical)
+                        const T* gsrc = SR == SR_LOG ? p.flin + size_t((n - 1) & 1) * frame_q : fin.prev;
+                        stream_items<T, SR, SA>(fwd_src, ch.z, ch.w, gsrc + uoff, fin);
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) atomicMax(&s_key[uoff + j], fkey(float(fin.mx[j])));
@@ -950,11 +1006,9 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
             const int4 ch = __ldg(p.bwd.chunks + c0 + (wk - c0) / p.ntiles);
             const int uoff = ((wk - c0) % p.ntiles) * kTileUtts + lane * 4;
             if (uoff < U4) {
-                BwdFin<T, SR> fin{p, p.bt + size_t((n + 1) & 1) * frame, p.bt + size_t(n & 1) * frame,
-                                  p.E + size_t(n) * p.Dh * U4, p.alpha + size_t(n) * frame_q, n, uoff,
-                                  s_shift, s_g};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { fin.mx[j] = neg_inf<T>(); fin.zs[j] = T(0); }
+                BwdFin<T, SR> fin(p, p.bt + size_t((n + 1) & 1) * frame, p.bt + size_t(n & 1) * frame,
+                                  p.blin + size_t(n & 1) * frame, p.E + size_t(n) * p.Dh * U4,
+                                  p.alpha + size_t(n) * frame_q, n, uoff, s_shift, s_g);
                 if (n == p.N1 - 1) {
                     for (int i = ch.z; i < ch.w; ++i) {
                         fin.prefetch(bwd_src, i);
@@ -964,7 +1018,8 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
                         fin.finish(beta);
                     }
                 } else {
-                    stream_chunk<T, SR, SA>(bwd_src, ch, fin.bt_next + uoff, ring, queue, fin);
+                    const T* gsrc = SR == SR_LOG ? p.blin + size_t((n + 1) & 1) * frame : fin.bt_next;
+                    stream_items<T, SR, SA>(bwd_src, ch.z, ch.w, gsrc + uoff, fin);
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {

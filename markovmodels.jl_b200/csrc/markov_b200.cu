@@ -99,16 +99,16 @@ template <typename T> static int upload(const std::vector<T>& h, void** d) {
 // device-side work plan of one direction (kernels.cuh DirPlan)
 struct DirDev {
     int4 *items = nullptr, *chunks = nullptr;
-    int2* item_arcs = nullptr;
+    int2 *item_arcs = nullptr, *item_pa = nullptr;
     int *cta_chunks = nullptr, *pidx = nullptr;
     void *pw = nullptr, *arcs = nullptr;  // arcs: un-padded Arc<T> holding w - R in kernel units
-    unsigned char* qflags = nullptr;
     int cache_cap = 0;  // largest per-CTA range of padded arcs (multiple of 4)
     int cache_items = 0;  // largest per-CTA number of items
     double R = 0;       // bound on the ⊕ exponents, kernel units
+    double H = 0;       // Log: linear copy of a stored value v = 2^(v + H), kernel units
     void release() {
         cudaFree(items); cudaFree(chunks); cudaFree(item_arcs); cudaFree(cta_chunks); cudaFree(pidx);
-        cudaFree(pw); cudaFree(arcs); cudaFree(qflags);
+        cudaFree(pw); cudaFree(arcs); cudaFree(item_pa);
     }
 };
 
@@ -158,10 +158,9 @@ static double chunk_cost_target(double cta_total) {
 
 template <typename T> struct DirHost {
     std::vector<int4> items, chunks;
-    std::vector<int2> item_arcs;
+    std::vector<int2> item_arcs, item_pa;
     std::vector<int> cta_chunks, pidx;
     std::vector<T> pw;
-    std::vector<unsigned char> qflags;
     int cache_cap = 0, cache_items = 0;
 };
 
@@ -171,9 +170,11 @@ template <typename T> struct DirHost {
 template <typename T>
 static void build_plan(const std::vector<int>& ptr, const std::vector<Arc<T>>& arcs, const std::vector<int>& pdf,
                        int S, int n_ctas, bool split, const std::vector<int>& gflags, const std::vector<char>& tied,
-                       bool reuse, DirHost<T>& d, std::vector<int4>& long_rows, std::vector<Arc<T>>& long_arcs,
-                       int& n_slots) {
-    const T ninf = -std::numeric_limits<T>::infinity();
+                       bool reuse, bool linear, double H, DirHost<T>& d, std::vector<int4>& long_rows,
+                       std::vector<Arc<T>>& long_arcs, int& n_slots) {
+    // Log semiring: the padded (streamed) arcs hold LINEAR weights 2^(w - R - H) that multiply the linear
+    // copies 2^(v + H) of the vector; pads are 0.  Tropical: w itself, pads 0̄.
+    const T ninf = linear ? T(0) : -std::numeric_limits<T>::infinity();
     n_slots = 0;
     for (int r = 0; r < S; ++r) {
         const int beg = ptr[r], end = ptr[r + 1], deg = end - beg;
@@ -222,11 +223,12 @@ static void build_plan(const std::vector<int>& ptr, const std::vector<Arc<T>>& a
         cta_items[k] = i;
     }
     d.cta_chunks.assign(n_ctas + 1, 0);
+    d.item_pa.assign(n_items, make_int2(0, 0));
     auto emit = [&](int idx, T w) { d.pidx.push_back(idx); d.pw.push_back(w); };
     for (int k = 0; k < n_ctas; ++k) {
         const size_t first = d.chunks.size();
         const int cta_arc0 = int(d.pidx.size());
-        int cb = cta_items[k], n_arcs = 0, pb = int(d.pidx.size());
+        int cb = cta_items[k], pb = int(d.pidx.size());
         // guided self-scheduling: chunks shrink from ~2x the target to 1/4 of it along the CTA's work, so
         // that the last chunks pulled (they are sorted largest first) are small and the frame ends evenly
         double cta_total = 0, done = 0, n_cost = 0;
@@ -235,13 +237,11 @@ static void build_plan(const std::vector<int>& ptr, const std::vector<Arc<T>>& a
         for (int it = cta_items[k]; it < cta_items[k + 1]; ++it) {
             const int2 ar = d.item_arcs[it];
             const bool owns_arcs = !(reuse && tied[d.items[it].x]);
+            d.item_pa[it] = make_int2(int(d.pidx.size()), owns_arcs ? ar.y - ar.x : 0);
             if (owns_arcs) {
-                for (int a = ar.x; a < ar.y; ++a) emit(arcs[a].idx, arcs[a].w);
-                if (ar.y == ar.x) emit(0, ninf);  // an empty row still owns one (pad) arc
-                const size_t last = d.pidx.size() - 1;
-                if (d.qflags.size() <= last / 4) d.qflags.resize(last / 4 + 1, 0);
-                d.qflags[last / 4] |= (unsigned char)(1u << (last % 4));
-                n_arcs += std::max(1, ar.y - ar.x);
+                for (int a = ar.x; a < ar.y; ++a)
+                    emit(arcs[a].idx, linear ? T(std::exp2(double(arcs[a].w) - H)) : arcs[a].w);
+                while (d.pidx.size() % 4) emit(0, ninf);  // every item starts on a quad
             }
             n_cost += cost(it);
             const bool next_tied = it + 1 < cta_items[k + 1] && tied[d.items[it + 1].x] && d.items[it + 1].z < 0;
@@ -250,10 +250,8 @@ static void build_plan(const std::vector<int>& ptr, const std::vector<Arc<T>>& a
             if ((n_cost >= target && !next_tied) || it + 1 == cta_items[k + 1]) {
                 done += n_cost;
                 n_cost = 0;
-                while (d.pidx.size() % 4) emit(0, ninf);
                 d.chunks.push_back(make_int4(pb, int(d.pidx.size()), cb, it + 1));
                 cb = it + 1;
-                n_arcs = 0;
                 pb = int(d.pidx.size());
             }
         }
@@ -263,7 +261,7 @@ static void build_plan(const std::vector<int>& ptr, const std::vector<Arc<T>>& a
         d.cache_cap = std::max(d.cache_cap, int(d.pidx.size()) - cta_arc0);
         d.cache_items = std::max(d.cache_items, cta_items[k + 1] - cta_items[k]);
     }
-    d.qflags.resize(d.pidx.size() / 4 + 1, 0);
+    for (int q = 0; q < 4; ++q) emit(0, ninf);  // the global (uncached) path reads whole quads
 }
 
 template <typename T> static int upload_plan(const DirHost<T>& hst, const std::vector<Arc<T>>& arcs, DirDev& dev) {
@@ -273,7 +271,7 @@ template <typename T> static int upload_plan(const DirHost<T>& hst, const std::v
     TRY(upload(hst.cta_chunks, (void**)&dev.cta_chunks));
     TRY(upload(hst.pidx, (void**)&dev.pidx));
     TRY(upload(hst.pw, &dev.pw));
-    TRY(upload(hst.qflags, (void**)&dev.qflags));
+    TRY(upload(hst.item_pa, (void**)&dev.item_pa));
     TRY(upload(arcs, &dev.arcs));
     dev.cache_cap = hst.cache_cap;
     dev.cache_items = hst.cache_items;
@@ -442,18 +440,20 @@ static int build_graph(mk_graph* g, const int64_t* colptr, const int64_t* rowval
 
     // Bounds for the single-pass ⊕ (kernels.cuh): stored a_n <= max(log max column-sum, max α̂),
     // stored b_n ⊗ e' <= max(log max row-sum, 0); every exponent v + (w - R) is then <= 0.
-    double R_f = 0, R_b = 0;
-    if (g->semiring == MK_LOG && nnz > 0) {
+    double R_f = 0, R_b = 0, vf = 0, vb = 0;
+    if (g->semiring == MK_LOG) {
         const double ninf_d = -std::numeric_limits<double>::infinity();
         double wmax = ninf_d, li = ninf_d;
         for (int64_t a = 0; a < nnz; ++a) wmax = std::max(wmax, double(in_arcs[a].w));
         for (int64_t k = 0; k < n_init; ++k) li = std::max(li, double(init_w[k]));
+        if (!(li > ninf_d && li < std::numeric_limits<double>::infinity())) li = 0;
         if (wmax > ninf_d && wmax < std::numeric_limits<double>::infinity()) {
-            double vf = std::max(max_row_logsum<T>(in_ptr, in_arcs, S), li) + std::log(double(max_run));  // q_g <= max + log|run|
-            double vb = std::max(max_row_logsum<T>(out_ptr, out_arcs, S), 0.0);
-            if (!(vf > ninf_d)) vf = 0;
+            vf = std::max(max_row_logsum<T>(in_ptr, in_arcs, S), li) + std::log(double(max_run));  // q_g <= max + log|run|
+            vb = std::max(max_row_logsum<T>(out_ptr, out_arcs, S), 0.0);
             R_f = vf + wmax;
             R_b = vb + wmax;
+        } else {
+            vf = li + std::log(double(max_run));  // (no usable arc: only frame 0 holds finite values)
         }
     }
     // the shared-graph kernel works in log2 units for the Log semiring.  The bound is placed at 2^kHeadroom
@@ -470,14 +470,20 @@ static int build_graph(mk_graph* g, const int64_t* colptr, const int64_t* rowval
     for (auto& x : init_s) x = T(double(x) * unit);
     g->fwd.R = R_f * unit;
     g->bwd.R = R_b * unit;
+    // linear copies: stored values are <= vf (vb), so 2^(v + H) <= 2^headroom and the linear weights are
+    // 2^((w - wmax) unit) <= 1
+    const bool linear = g->semiring == MK_LOG;
+    g->fwd.H = linear ? headroom - vf * unit : 0.0;
+    g->bwd.H = linear ? headroom - vb * unit : 0.0;
 
     DirHost<T> fwd, bwd;
     std::vector<int4> fwd_long, no_long;
     std::vector<Arc<T>> fwd_long_arcs, no_arcs;
     int no_slots = 0;
-    build_plan<T>(in_ptr_m, in_s, pdf, S, g->n_sms, true, gf_fwd, tied, false, fwd, fwd_long, fwd_long_arcs,
-                  g->n_slots);
-    build_plan<T>(out_ptr, out_s, pdf, S, g->n_sms, false, gf_bwd, tied, true, bwd, no_long, no_arcs, no_slots);
+    build_plan<T>(in_ptr_m, in_s, pdf, S, g->n_sms, true, gf_fwd, tied, false, linear, g->fwd.H, fwd, fwd_long,
+                  fwd_long_arcs, g->n_slots);
+    build_plan<T>(out_ptr, out_s, pdf, S, g->n_sms, false, gf_bwd, tied, true, linear, g->bwd.H, bwd, no_long,
+                  no_arcs, no_slots);
     g->n_long = int(fwd_long.size());
 
     TRY(upload(in_ptr, (void**)&g->d_in_ptr));
@@ -506,7 +512,7 @@ struct Group {  // utterances sharing one graph, run by shared_fb_kernel
     bool vec4 = false;
     int* d_utt_b = nullptr;
     long long* d_utt_off = nullptr;
-    DevBuf E, emax, alpha, bt, part, gkey, coff, lz2;
+    DevBuf E, emax, alpha, bt, flin, blin, part, gkey, coff, lz2;
 };
 
 struct mk_batch {
@@ -531,7 +537,7 @@ struct mk_batch {
     ~mk_batch() {
         for (auto& gr : groups) {
             cudaFree(gr.d_utt_b); cudaFree(gr.d_utt_off);
-            gr.E.release(); gr.alpha.release(); gr.bt.release();
+            gr.E.release(); gr.alpha.release(); gr.bt.release(); gr.flin.release(); gr.blin.release();
             gr.part.release(); gr.gkey.release(); gr.coff.release(); gr.emax.release(); gr.lz2.release();
         }
         DevBuf* all[] = {&small_descs, &small_alpha, &small_ca, &zsum, &lz, &seqlens, &barrier, &trace,
@@ -546,7 +552,7 @@ struct mk_batch {
     size_t ws_bytes() const {
         size_t t = small_descs.cap + small_alpha.cap + small_ca.cap + zsum.cap + lz.cap + seqlens.cap + barrier.cap +
                    trace.cap + h_ll.cap + h_post.cap + h_logz.cap + h_path.cap;
-        for (auto& gr : groups) t += gr.E.cap + gr.alpha.cap + gr.bt.cap + gr.part.cap + gr.gkey.cap + gr.coff.cap + gr.emax.cap;
+        for (auto& gr : groups) t += gr.E.cap + gr.alpha.cap + gr.bt.cap + gr.flin.cap + gr.blin.cap + gr.part.cap + gr.gkey.cap + gr.coff.cap + gr.emax.cap;
         return t;
     }
 };
@@ -577,6 +583,10 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     TRY(gr.E.ensure(size_t(N1) * Dh * U4 * sizeof(T)));
     TRY(gr.alpha.ensure(size_t(N1) * frame_q));
     if (mode == MODE_POST || mode == MODE_BETA) TRY(gr.bt.ensure(2 * frame));
+    if (SR == SR_LOG) {  // linear copies of the two frames in flight: the gather sources
+        if (mode != MODE_BETA) TRY(gr.flin.ensure(2 * frame_q));
+        if (mode == MODE_POST || mode == MODE_BETA) TRY(gr.blin.ensure(2 * frame));
+    }
     TRY(gr.part.ensure(2 * size_t(std::max(g->n_slots, 1)) * U4 * sizeof(T)));
     TRY(gr.gkey.ensure(2 * size_t(N1) * U4 * sizeof(int)));
     TRY(gr.emax.ensure(size_t(N1) * U4 * sizeof(T)));
@@ -605,8 +615,8 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     auto plan = [](const DirDev& d) {
         DirPlan<T> q;
         q.items = d.items; q.item_arcs = d.item_arcs; q.chunks = d.chunks; q.cta_chunks = d.cta_chunks;
-        q.pidx = d.pidx; q.pw = static_cast<const T*>(d.pw); q.qflags = d.qflags;
-        q.arcs = static_cast<const Arc<T>*>(d.arcs); q.R = T(d.R);
+        q.pidx = d.pidx; q.pw = static_cast<const T*>(d.pw); q.item_pa = d.item_pa;
+        q.arcs = static_cast<const Arc<T>*>(d.arcs); q.R = T(d.R); q.H = T(d.H);
         return q;
     };
     p.fwd = plan(g->fwd); p.bwd = plan(g->bwd);
@@ -620,6 +630,7 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     p.E = static_cast<const T*>(gr.E.p);
     p.alpha = static_cast<T*>(gr.alpha.p);
     p.bt = static_cast<T*>(gr.bt.p);
+    p.flin = static_cast<T*>(gr.flin.p); p.blin = static_cast<T*>(gr.blin.p);
     p.beta_out = nullptr;
     p.post = nullptr; p.B = int(bt->B); p.D = Dout; p.Tn = Tout;
     p.utt_b = gr.d_utt_b; p.post_vec4 = 0;
@@ -637,7 +648,7 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
             break;
     }
     void* args[] = {&p};
-    const size_t scal = shared_scalars_bytes(U4, sizeof(T)) + size_t(kSharedWarps) * (kQueue + RingOf<T>::rows) * 128 * sizeof(T);
+    const size_t scal = shared_scalars_bytes(U4, sizeof(T));
     const int slot = bt->prof_n % mk_batch::kProfRing;
     if (bt->profile) CK(cudaEventRecord(bt->ev0[slot], c.stream));
     for (int phase = 0; phase < 2; ++phase) {
