@@ -139,7 +139,13 @@ __device__ __forceinline__ V4<double> ld4_ca(const double* p) {
     asm volatile("ld.global.ca.v2.f64 {%0, %1}, [%2];" : "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p + 2) : "memory");
     return r;
 }
+#ifdef MK_ABLATE
+__device__ int g_no_stores;
+#endif
 __device__ __forceinline__ void st4_cg(float* p, const V4<float>& x) {
+#ifdef MK_ABLATE
+    if (g_no_stores) return;
+#endif
     __stcg(reinterpret_cast<float4*>(p), make_float4(x.v[0], x.v[1], x.v[2], x.v[3]));
 }
 __device__ __forceinline__ void st4_cg(double* p, const V4<double>& x) {
@@ -149,6 +155,9 @@ __device__ __forceinline__ void st4_cg(double* p, const V4<double>& x) {
 
 // posterior accumulation into the (B, D, N) output: Log -> add, Tropical -> max
 __device__ __forceinline__ void red_add4(float* p, const V4<float>& x) {
+#ifdef MK_ABLATE
+    if (g_no_stores) return;
+#endif
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x.v[0]),
                  "f"(x.v[1]), "f"(x.v[2]), "f"(x.v[3])
                  : "memory");
@@ -176,6 +185,11 @@ template <int SR, typename T> __device__ __forceinline__ T lin_add(T a, T b) {
 // Monotonic counter; the kernel is launched cooperatively (all CTAs co-resident).  Writers'
 // stores are ordered by bar.sync + fence + the atomic; the waiting thread uses an acquire load
 // and every consumer then reads other CTAs' data with L1-bypassing loads only (ld4_cg).
+#ifdef MK_ABLATE
+#define MK_ABL(p, bit) ((p).ablate & (bit))
+#else
+#define MK_ABL(p, bit) false
+#endif
 #ifdef MK_PROFILE_BARRIER
 __device__ unsigned long long g_prof[148 * 4];
 __device__ unsigned long long g_redo;  // exact-fallback events  // per CTA: cycles before arriving, cycles waiting, ...
@@ -191,8 +205,8 @@ __device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& target) {
 #endif
     if (threadIdx.x == 0) {
         target += gridDim.x;
-        __threadfence();
-        atomicAdd(ctr, 1u);
+        // release: the CTA's writes (ordered before this thread by bar.sync) become visible before the arrival
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
         unsigned v;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
@@ -369,8 +383,18 @@ __device__ __forceinline__ V4<T> resolve_sum(const V4<T>& acc, const V4<T>& e, b
 template <typename T, bool SA> struct ArcSrc {
     const int* gidx; const T* gw;  // global
     unsigned soff, sw;             // shared addresses of (virtual) padded arc 0
-    const int4* gitems; const int2* gpa;
+    const int4* gitems; const int2* gpa; const int4* gchunks;
     unsigned sitems, spa;          // shared addresses of (virtual) item 0
+    unsigned schunks;              // shared address of (virtual) chunk 0
+    __device__ __forceinline__ int4 chunk(int c) const {
+        if (SA) {
+            int4 r;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(schunks + unsigned(c) * 16u));
+            return r;
+        }
+        return __ldg(gchunks + c);
+    }
     int U4q;                       // U4 / 4
     int zpdf;                      // backward sweep: item.z carries the pdf index (no slots there)
     // item record with pre-multiplied offsets: {row * U4/4, pdf * U4/4, slot (forward) or pdf (backward), flags}
@@ -463,7 +487,12 @@ __device__ __forceinline__ void stream_items(const ArcSrc<T, SA>& src, const int
                 if (left > 0) {  // warp-uniform
                     unsigned off[4];
                     src.offsets(a + q * 4, off);
-                    if (left >= 4) {
+                    if (MK_ABL(fin.p, 1)) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) v[q * 4 + k].v[j] = T(1);
+                    } else if (left >= 4) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) v[q * 4 + k] = ld4_cg(vec_lane + size_t(off[k]) * 4);
                     } else {
@@ -496,7 +525,7 @@ __device__ __forceinline__ void stream_items(const ArcSrc<T, SA>& src, const int
             a += kPassQuads * 4;
             rem -= kPassQuads * 4;
         }
-        fin(item, acc);
+        if (!MK_ABL(fin.p, 2)) fin(item, acc);
     }
 }
 
@@ -549,6 +578,7 @@ template <typename T> struct SharedParams {
     double* lz2;       // [U4] the same in kernel units, handed from the forward to the backward launch
     unsigned* barrier;
     int do_fwd, do_bwd, do_post;
+    int ablate;        // debug builds (MK_ABLATE): 1 no gathers, 2 no finalise, 4 no chunk work, 8 no emission/α loads, 16 no stores
     int bwd_dead_ok;   // the library applied `expand`: co-unreachable rows have β = 0̄ before the last frame
 };
 
@@ -659,6 +689,7 @@ template <typename T, int SR> struct FwdFin {
     }
     template <class Src> __device__ __forceinline__ void prefetch(const Src& src, int item) {
         it = src.item(item);
+        if (MK_ABL(p, 8)) { for (int j = 0; j < 4; ++j) e.v[j] = T(-1); return; }
         e = ld4_nc<T>(En_l + size_t(unsigned(it.y)) * 4);
     }
     __device__ __forceinline__ bool is_passive() const { return false; }
@@ -757,6 +788,7 @@ template <typename T, int SR> struct BwdFin {
     __device__ __forceinline__ void passive() { finish(last); }
     template <class Src> __device__ __forceinline__ void prefetch(const Src& src, int item) {
         it = src.item(item);
+        if (MK_ABL(p, 8)) { for (int j = 0; j < 4; ++j) { e.v[j] = T(-1); a.v[j] = T(-1); } return; }
         e = ld4_nc<T>(En_l + size_t(unsigned(it.y)) * 4);
         if (p.do_post) a = ld4_cs(An_l + size_t(unsigned(it.x)) * 4);
     }
@@ -818,8 +850,8 @@ __device__ __forceinline__ ArcSrc<T, SA> make_arc_src(const DirPlan<T>& pl, int 
                                                       int U4q, int zpdf) {
     ArcSrc<T, SA> src;
     src.gidx = pl.pidx; src.gw = pl.pw; src.U4q = U4q; src.zpdf = zpdf;
-    src.gitems = pl.items; src.gpa = pl.item_pa;
-    src.soff = src.sw = src.sitems = src.spa = 0;
+    src.gitems = pl.items; src.gpa = pl.item_pa; src.gchunks = pl.chunks;
+    src.soff = src.sw = src.sitems = src.spa = src.schunks = 0;
     if (SA && cap + cap_items > 0) {  // (both 0: the other sweep's plan, unused in this launch)
         // the CTA's chunks cover one contiguous range of padded arcs and of items
         int a0 = 0x7fffffff, a1 = 0, i0 = 0x7fffffff, i1 = 0;
@@ -836,6 +868,10 @@ __device__ __forceinline__ ArcSrc<T, SA> make_arc_src(const DirPlan<T>& pl, int 
         T* s_w = reinterpret_cast<T*>(smem + size_t(cap) * 4);
         int4* s_items = reinterpret_cast<int4*>(smem + size_t(cap) * (4 + sizeof(T)));
         int2* s_pa = reinterpret_cast<int2*>(smem + size_t(cap) * (4 + sizeof(T)) + size_t(cap_items) * 16);
+        int4* s_chunks = reinterpret_cast<int4*>(smem + size_t(cap) * (4 + sizeof(T)) + ((size_t(cap_items) * 24 + 15) & ~size_t(15)));
+        const int c0 = pl.cta_chunks[blockIdx.x], c1 = pl.cta_chunks[blockIdx.x + 1];
+        for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x) s_chunks[c - c0] = pl.chunks[c];
+        src.schunks = unsigned(__cvta_generic_to_shared(s_chunks)) - unsigned(c0) * 16u;
         for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
             s_items[i - i0] = ArcSrc<T, SA>::cook(pl.items[i], U4q, zpdf);
             s_pa[i - i0] = pl.item_pa[i];
@@ -852,8 +888,8 @@ __device__ __forceinline__ ArcSrc<T, SA> make_arc_src(const DirPlan<T>& pl, int 
     return src;
 }
 // padded arcs (offset, weight; cap is a multiple of 4), then the CTA's item records
-__host__ __device__ inline size_t arc_cache_bytes(int cap, int items, size_t tsize) {
-    return size_t(cap) * (4 + tsize) + size_t(items) * 24;
+__host__ __device__ inline size_t arc_cache_bytes(int cap, int items, int chunks, size_t tsize) {
+    return size_t(cap) * (4 + tsize) + ((size_t(items) * 24 + 15) & ~size_t(15)) + size_t(chunks) * 16;
 }
 __host__ __device__ inline size_t shared_scalars_bytes(int U4, size_t tsize) {
     return (size_t(U4) * (2 * sizeof(double) + 3 * tsize + sizeof(int)) + 16 + 15) & ~size_t(15);
@@ -920,7 +956,8 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
                 if (lane == 0) wk = atomicAdd(s_next, 1);
                 wk = __shfl_sync(0xffffffffu, wk, 0);
                 if (wk >= work1) break;
-                const int4 ch = __ldg(p.fwd.chunks + c0 + (wk - c0) / p.ntiles);
+                if (MK_ABL(p, 4)) continue;
+                const int4 ch = fwd_src.chunk(c0 + (wk - c0) / p.ntiles);
                 const int uoff = ((wk - c0) % p.ntiles) * kTileUtts + lane * 4;
                 if (uoff < U4) {  // (lanes beyond the batch stay converged for the next pull)
                     FwdFin<T, SR> fin(p, p.alpha + size_t(n > 0 ? n - 1 : 0) * frame_q, p.alpha + size_t(n) * frame_q,
@@ -1003,7 +1040,8 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
             if (lane == 0) wk = atomicAdd(s_next, 1);
             wk = __shfl_sync(0xffffffffu, wk, 0);
             if (wk >= work1) break;
-            const int4 ch = __ldg(p.bwd.chunks + c0 + (wk - c0) / p.ntiles);
+            if (MK_ABL(p, 4)) continue;
+            const int4 ch = bwd_src.chunk(c0 + (wk - c0) / p.ntiles);
             const int uoff = ((wk - c0) % p.ntiles) * kTileUtts + lane * 4;
             if (uoff < U4) {
                 BwdFin<T, SR> fin(p, p.bt + size_t((n + 1) & 1) * frame, p.bt + size_t(n & 1) * frame,

@@ -104,6 +104,7 @@ struct DirDev {
     void *pw = nullptr, *arcs = nullptr;  // arcs: un-padded Arc<T> holding w - R in kernel units
     int cache_cap = 0;  // largest per-CTA range of padded arcs (multiple of 4)
     int cache_items = 0;  // largest per-CTA number of items
+    int cache_chunks = 0; // largest per-CTA number of chunks
     double R = 0;       // bound on the ⊕ exponents, kernel units
     double H = 0;       // Log: linear copy of a stored value v = 2^(v + H), kernel units
     void release() {
@@ -147,13 +148,13 @@ constexpr double kItemCost = 12.0;
 constexpr int kLongRow = 128;
 constexpr int kMinSegment = 64;
 constexpr int kMaxSlotsPerRow = 160;
-// Target cost (arcs + kItemCost per item) of a dynamically scheduled chunk: about two chunks per warp of
-// the CTA, between 48 and 192 (measured optimum for the 30k-state denominator: 160-190; small graphs want
-// more, smaller chunks).  MK_CHUNK_ARCS overrides, for tuning.
+// Target cost (arcs + kItemCost per item) of a dynamically scheduled chunk: about six chunks per warp of
+// the CTA, between 24 and 44 (measured optimum for the 30k-state denominator with register-destination
+// gathers: 40-48; small chunks keep the tail of a frame short).  MK_CHUNK_ARCS overrides, for tuning.
 static double chunk_cost_target(double cta_total) {
     const char* e = getenv("MK_CHUNK_ARCS");
     if (e && atoi(e) >= 4) return atoi(e);
-    return std::min(192.0, std::max(48.0, cta_total / (2.0 * kSharedWarps)));
+    return std::min(44.0, std::max(24.0, cta_total / (6.0 * kSharedWarps)));
 }
 
 template <typename T> struct DirHost {
@@ -161,7 +162,7 @@ template <typename T> struct DirHost {
     std::vector<int2> item_arcs, item_pa;
     std::vector<int> cta_chunks, pidx;
     std::vector<T> pw;
-    int cache_cap = 0, cache_items = 0;
+    int cache_cap = 0, cache_items = 0, cache_chunks = 0;
 };
 
 // gflags[r] (kernels.cuh, item.w): run bookkeeping of row merging.  `tied[r]` = row r must stay in the
@@ -258,6 +259,7 @@ static void build_plan(const std::vector<int>& ptr, const std::vector<Arc<T>>& a
         std::stable_sort(d.chunks.begin() + first, d.chunks.end(),
                          [](const int4& x, const int4& y) { return x.y - x.x > y.y - y.x; });
         d.cta_chunks[k + 1] = int(d.chunks.size());
+        d.cache_chunks = std::max(d.cache_chunks, int(d.chunks.size() - first));
         d.cache_cap = std::max(d.cache_cap, int(d.pidx.size()) - cta_arc0);
         d.cache_items = std::max(d.cache_items, cta_items[k + 1] - cta_items[k]);
     }
@@ -275,6 +277,7 @@ template <typename T> static int upload_plan(const DirHost<T>& hst, const std::v
     TRY(upload(arcs, &dev.arcs));
     dev.cache_cap = hst.cache_cap;
     dev.cache_items = hst.cache_items;
+    dev.cache_chunks = hst.cache_chunks;
     return MK_OK;
 }
 
@@ -638,6 +641,10 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     p.barrier = static_cast<unsigned*>(bt->barrier.p);
     p.do_fwd = p.do_bwd = p.do_post = 0;
     p.bwd_dead_ok = c.expanded ? 0 : 1;
+    p.ablate = getenv("MK_ABLATE") ? atoi(getenv("MK_ABLATE")) : 0;
+#ifdef MK_ABLATE
+    { int ns = (p.ablate & 16) ? 1 : 0; CK(cudaMemcpyToSymbol(g_no_stores, &ns, sizeof ns)); }
+#endif
     switch (mode) {
         case MODE_ALPHA: case MODE_BEST: p.do_fwd = 1; break;
         case MODE_BETA: p.do_bwd = 1; p.beta_out = static_cast<T*>(gr.alpha.p); break;
@@ -656,7 +663,7 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
         const DirDev& dd = phase == 0 ? g->fwd : g->bwd;
         // shared-memory arc cache of this sweep when it fits next to the scalars, queues and rings
         size_t smem = scal;
-        const size_t need = arc_cache_bytes(dd.cache_cap, dd.cache_items, sizeof(T));
+        const size_t need = arc_cache_bytes(dd.cache_cap, dd.cache_items, dd.cache_chunks, sizeof(T));
         const bool sa = smem + need <= bt->max_smem_optin;
         p.cache_f = p.cache_b = p.cache_items_f = p.cache_items_b = 0;
         if (sa) {
