@@ -138,6 +138,17 @@ int mk_bestpath_host(mk_batch* b, const void* ll, int64_t stride_b, int64_t stri
                      int64_t stride_n, int64_t D, int64_t T, int expanded,
                      const int32_t* seqlens, int32_t* out_path, void* out_score);
 
+/* LF-MMI gradient — the step after the two pdfposteriors calls of the reference's training
+ * loop (examples/test_cuda.jl:118-152: permutedims :120, numerator / denominator posteriors
+ * :140-143, their difference :152):
+ *   grad[b, n, d] = scale * (den_post[b, d, n] - num_post[b, d, n])   for n < seqlens[b], else 0
+ * num_post / den_post: (B, D, N) b-fastest device arrays as written by mk_pdfposteriors; grad:
+ * the network's (B, T, D) device array, element strides given; seqlens_dev: DEVICE int32[B] or
+ * NULL.  With scale = 1 this is d(-Σ_b (logZ_num - logZ_den)) / d(loglikes). */
+int mk_lfmmi_grad(int dtype, const void* num_post, const void* den_post, int64_t B, int64_t D,
+                  int64_t N, const int32_t* seqlens_dev, double scale, void* grad,
+                  int64_t stride_b, int64_t stride_n, int64_t stride_d, void* stream);
+
 /* Instrumentation: number of kernels this library launched on the calling thread since
  * the last reset (bench.py's gpu_launches), and workspace bytes held by a batch. */
 int64_t mk_launch_count(int reset);

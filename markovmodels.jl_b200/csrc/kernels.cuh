@@ -1332,6 +1332,38 @@ template <typename T> __global__ void total_kernel(const T* zsum, const T* lz, T
 }
 
 // ================================================================================================
+// LF-MMI gradient (caller pattern examples/test_cuda.jl:118-152: permutedims :120, the two
+// pdfposteriors calls :140-143, their difference :152):
+//   grad[b][n][d] = scale * (den[n][d][b] - num[n][d][b])        for n < len[b], else 0
+// num / den are (B, D, N) b-fastest posterior arrays = [N][D][B]; grad is the network's (B, T, D) array
+// with element strides (gsb, gsn, gsd).  One 32 x 32 (d, b) tile per block: transposes through shared
+// memory so that both sides are coalesced.   grid (ceil(D/32), ceil(B/32), N), block (32, 8)
+// ================================================================================================
+template <typename T>
+__global__ void lfmmi_grad_kernel(const T* num, const T* den, int B, int D, int N, const int* seqlens, T scale, T* grad,
+                                  long long gsb, long long gsn, long long gsd) {
+    __shared__ T tile[32][33];
+    const int n = blockIdx.z, d0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+    for (int k = threadIdx.y; k < 32; k += 8) {
+        const int d = d0 + k, b = b0 + threadIdx.x;
+        T v = T(0);
+        if (d < D && b < B) {
+            const size_t i = (size_t(n) * D + d) * B + b;
+            v = scale * (den[i] - num[i]);
+        }
+        tile[k][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += 8) {
+        const int b = b0 + k, d = d0 + threadIdx.x;
+        if (b < B && d < D) {
+            const bool live = !seqlens || n < seqlens[b];
+            grad[b * gsb + n * gsn + d * gsd] = live ? tile[threadIdx.x][k] : T(0);
+        }
+    }
+}
+
+// ================================================================================================
 // Layout conversion for the αrecursion / βrecursion entry points:
 //   src [N1][S][U4] (shared-graph layout, normalised) + C[n][u] -> dst[(off_b + s) + total*n]
 //   (reference layout, un-normalised)

@@ -1021,6 +1021,28 @@ int mk_batch_info(const mk_batch* b, int64_t* B, int64_t* total_states_hat) {
 
 int64_t mk_batch_workspace_bytes(const mk_batch* b) { return b ? int64_t(b->ws_bytes()) : 0; }
 
+int mk_lfmmi_grad(int dtype, const void* num_post, const void* den_post, int64_t B, int64_t D, int64_t N,
+                  const int32_t* seqlens_dev, double scale, void* grad, int64_t stride_b, int64_t stride_n,
+                  int64_t stride_d, void* stream) {
+    if (dtype != MK_F32 && dtype != MK_F64) return fail(MK_EINVAL, "unknown dtype %d", dtype);
+    if (!num_post || !den_post || !grad) return fail(MK_EINVAL, "null buffer");
+    if (B <= 0 || D <= 0 || N <= 0 || N > 65535 || (B + 31) / 32 > 65535)
+        return fail(MK_EINVAL, "DimensionMismatch: bad (B, D, N) = (%lld, %lld, %lld)", (long long)B, (long long)D, (long long)N);
+    dim3 grid(unsigned((D + 31) / 32), unsigned((B + 31) / 32), unsigned(N)), block(32, 8);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == MK_F32)
+        lfmmi_grad_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(num_post), static_cast<const float*>(den_post),
+                                                        int(B), int(D), int(N), seqlens_dev, float(scale),
+                                                        static_cast<float*>(grad), stride_b, stride_n, stride_d);
+    else
+        lfmmi_grad_kernel<double><<<grid, block, 0, st>>>(static_cast<const double*>(num_post), static_cast<const double*>(den_post),
+                                                         int(B), int(D), int(N), seqlens_dev, scale,
+                                                         static_cast<double*>(grad), stride_b, stride_n, stride_d);
+    CK(cudaGetLastError());
+    ++g_launches;
+    return MK_OK;
+}
+
 #ifdef MK_PROFILE_BARRIER
 // debug: per-CTA cycle counters of grid_sync (work, CTA wait, grid wait); resets after reading
 int mk_debug_barrier_profile(unsigned long long* out /* [148*4] */) {

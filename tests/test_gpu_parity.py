@@ -218,6 +218,46 @@ def test_denominator_vs_oracle(torch, mm, orc, dtype, force):
     check_posteriors(mm, orc, [g] * B, D, V, lens, post, ttl, dtype)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_linear_copies_underflow_falls_back_exactly(torch, mm, orc, dtype):
+    """The shared-graph kernel accumulates linear copies 2^(v + H) of the state vectors and redoes a row
+    exactly (log domain) when its linear sum underflows.  A long left-to-right chain with sharply peaked
+    emissions drives most rows of most frames far below 2^-126 of the frame maximum; posteriors and
+    log-likelihoods must still match the Float64 oracle."""
+    K = mm.LogSemiring[dtype]
+    rng = np.random.default_rng(77)
+    S, T, B = 90, 120, 8
+    D = S
+    f, pdf = mm.graphs.hmm3(K, S)  # left-to-right, self-loop + forward arc per state
+    # every frame strongly prefers one pdf (60 nats above the rest): the forward mass collapses on a
+    # narrow band, everything else is ~e^-60 per frame away from it
+    V = (rng.standard_normal((B, T, D)) * 2).astype(dtype)
+    for b in range(B):
+        best = np.minimum(np.arange(T) * S // T + rng.integers(0, 3, T), S - 1)
+        V[b, np.arange(T), best] += 60.0
+    lens = rng.integers(T - 10, T + 1, B).astype(np.int32)
+    b_ = gpu_batch(mm, [(f, pdf)] * B, D, "shared")
+    post, ttl = mm.pdfposteriors(b_, dev(torch, V), seqlengths=lens)
+    K64 = mm.LogSemiring[np.float64]
+    xpost, xttl = orc.pdfposteriors(orc_graphs(orc, [(f.astype(K64), pdf)] * B, D), V.astype(np.float64), lens)
+    assert np.all(np.isfinite(xttl))
+    np.testing.assert_allclose(ttl.cpu().numpy(), xttl, rtol=1e-4 if dtype == np.float32 else 1e-9)
+    np.testing.assert_allclose(post.cpu().numpy(), xpost, **TOL[dtype])
+    A = mm.αrecursion(b_, dev(torch, V), seqlengths=lens).cpu().numpy()
+    og = orc_graphs(orc, [(f.astype(K64), pdf)] * B, D)
+    for k in range(B):
+        oA, _ = orc.alpha_beta(og[k], V[k].astype(np.float64), lens[k], want_beta=False)
+        got = A[b_.offsets[k]:b_.offsets[k + 1]]
+        if dtype == np.float64:
+            assert_states_close(got, oA, dtype)
+        else:
+            # Float32: a state 4 000 log2 units below the frame maximum is stored with ulp(4000) = 2.4e-4
+            # absolute resolution (the reference's un-normalised Float32 α has ulp(|α|) everywhere)
+            np.testing.assert_array_equal(np.isneginf(got), np.isneginf(oA))
+            fin = ~np.isneginf(oA)
+            np.testing.assert_allclose(got[fin], oA[fin], rtol=1e-4, atol=5e-3)
+
+
 def test_row_merging_is_transparent(torch, mm, orc):
     """The graph compiler merges runs of adjacent states with identical out-arc lists (the A/B pairs of
     the chain topology).  With and without merging (MK_NO_MERGE=1) the results agree with each other
