@@ -33,6 +33,10 @@ METRIC = "LF-MMI denominator forward-backward frames/sec (batch x T)"
 UNIT = "frames/s"
 B_PER_GPU, T_FRAMES, N_PDF, N_TOKENS, SEED = 128, 150, 3000, 15000, 303
 HBM_FALLBACK_GBS = 6650.0
+# dram__bytes_read.sum + dram__bytes_write.sum of the two shared_fb_kernel launches of ONE pdfposteriors call on
+# this workload, from the `ncu --set full` capture summarised in profiles/r01_shared_fb_kernel_ncu.md
+# (forward 0.218 + 3.470 GB, backward 2.763 + 2.542 GB); null for any other shape
+NCU_DRAM_BYTES_PER_LAUNCH = 8.993e9
 
 
 def workload_config(n_gpus, b_per_gpu, frames):
@@ -251,12 +255,17 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})",
-                     "kernel": "shared_fb_kernel<float, Log>", "kernel_ms": kernel_ms,
+                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (B, T) == (B_PER_GPU, T_FRAMES) else None,
+                     "traffic_unit": "bytes per launch pair (ncu --set full, profiles/r01_shared_fb_kernel_ncu.md)",
+                     "algorithmic_bytes_per_launch": bytes_per_unit * units,
+                     "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})",
+                     "kernel": "shared_fb_kernel<float, Log> (forward sweep + backward sweep: two cooperative "
+                               "launches, timed together)", "kernel_ms": kernel_ms,
                      "bytes_per_frame_utt": bytes_per_unit, "units_per_launch": units,
                      "kernel_share_of_step": kernel_ms / (ms_total / args.steps),
-                     "note": "HBM is not the binding ceiling of this kernel: the recursion is bound by the L2 "
-                             "gather of state vectors and the MUFU ex2 rate (DESIGN.md)"},
+                     "note": "HBM is not the binding ceiling of this kernel: the recursion is bound by the latency of "
+                             "the L2 gathers of state vectors per warp and the per-frame grid barrier (DESIGN.md "
+                             "section 4, profiles/)"},
         "mean_logz": logz_mean,
     }
     if world == 1 and not args.skip_cpu_baseline:
