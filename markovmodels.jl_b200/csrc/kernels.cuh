@@ -892,7 +892,8 @@ __host__ __device__ inline size_t arc_cache_bytes(int cap, int items, int chunks
     return size_t(cap) * (4 + tsize) + ((size_t(items) * 24 + 15) & ~size_t(15)) + size_t(chunks) * 16;
 }
 __host__ __device__ inline size_t shared_scalars_bytes(int U4, size_t tsize) {
-    return (size_t(U4) * (2 * sizeof(double) + 3 * tsize + sizeof(int)) + 16 + 15) & ~size_t(15);
+    return (size_t(U4) * (2 * sizeof(double) + 3 * tsize + sizeof(int)) + size_t((U4 + 127) / 128) * sizeof(int) + 16 + 15) &
+           ~size_t(15);
 }
 
 // PHASE 0: forward sweep (αrecursion), leaves log Z in p.lz2.  PHASE 1: backward sweep (βrecursion + γ).
@@ -907,7 +908,7 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
     T* s_g = s_shift + U4;                                // [U4] Ca_n + Cb_n - log Z
     T* s_z = s_g + U4;                                    // [U4] per-frame posterior mass
     int* s_key = reinterpret_cast<int*>(s_z + U4);        // [U4] running maxima
-    int* s_next = s_key + U4;                             // dynamic chunk counter
+    int* s_next = s_key + U4;                             // [ntiles] dynamic chunk counters, one per utterance tile
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t frame = size_t(S) * U4;      // β-side vectors: Ŝ rows
     const size_t frame_q = size_t(p.Sq) * U4;  // α store: Ŝ + merged-run rows
@@ -935,7 +936,6 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
     // ---------------------------------------------------------------- forward (αrecursion)
     if (PHASE == 0) {
         const int c0 = p.fwd.cta_chunks[blockIdx.x], c1 = p.fwd.cta_chunks[blockIdx.x + 1];
-        const int work1 = c0 + (c1 - c0) * p.ntiles;  // (chunk, tile) pairs
         for (int n = 0; n < p.N1; ++n) {
             if (n >= 1 && p.n_long) {
                 fwd_combine<T, SR>(p, n - 1, s_shift, s_key);
@@ -949,39 +949,46 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
                 s_key[u] = kKeyMin;
                 if (blockIdx.x == 0) p.Coff[size_t(n) * U4 + u] = s_C[u];
             }
-            if (threadIdx.x == 0) *s_next = c0;
+            for (int t = threadIdx.x; t < p.ntiles; t += blockDim.x) s_next[t] = c0;
             __syncthreads();
-            for (;;) {  // warps pull (chunk, tile) pairs, largest chunks first
-                int wk = 0;
-                if (lane == 0) wk = atomicAdd(s_next, 1);
-                wk = __shfl_sync(0xffffffffu, wk, 0);
-                if (wk >= work1) break;
-                if (MK_ABL(p, 4)) continue;
-                const int4 ch = fwd_src.chunk(c0 + (wk - c0) / p.ntiles);
-                const int uoff = ((wk - c0) % p.ntiles) * kTileUtts + lane * 4;
-                if (uoff < U4) {  // (lanes beyond the batch stay converged for the next pull)
-                    FwdFin<T, SR> fin(p, p.alpha + size_t(n > 0 ? n - 1 : 0) * frame_q, p.alpha + size_t(n) * frame_q,
-                                      p.flin + size_t(n & 1) * frame_q, p.part + size_t(n & 1) * p.n_slots * U4,
-                                      p.E + size_t(n) * p.Dh * U4, uoff, s_shift);
-                    if (n == 0) {
-                        for (int i = ch.z; i < ch.w; ++i) {
-                            fin.prefetch(fwd_src, i);
-                            if (fin.it.z >= 0) continue;
-                            const T a0 = __ldg(p.init_dense + unsigned(fin.it.x) / unsigned(U4 >> 2));  // A[:,1] = α̂ ⊗ e₁  (:68)
-                            V4<T> val;
+            // Utterance tiles in turn; inside a tile the warps pull the CTA's chunks dynamically, largest first.
+            // The finaliser (lane pointers, per-utterance scalars, running maxima) is set up once per tile.
+            for (int tile = 0; tile < p.ntiles; ++tile) {
+                const bool live = tile * kTileUtts + lane * 4 < U4;  // (lanes beyond the batch stay converged for the pulls)
+                const int uoff = live ? tile * kTileUtts + lane * 4 : 0;
+                FwdFin<T, SR> fin(p, p.alpha + size_t(n > 0 ? n - 1 : 0) * frame_q, p.alpha + size_t(n) * frame_q,
+                                  p.flin + size_t(n & 1) * frame_q, p.part + size_t(n & 1) * p.n_slots * U4,
+                                  p.E + size_t(n) * p.Dh * U4, uoff, s_shift);
+                // gather source: the previous frame's linear copies (Log) / the vector itself (Tropical)
+                const T* gsrc = (SR == SR_LOG ? p.flin + size_t((n - 1) & 1) * frame_q : fin.prev) + uoff;
+                for (;;) {
+                    int wk = 0;
+                    if (lane == 0) wk = atomicAdd(s_next + tile, 1);
+                    wk = __shfl_sync(0xffffffffu, wk, 0);
+                    if (wk >= c1) break;
+                    if (MK_ABL(p, 4)) continue;
+                    const int4 ch = fwd_src.chunk(wk);
+                    if (live) {
+                        if (n == 0) {
+                            for (int i = ch.z; i < ch.w; ++i) {
+                                fin.prefetch(fwd_src, i);
+                                if (fin.it.z >= 0) continue;
+                                const T a0 = __ldg(p.init_dense + unsigned(fin.it.x) / unsigned(U4 >> 2));  // A[:,1] = α̂ ⊗ e₁  (:68)
+                                V4<T> val;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) val.v[j] = a0 + fin.e.v[j];
-                            fin.store(val);
+                                for (int j = 0; j < 4; ++j) val.v[j] = a0 + fin.e.v[j];
+                                fin.store(val);
+                            }
+                        } else {
+                            stream_items<T, SR, SA>(fwd_src, ch.z, ch.w, gsrc, fin);
                         }
-                    } else {
-                        // gather source: the previous frame's linear copies (Log) / the vector itself (Tropical)
-                        const T* gsrc = SR == SR_LOG ? p.flin + size_t((n - 1) & 1) * frame_q : fin.prev;
-                        stream_items<T, SR, SA>(fwd_src, ch.z, ch.w, gsrc + uoff, fin);
                     }
+                    __syncwarp();
+                }
+                if (live) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) atomicMax(&s_key[uoff + j], fkey(float(fin.mx[j])));
                 }
-                __syncwarp();
             }
             __syncthreads();
             for (int u = threadIdx.x; u < U4; u += blockDim.x) {
@@ -1016,7 +1023,6 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
     }
     __syncthreads();
     const int c0 = p.bwd.cta_chunks[blockIdx.x], c1 = p.bwd.cta_chunks[blockIdx.x + 1];
-    const int work1 = c0 + (c1 - c0) * p.ntiles;
     int* gkey_b = p.gkey + size_t(p.N1) * U4;
     double* Cb = p.Coff + size_t(p.N1) * U4;
     for (int n = p.N1 - 1; n >= 0; --n) {
@@ -1033,32 +1039,38 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
                 s_g[u] = (lz == double(neg_inf<T>())) ? T(0) : T(__ldcg(p.Coff + size_t(n) * U4 + u) + s_C[u] - lz);
             }
         }
-        if (threadIdx.x == 0) *s_next = c0;
+        for (int t = threadIdx.x; t < p.ntiles; t += blockDim.x) s_next[t] = c0;
         __syncthreads();
-        for (;;) {
-            int wk = 0;
-            if (lane == 0) wk = atomicAdd(s_next, 1);
-            wk = __shfl_sync(0xffffffffu, wk, 0);
-            if (wk >= work1) break;
-            if (MK_ABL(p, 4)) continue;
-            const int4 ch = bwd_src.chunk(c0 + (wk - c0) / p.ntiles);
-            const int uoff = ((wk - c0) % p.ntiles) * kTileUtts + lane * 4;
-            if (uoff < U4) {
-                BwdFin<T, SR> fin(p, p.bt + size_t((n + 1) & 1) * frame, p.bt + size_t(n & 1) * frame,
-                                  p.blin + size_t(n & 1) * frame, p.E + size_t(n) * p.Dh * U4,
-                                  p.alpha + size_t(n) * frame_q, n, uoff, s_shift, s_g);
-                if (n == p.N1 - 1) {
-                    for (int i = ch.z; i < ch.w; ++i) {
-                        fin.prefetch(bwd_src, i);
-                        V4<T> beta;
+        for (int tile = 0; tile < p.ntiles; ++tile) {  // (as in the forward sweep)
+            const bool live = tile * kTileUtts + lane * 4 < U4;
+            const int uoff = live ? tile * kTileUtts + lane * 4 : 0;
+            BwdFin<T, SR> fin(p, p.bt + size_t((n + 1) & 1) * frame, p.bt + size_t(n & 1) * frame,
+                              p.blin + size_t(n & 1) * frame, p.E + size_t(n) * p.Dh * U4,
+                              p.alpha + size_t(n) * frame_q, n, uoff, s_shift, s_g);
+            const T* gsrc = (SR == SR_LOG ? p.blin + size_t((n + 1) & 1) * frame : fin.bt_next) + uoff;
+            for (;;) {
+                int wk = 0;
+                if (lane == 0) wk = atomicAdd(s_next + tile, 1);
+                wk = __shfl_sync(0xffffffffu, wk, 0);
+                if (wk >= c1) break;
+                if (MK_ABL(p, 4)) continue;
+                const int4 ch = bwd_src.chunk(wk);
+                if (live) {
+                    if (n == p.N1 - 1) {
+                        for (int i = ch.z; i < ch.w; ++i) {
+                            fin.prefetch(bwd_src, i);
+                            V4<T> beta;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) beta.v[j] = T(0);  // B[:,end] = 1̄  (:104)
-                        fin.finish(beta);
+                            for (int j = 0; j < 4; ++j) beta.v[j] = T(0);  // B[:,end] = 1̄  (:104)
+                            fin.finish(beta);
+                        }
+                    } else {
+                        stream_items<T, SR, SA>(bwd_src, ch.z, ch.w, gsrc, fin);
                     }
-                } else {
-                    const T* gsrc = SR == SR_LOG ? p.blin + size_t((n + 1) & 1) * frame : fin.bt_next;
-                    stream_items<T, SR, SA>(bwd_src, ch.z, ch.w, gsrc + uoff, fin);
                 }
+                __syncwarp();
+            }
+            if (live) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (n > 0) atomicMax(&s_key[uoff + j], fkey(float(fin.mx[j])));
@@ -1068,7 +1080,6 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
                     }
                 }
             }
-            __syncwarp();
         }
         __syncthreads();
         for (int u = threadIdx.x; u < U4; u += blockDim.x) {
