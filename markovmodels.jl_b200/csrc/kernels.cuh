@@ -560,8 +560,8 @@ template <typename T> struct SharedParams {
     const Arc<T>* fwd_long_arcs;                  // pseudo arcs {slot, 1̄} of the long rows
     int n_slots; T* part;                         // [2][n_slots][U4] segment partials
     const T* init_dense;                          // α̂ as a dense vector [S] (kernel units)
-    const T* E;      // expanded, transposed emissions minus emax (kernel units): [N1][Dh][U4]
-    const T* emax;   // [N1][U4]
+    const T* E;      // expanded, transposed emissions (kernel units, NOT normalised): [N1][Dh][U4]
+    const T* emax;   // [N1][U4] per-frame emission maxima (kernel units), subtracted together with the shift
     T* alpha;        // [N1][Sq][U4]  normalised a_n, then the merged-run sources q_g
     T* bt;           // [2][S][U4]    b_{n+1} ⊗ e'_{n+1} ping-pong
     T* flin;         // [2][Sq][U4]   Log: linear copies 2^(a_n + H_f) of the forward vector (ping-pong), the gather source
@@ -630,7 +630,8 @@ __device__ __forceinline__ void fwd_combine(const SharedParams<T>& p, int m, con
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                val.v[j] = val.v[j] + e.v[j] - s_shift[uoff + j];
+                // (e - emax first: the two are close for the pdfs that matter, the difference is exact)
+                val.v[j] = val.v[j] + (e.v[j] - __ldg(p.emax + size_t(m) * U4 + uoff + j)) - s_shift[uoff + j];
                 atomicMax(&s_key[uoff + j], fkey(float(val.v[j])));
             }
             st4_cg(p.alpha + size_t(m) * frame + size_t(r) * U4 + uoff, val);
@@ -675,16 +676,20 @@ template <typename T, int SR> struct FwdFin {
     const T* En_l;      //   this frame's emissions
     int uoff;
     T c[4];             // -shift_n of the lane's utterances
-    T mx[4];            // running maxima of this chunk's a values, flushed once per chunk
+    T cm[4];            // -emax_n: e'_n = e_n - emax_n (formed first: exact for the pdfs near the maximum)
+    T mx[4];            // running maxima of this tile's a values, flushed once per tile
     int4 it;            // the item being streamed and its emissions, requested when the item starts
     V4<T> e;
     V4<T> qacc;         // merged run: Σ of the members' linear copies (Log) / their maximum (Tropical)
     unsigned qfirst;    // row offset of the run's first member
     __device__ __forceinline__ FwdFin(const SharedParams<T>& p_, const T* prev_, T* cur, T* lin, T* part, const T* En,
-                                      int uoff_, const T* s_shift)
+                                      int uoff_, const T* s_shift, const T* emax_n)
         : p(p_), prev(prev_), cur_l(cur + uoff_), lin_l(lin + uoff_), part_l(part + uoff_), En_l(En + uoff_), uoff(uoff_) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { c[j] = -s_shift[uoff_ + j]; mx[j] = neg_inf<T>(); qacc.v[j] = T(0); }
+        for (int j = 0; j < 4; ++j) {
+            c[j] = -s_shift[uoff_ + j]; cm[j] = -__ldg(emax_n + uoff_ + j);
+            mx[j] = neg_inf<T>(); qacc.v[j] = T(0);
+        }
         qfirst = 0;
     }
     template <class Src> __device__ __forceinline__ void prefetch(const Src& src, int item) {
@@ -749,7 +754,7 @@ template <typename T, int SR> struct FwdFin {
             return;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) val.v[j] += e.v[j] + c[j];  // ⊗ e_n (:71), normalised
+        for (int j = 0; j < 4; ++j) val.v[j] += (e.v[j] + cm[j]) + c[j];  // ⊗ e_n (:71), normalised
         store(val);
     }
 };
@@ -766,6 +771,7 @@ template <typename T, int SR> struct BwdFin {
     int n, uoff;
     bool post_on;       // this frame and these utterances have posterior rows
     T c[4], g[4];       // -shift_n and Ca_n + Cb_n - log Z of the lane's utterances
+    T cm[4];            // -emax_n: b_n ⊗ e'_n = b_n + e_n - emax_n
     T mx[4], zs[4];     // running maxima of b ⊗ e and posterior mass, flushed once per chunk
     int4 it;            // the item being streamed (it.z = pdf), its emissions and α, requested when the item starts
     V4<T> e, a;
@@ -777,6 +783,7 @@ template <typename T, int SR> struct BwdFin {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             c[j] = -s_shift[uoff_ + j]; g[j] = s_g[uoff_ + j];
+            cm[j] = -__ldg(p.emax + size_t(n_) * p.U4 + uoff_ + j);
             mx[j] = neg_inf<T>(); zs[j] = T(0); last.v[j] = neg_inf<T>();
         }
         beta_l = p.beta_out ? p.beta_out + size_t(n_) * p.S * p.U4 + uoff_ : nullptr;
@@ -820,7 +827,7 @@ template <typename T, int SR> struct BwdFin {
         if (n > 0) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                beta.v[j] += e.v[j];
+                beta.v[j] += e.v[j] + cm[j];
                 mx[j] = max_(mx[j], beta.v[j]);
             }
             st4_cg(bt_l + size_t(unsigned(it.x)) * 4, beta);
@@ -958,7 +965,7 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
                 const int uoff = live ? tile * kTileUtts + lane * 4 : 0;
                 FwdFin<T, SR> fin(p, p.alpha + size_t(n > 0 ? n - 1 : 0) * frame_q, p.alpha + size_t(n) * frame_q,
                                   p.flin + size_t(n & 1) * frame_q, p.part + size_t(n & 1) * p.n_slots * U4,
-                                  p.E + size_t(n) * p.Dh * U4, uoff, s_shift);
+                                  p.E + size_t(n) * p.Dh * U4, uoff, s_shift, p.emax + size_t(n) * U4);
                 // gather source: the previous frame's linear copies (Log) / the vector itself (Tropical)
                 const T* gsrc = (SR == SR_LOG ? p.flin + size_t((n - 1) & 1) * frame_q : fin.prev) + uoff;
                 for (;;) {
@@ -976,7 +983,7 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
                                 const T a0 = __ldg(p.init_dense + unsigned(fin.it.x) / unsigned(U4 >> 2));  // A[:,1] = α̂ ⊗ e₁  (:68)
                                 V4<T> val;
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) val.v[j] = a0 + fin.e.v[j];
+                                for (int j = 0; j < 4; ++j) val.v[j] = a0 + (fin.e.v[j] + fin.cm[j]);
                                 fin.store(val);
                             }
                         } else {
@@ -1110,6 +1117,8 @@ template <typename T> struct EmisParams {
     const int* utt_b;          // [U4]
     int U4;
     T* E;
+    T scale;                   // log2(e) for the Log semiring (the kernels work in log2 units), 1 for Tropical
+    int* emax_key;             // [N1][U4] ordered keys of the per-(frame, utterance) maxima of E, or null
 };
 
 template <typename T>
@@ -1135,34 +1144,30 @@ template <typename T> __global__ void expand_transpose_kernel(EmisParams<T> p) {
                 v = emission<T>(p.ll, p.sb, p.sd, p.sn, p.D, p.expanded, L, b, d, n);
             }
         }
-        tile[k][threadIdx.x] = v;
+        tile[k][threadIdx.x] = v * p.scale;
     }
     __syncthreads();
+    T m = neg_inf<T>();
     for (int k = threadIdx.y; k < 32; k += 8) {
         int d = d0 + k, u = u0 + threadIdx.x;
-        if (d < p.Dh && u < p.U4) p.E[(size_t(n) * p.Dh + d) * p.U4 + u] = tile[threadIdx.x][k];
+        if (d < p.Dh && u < p.U4) {
+            const T v = tile[threadIdx.x][k];
+            p.E[(size_t(n) * p.Dh + d) * p.U4 + u] = v;
+            m = max_(m, v);
+        }
     }
+    // per-(frame, utterance) maximum over the pdfs: the emission part of the per-frame normaliser
+    // (the recursion kernels subtract it together with the shift; E itself stays un-normalised)
+    if (p.emax_key && u0 + threadIdx.x < p.U4 && m > neg_inf<T>())
+        atomicMax(p.emax_key + size_t(n) * p.U4 + u0 + threadIdx.x, fkey(float(m)));
 }
 
-// emax[n][u] = scale * max_d E[n][d][u] (0 when the whole column is 0̄);
-// E[n][d][u] = scale * (E[n][d][u] - max).   scale = log2(e): the kernel works in log2 units.
-// grid (ceil(U4/32), N1), block (32, 8)
-template <typename T> __global__ void emission_max_kernel(T* E, T* emax, int Dh, int U4, T scale) {
-    __shared__ T red[8][32];
-    const int n = blockIdx.y, u = blockIdx.x * 32 + threadIdx.x;
-    T* En = E + size_t(n) * Dh * U4;
-    T m = neg_inf<T>();
-    if (u < U4)
-        for (int d = threadIdx.y; d < Dh; d += 8) m = max_(m, En[size_t(d) * U4 + u]);
-    red[threadIdx.y][threadIdx.x] = m;
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 8; ++k) m = max_(m, red[k][threadIdx.x]);
-    if (m == neg_inf<T>()) m = T(0);
-    if (u < U4) {
-        if (threadIdx.y == 0) emax[size_t(n) * U4 + u] = m * scale;
-        for (int d = threadIdx.y; d < Dh; d += 8) En[size_t(d) * U4 + u] = (En[size_t(d) * U4 + u] - m) * scale;
-    }
+// emax[n][u] from its key (0 when the whole column is 0̄; keys start as 0x80808080 = memset 0x80)
+template <typename T> __global__ void emission_max_decode_kernel(const int* key, T* emax, int count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float m = fkey_inv(key[i]);
+    emax[i] = (m > -3.0e38f && m < 3.0e38f) ? T(m) : T(0);
 }
 
 // ================================================================================================

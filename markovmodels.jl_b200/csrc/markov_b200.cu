@@ -515,7 +515,7 @@ struct Group {  // utterances sharing one graph, run by shared_fb_kernel
     bool vec4 = false;
     int* d_utt_b = nullptr;
     long long* d_utt_off = nullptr;
-    DevBuf E, emax, alpha, bt, flin, blin, part, gkey, coff, lz2;
+    DevBuf E, emax, emax_key, alpha, bt, flin, blin, part, gkey, coff, lz2;
 };
 
 struct mk_batch {
@@ -541,7 +541,7 @@ struct mk_batch {
         for (auto& gr : groups) {
             cudaFree(gr.d_utt_b); cudaFree(gr.d_utt_off);
             gr.E.release(); gr.alpha.release(); gr.bt.release(); gr.flin.release(); gr.blin.release();
-            gr.part.release(); gr.gkey.release(); gr.coff.release(); gr.emax.release(); gr.lz2.release();
+            gr.part.release(); gr.gkey.release(); gr.coff.release(); gr.emax.release(); gr.emax_key.release(); gr.lz2.release();
         }
         DevBuf* all[] = {&small_descs, &small_alpha, &small_ca, &zsum, &lz, &seqlens, &barrier, &trace,
                          &h_ll, &h_post, &h_logz, &h_path};
@@ -593,6 +593,7 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     TRY(gr.part.ensure(2 * size_t(std::max(g->n_slots, 1)) * U4 * sizeof(T)));
     TRY(gr.gkey.ensure(2 * size_t(N1) * U4 * sizeof(int)));
     TRY(gr.emax.ensure(size_t(N1) * U4 * sizeof(T)));
+    if (SR == SR_LOG) TRY(gr.emax_key.ensure(size_t(N1) * U4 * sizeof(int)));
     TRY(gr.lz2.ensure(size_t(U4) * sizeof(double)));
     TRY(gr.coff.ensure(2 * size_t(N1) * U4 * sizeof(double)));
 
@@ -600,13 +601,18 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     ep.ll = static_cast<const T*>(c.ll); ep.sb = c.sb; ep.sd = c.sd; ep.sn = c.sn;
     ep.D = int(c.D); ep.Tn = int(c.T); ep.expanded = c.expanded; ep.Dh = Dh; ep.N1 = N1;
     ep.seqlens = d_seqlens; ep.utt_b = gr.d_utt_b; ep.U4 = U4; ep.E = static_cast<T*>(gr.E.p);
+    ep.scale = SR == SR_LOG ? T(1.4426950408889634) : T(1);
+    ep.emax_key = SR == SR_LOG ? static_cast<int*>(gr.emax_key.p) : nullptr;
+    // keys start below every finite value (0x80808080 decodes to -3.4e38)
+    if (SR == SR_LOG) CK(cudaMemsetAsync(gr.emax_key.p, 0x80, size_t(N1) * U4 * sizeof(int), c.stream));
     dim3 eg((Dh + 31) / 32, (U4 + 31) / 32, N1), eb(32, 8);
     expand_transpose_kernel<T><<<eg, eb, 0, c.stream>>>(ep);
     CK(cudaGetLastError());
     ++g_launches;
     if (SR == SR_LOG) {
-        emission_max_kernel<T><<<dim3((U4 + 31) / 32, N1), dim3(32, 8), 0, c.stream>>>(
-            static_cast<T*>(gr.E.p), static_cast<T*>(gr.emax.p), Dh, U4, T(1.4426950408889634));
+        const int count = N1 * U4;
+        emission_max_decode_kernel<T><<<(count + 255) / 256, 256, 0, c.stream>>>(
+            static_cast<const int*>(gr.emax_key.p), static_cast<T*>(gr.emax.p), count);
         CK(cudaGetLastError());
         ++g_launches;
     } else {

@@ -242,7 +242,11 @@ def test_linear_copies_underflow_falls_back_exactly(torch, mm, orc, dtype):
     xpost, xttl = orc.pdfposteriors(orc_graphs(orc, [(f.astype(K64), pdf)] * B, D), V.astype(np.float64), lens)
     assert np.all(np.isfinite(xttl))
     np.testing.assert_allclose(ttl.cpu().numpy(), xttl, rtol=1e-4 if dtype == np.float32 else 1e-9)
-    np.testing.assert_allclose(post.cpu().numpy(), xpost, **TOL[dtype])
+    # Float32: emissions of magnitude 100 (log2 units) are stored with ulp(100) = 7.6e-6 absolute resolution and
+    # that rounding enters every frame; over 120 frames the posteriors keep 3e-4 relative (the Float32 oracle,
+    # the reference's arithmetic, loses all significant digits on this input)
+    tol = dict(rtol=3e-4, atol=1e-6) if dtype == np.float32 else TOL[dtype]
+    np.testing.assert_allclose(post.cpu().numpy(), xpost, **tol)
     A = mm.αrecursion(b_, dev(torch, V), seqlengths=lens).cpu().numpy()
     og = orc_graphs(orc, [(f.astype(K64), pdf)] * B, D)
     for k in range(B):
