@@ -578,6 +578,11 @@ template <typename T> struct SharedParams {
     double* lz2;       // [U4] the same in kernel units, handed from the forward to the backward launch
     unsigned* barrier;
     int do_fwd, do_bwd, do_post;
+    // frame segment of this launch: the forward sweep runs frames [n_lo, n_hi) upwards, the backward sweep the same
+    // range downwards.  A sweep cut into several launches (host-buffer pipeline: copies overlap the kernels) carries
+    // its running per-utterance scalars through `carry_C` ([U4] float64) and `carry_shift` ([U4]).
+    int n_lo, n_hi;
+    double* carry_C; T* carry_shift;
     int ablate;        // debug builds (MK_ABLATE): 1 no gathers, 2 no finalise, 4 no chunk work, 8 no emission/α loads, 16 no stores
     int bwd_dead_ok;   // the library applied `expand`: co-unreachable rows have β = 0̄ before the last frame
 };
@@ -929,21 +934,24 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
     const ArcSrc<T, SA> bwd_src = make_arc_src<T, SA>(p.bwd, PHASE == 1 ? p.cache_b : 0, PHASE == 1 ? p.cache_items_b : 0,
                                                       cache, U4 >> 2, 1);
 
-    {   // this sweep's per-frame maxima
+    const bool first_segment = PHASE == 0 ? p.n_lo == 0 : p.n_hi == p.N1;
+    if (first_segment) {   // this sweep's per-frame maxima
         int* keys = p.gkey + size_t(PHASE) * p.N1 * U4;
         for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < size_t(p.N1) * U4;
              i += size_t(gridDim.x) * blockDim.x)
             keys[i] = kKeyMin;
     }
     for (int u = threadIdx.x; u < U4; u += blockDim.x) {
-        s_C[u] = 0.0; s_lz[u] = 0.0; s_shift[u] = T(0); s_g[u] = T(0); s_z[u] = T(0); s_key[u] = kKeyMin;
+        s_C[u] = first_segment ? 0.0 : p.carry_C[u];
+        s_shift[u] = (first_segment || PHASE == 1) ? T(0) : p.carry_shift[u];
+        s_lz[u] = 0.0; s_g[u] = T(0); s_z[u] = T(0); s_key[u] = kKeyMin;
     }
     grid_sync(p.barrier, bar_target);
 
     // ---------------------------------------------------------------- forward (αrecursion)
     if (PHASE == 0) {
         const int c0 = p.fwd.cta_chunks[blockIdx.x], c1 = p.fwd.cta_chunks[blockIdx.x + 1];
-        for (int n = 0; n < p.N1; ++n) {
+        for (int n = p.n_lo; n < p.n_hi; ++n) {
             if (n >= 1 && p.n_long) {
                 fwd_combine<T, SR>(p, n - 1, s_shift, s_key);
                 __syncthreads();
@@ -1005,6 +1013,11 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
             }
             grid_sync(p.barrier, bar_target);
         }
+        if (p.n_hi < p.N1) {  // the sweep continues in the next launch
+            if (blockIdx.x == 0)
+                for (int u = threadIdx.x; u < U4; u += blockDim.x) { p.carry_C[u] = s_C[u]; p.carry_shift[u] = s_shift[u]; }
+            return;
+        }
         if (p.n_long) {
             fwd_combine<T, SR>(p, p.N1 - 1, s_shift, s_key);
             __syncthreads();
@@ -1025,14 +1038,14 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
 
     // ---------------------------------------------------------------- backward (βrecursion + γ)
     for (int u = threadIdx.x; u < U4; u += blockDim.x) {
-        s_C[u] = 0.0; s_key[u] = kKeyMin; s_z[u] = T(0);
+        s_key[u] = kKeyMin; s_z[u] = T(0);
         s_lz[u] = p.do_post ? p.lz2[u] : 0.0;
     }
     __syncthreads();
     const int c0 = p.bwd.cta_chunks[blockIdx.x], c1 = p.bwd.cta_chunks[blockIdx.x + 1];
     int* gkey_b = p.gkey + size_t(p.N1) * U4;
     double* Cb = p.Coff + size_t(p.N1) * U4;
-    for (int n = p.N1 - 1; n >= 0; --n) {
+    for (int n = p.n_hi - 1; n >= p.n_lo; --n) {
         for (int u = threadIdx.x; u < U4; u += blockDim.x) {
             T sh = T(0);
             if (n < p.N1 - 1) {
@@ -1102,6 +1115,8 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
         }
         grid_sync(p.barrier, bar_target);
     }
+    if (p.n_lo > 0 && blockIdx.x == 0)  // the sweep continues in the next launch
+        for (int u = threadIdx.x; u < U4; u += blockDim.x) p.carry_C[u] = s_C[u];
 }
 
 // ================================================================================================
@@ -1117,6 +1132,7 @@ template <typename T> struct EmisParams {
     const int* utt_b;          // [U4]
     int U4;
     T* E;
+    int n0;                    // first frame of this launch (grid z counts from it)
     T scale;                   // log2(e) for the Log semiring (the kernels work in log2 units), 1 for Tropical
     int* emax_key;             // [N1][U4] ordered keys of the per-(frame, utterance) maxima of E, or null
 };
@@ -1132,7 +1148,7 @@ __device__ __forceinline__ T emission(const T* ll, long long sb, long long sd, l
 // grid: (ceil(Dh/32), ceil(U4/32), N1), block (32, 8)
 template <typename T> __global__ void expand_transpose_kernel(EmisParams<T> p) {
     __shared__ T tile[32][33];
-    const int n = blockIdx.z;
+    const int n = p.n0 + blockIdx.z;
     const int d0 = blockIdx.x * 32, u0 = blockIdx.y * 32;
     for (int k = threadIdx.y; k < 32; k += 8) {
         int u = u0 + k, d = d0 + threadIdx.x;
@@ -1199,6 +1215,11 @@ template <typename T> struct SmallParams {
     T* post; int B;
     T* zsum; T* lz;
     int do_fwd, do_bwd, do_post;
+    // frame segment of this launch: the forward sweep runs frames [n_lo, n_hi) upwards, the backward sweep the same
+    // range downwards.  A sweep cut into several launches (host-buffer pipeline: copies overlap the kernels) carries
+    // its running per-utterance scalars through `carry_C` ([U4] float64) and `carry_shift` ([U4]).
+    int n_lo, n_hi;
+    double* carry_C; T* carry_shift;
 };
 
 template <typename T, int SR>

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <map>
 #include <new>
@@ -515,7 +516,7 @@ struct Group {  // utterances sharing one graph, run by shared_fb_kernel
     bool vec4 = false;
     int* d_utt_b = nullptr;
     long long* d_utt_off = nullptr;
-    DevBuf E, emax, emax_key, alpha, bt, flin, blin, part, gkey, coff, lz2;
+    DevBuf E, emax, emax_key, alpha, bt, flin, blin, part, gkey, coff, lz2, carry;
 };
 
 struct mk_batch {
@@ -529,7 +530,9 @@ struct mk_batch {
     int small_smax = 0;
     int64_t small_cached_n1 = -1;
     DevBuf small_descs, small_alpha, small_ca, zsum, lz, seqlens, barrier, trace, h_ll, h_post, h_logz, h_path;
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+    static constexpr int kMaxSegments = 8;
+    cudaEvent_t ev_h2d[kMaxSegments] = {}, ev_done[kMaxSegments] = {};
     size_t max_smem_optin = 0;
     // optional timing of the dominant kernel (bench.py roofline): events around the last
     // shared_fb_kernel launch, on the stream it was launched on
@@ -541,12 +544,17 @@ struct mk_batch {
         for (auto& gr : groups) {
             cudaFree(gr.d_utt_b); cudaFree(gr.d_utt_off);
             gr.E.release(); gr.alpha.release(); gr.bt.release(); gr.flin.release(); gr.blin.release();
-            gr.part.release(); gr.gkey.release(); gr.coff.release(); gr.emax.release(); gr.emax_key.release(); gr.lz2.release();
+            gr.part.release(); gr.gkey.release(); gr.coff.release(); gr.emax.release(); gr.emax_key.release(); gr.lz2.release(); gr.carry.release();
         }
         DevBuf* all[] = {&small_descs, &small_alpha, &small_ca, &zsum, &lz, &seqlens, &barrier, &trace,
                          &h_ll, &h_post, &h_logz, &h_path};
         for (DevBuf* d : all) d->release();
         if (own_stream) cudaStreamDestroy(own_stream);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        for (int i = 0; i < kMaxSegments; ++i) {
+            if (ev_h2d[i]) cudaEventDestroy(ev_h2d[i]);
+            if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+        }
         for (int i = 0; i < kProfRing; ++i) {
             if (ev0[i]) cudaEventDestroy(ev0[i]);
             if (ev1[i]) cudaEventDestroy(ev1[i]);
@@ -568,16 +576,26 @@ static size_t small_smem_bytes(int S, int dtype) { return (2 * size_t(S) + 64) *
 // ------------------------------------------------------------------------------------------------
 enum Mode { MODE_ALPHA, MODE_BETA, MODE_POST, MODE_BEST };
 
+// A call cut into frame segments (mk_pdfposteriors_host): the emissions of segment k arrive while the
+// forward sweep works on segment k-1, the posteriors of segment k leave while the backward sweep works
+// on segment k-1.  `before_fwd(k)` runs before the emission transform of segment k is enqueued (waits for
+// the copy), `after_bwd(k)` after the posteriors of segment k have been normalised (starts the copy).
+struct Segments {
+    std::vector<int> f;  // frame boundaries: f[0] = 0 < f[1] < ... < f[K] = N̂
+    std::function<int(int)> before_fwd, after_bwd;
+};
+
 struct CallArgs {
     const void* ll; int64_t sb, sd, sn, D, T; int expanded; const int32_t* seqlens;
     void* out0;  // A / B / post / path
     void* out1;  // logz / score
     cudaStream_t stream;
+    const Segments* seg = nullptr;  // host pipeline (single shared-graph group only)
 };
 
 template <typename T, int SR>
 static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, int Dh, int N1,
-                         int Dout, int Tout, const int* d_seqlens) {
+                         int Dout, int Tout, const int* d_seqlens, const Segments* seg = nullptr) {
     mk_graph* g = gr.g;
     const int S = int(g->S), U4 = gr.U4;
     const int Sq = S + g->n_runs;  // rows of the forward vector: states + merged-run sources
@@ -596,28 +614,43 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     if (SR == SR_LOG) TRY(gr.emax_key.ensure(size_t(N1) * U4 * sizeof(int)));
     TRY(gr.lz2.ensure(size_t(U4) * sizeof(double)));
     TRY(gr.coff.ensure(2 * size_t(N1) * U4 * sizeof(double)));
+    TRY(gr.carry.ensure(size_t(U4) * (sizeof(double) + sizeof(T))));
+
+    // frame segments of this call (one, unless the host pipeline cut it)
+    std::vector<int> fb = seg ? seg->f : std::vector<int>{0, N1};
+    const int K = int(fb.size()) - 1;
 
     EmisParams<T> ep;
     ep.ll = static_cast<const T*>(c.ll); ep.sb = c.sb; ep.sd = c.sd; ep.sn = c.sn;
     ep.D = int(c.D); ep.Tn = int(c.T); ep.expanded = c.expanded; ep.Dh = Dh; ep.N1 = N1;
-    ep.seqlens = d_seqlens; ep.utt_b = gr.d_utt_b; ep.U4 = U4; ep.E = static_cast<T*>(gr.E.p);
+    ep.seqlens = d_seqlens; ep.utt_b = gr.d_utt_b; ep.U4 = U4;
     ep.scale = SR == SR_LOG ? T(1.4426950408889634) : T(1);
-    ep.emax_key = SR == SR_LOG ? static_cast<int*>(gr.emax_key.p) : nullptr;
-    // keys start below every finite value (0x80808080 decodes to -3.4e38)
-    if (SR == SR_LOG) CK(cudaMemsetAsync(gr.emax_key.p, 0x80, size_t(N1) * U4 * sizeof(int), c.stream));
-    dim3 eg((Dh + 31) / 32, (U4 + 31) / 32, N1), eb(32, 8);
-    expand_transpose_kernel<T><<<eg, eb, 0, c.stream>>>(ep);
-    CK(cudaGetLastError());
-    ++g_launches;
-    if (SR == SR_LOG) {
-        const int count = N1 * U4;
-        emission_max_decode_kernel<T><<<(count + 255) / 256, 256, 0, c.stream>>>(
-            static_cast<const int*>(gr.emax_key.p), static_cast<T*>(gr.emax.p), count);
+    // expand + transpose + per-frame emission maxima of the frames [n0, n1)
+    auto emissions = [&](int n0, int n1) -> int {
+        const int nf = n1 - n0;
+        EmisParams<T> e = ep;
+        e.n0 = n0;
+        e.E = static_cast<T*>(gr.E.p);  // (the kernel indexes both arrays by the absolute frame n0 + blockIdx.z)
+        e.emax_key = SR == SR_LOG ? static_cast<int*>(gr.emax_key.p) : nullptr;
+        int* keys = static_cast<int*>(gr.emax_key.p) + size_t(n0) * U4;
+        // keys start below every finite value (0x80808080 decodes to -3.4e38)
+        if (SR == SR_LOG) CK(cudaMemsetAsync(keys, 0x80, size_t(nf) * U4 * sizeof(int), c.stream));
+        dim3 eg((Dh + 31) / 32, (U4 + 31) / 32, nf), eb(32, 8);
+        expand_transpose_kernel<T><<<eg, eb, 0, c.stream>>>(e);
         CK(cudaGetLastError());
         ++g_launches;
-    } else {
-        CK(cudaMemsetAsync(gr.emax.p, 0, size_t(N1) * U4 * sizeof(T), c.stream));
-    }
+        T* emax = static_cast<T*>(gr.emax.p) + size_t(n0) * U4;
+        if (SR == SR_LOG) {
+            const int count = nf * U4;
+            emission_max_decode_kernel<T><<<(count + 255) / 256, 256, 0, c.stream>>>(keys, emax, count);
+            CK(cudaGetLastError());
+            ++g_launches;
+        } else {
+            CK(cudaMemsetAsync(emax, 0, size_t(nf) * U4 * sizeof(T), c.stream));
+        }
+        return MK_OK;
+    };
+    if (!seg) TRY(emissions(0, N1));
 
     SharedParams<T> p;
     p.S = S; p.Sq = Sq; p.Dh = Dh; p.N1 = N1; p.U4 = U4; p.ntiles = (U4 + kTileUtts - 1) / kTileUtts;
@@ -645,6 +678,9 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     p.utt_b = gr.d_utt_b; p.post_vec4 = 0;
     p.zsum = static_cast<T*>(bt->zsum.p); p.lz = static_cast<T*>(bt->lz.p);
     p.barrier = static_cast<unsigned*>(bt->barrier.p);
+    p.carry_C = static_cast<double*>(gr.carry.p);
+    p.carry_shift = reinterpret_cast<T*>(static_cast<double*>(gr.carry.p) + U4);
+    p.n_lo = 0; p.n_hi = N1;
     p.do_fwd = p.do_bwd = p.do_post = 0;
     p.bwd_dead_ok = c.expanded ? 0 : 1;
     p.ablate = getenv("MK_ABLATE") ? atoi(getenv("MK_ABLATE")) : 0;
@@ -667,7 +703,7 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     for (int phase = 0; phase < 2; ++phase) {
         if (phase == 0 ? !p.do_fwd : !p.do_bwd) continue;
         const DirDev& dd = phase == 0 ? g->fwd : g->bwd;
-        // shared-memory arc cache of this sweep when it fits next to the scalars, queues and rings
+        // shared-memory arc cache of this sweep when it fits next to the scalars
         size_t smem = scal;
         const size_t need = arc_cache_bytes(dd.cache_cap, dd.cache_items, dd.cache_chunks, sizeof(T));
         const bool sa = smem + need <= bt->max_smem_optin;
@@ -682,9 +718,31 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
                        : (sa ? shared_fb_kernel<T, SR, true, 1> : shared_fb_kernel<T, SR, false, 1>);
         if (smem > 48 * 1024)
             CK(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        CK(cudaMemsetAsync(bt->barrier.p, 0, sizeof(unsigned), c.stream));
-        CK(cudaLaunchCooperativeKernel((void*)kern, dim3(g->n_sms), dim3(kSharedThreads), args, smem, c.stream));
-        ++g_launches;
+        for (int kk = 0; kk < K; ++kk) {  // forward: segments upwards; backward: downwards
+            const int k = phase == 0 ? kk : K - 1 - kk;
+            p.n_lo = fb[k]; p.n_hi = fb[k + 1];
+            if (seg && phase == 0) {
+                if (seg->before_fwd) TRY(seg->before_fwd(k));
+                TRY(emissions(p.n_lo, p.n_hi));
+            }
+            CK(cudaMemsetAsync(bt->barrier.p, 0, sizeof(unsigned), c.stream));
+            CK(cudaLaunchCooperativeKernel((void*)kern, dim3(g->n_sms), dim3(kSharedThreads), args, smem, c.stream));
+            ++g_launches;
+            if (seg && phase == 1 && mode == MODE_POST) {
+                // Ẑ ./ sums for the real frames of this segment, then hand them to the caller
+                const int t0 = fb[k], t1 = std::min(fb[k + 1], Tout);
+                if (t1 > t0) {
+                    size_t total = size_t(t1 - t0) * Dout * bt->B;
+                    int blocks = int(std::min<size_t>((total + 255) / 256, size_t(bt->n_sms) * 16));
+                    normalize_post_kernel<T><<<blocks, 256, 0, c.stream>>>(
+                        static_cast<T*>(c.out0) + size_t(t0) * Dout * bt->B,
+                        static_cast<const T*>(bt->zsum.p) + size_t(t0) * bt->B, int(bt->B), Dout, t1 - t0);
+                    CK(cudaGetLastError());
+                    ++g_launches;
+                }
+                if (seg->after_bwd) TRY(seg->after_bwd(k));
+            }
+        }
     }
     if (bt->profile) { CK(cudaEventRecord(bt->ev1[slot], c.stream)); ++bt->prof_n; }
 
@@ -788,15 +846,18 @@ template <typename T, int SR> static int run(mk_batch* bt, Mode mode, const Call
         CK(cudaMemsetAsync(c.out0, 0, size_t(Tout) * Dout * B * sizeof(T), c.stream));
         CK(cudaMemsetAsync(bt->zsum.p, 0, size_t(N1) * B * sizeof(T), c.stream));
     }
-    for (auto& gr : bt->groups) TRY((launch_shared<T, SR>(bt, gr, mode, c, Dh, N1, Dout, Tout, d_seqlens)));
+    const Segments* seg = (c.seg && bt->groups.size() == 1 && bt->small.empty()) ? c.seg : nullptr;
+    for (auto& gr : bt->groups) TRY((launch_shared<T, SR>(bt, gr, mode, c, Dh, N1, Dout, Tout, d_seqlens, seg)));
     TRY((launch_small<T, SR>(bt, mode, c, Dh, N1, Dout, Tout, d_seqlens)));
 
     if (mode == MODE_POST) {
         size_t total = size_t(Tout) * Dout * B;
         int blocks = int(std::min<size_t>((total + 255) / 256, size_t(bt->n_sms) * 16));
-        normalize_post_kernel<T><<<blocks, 256, 0, c.stream>>>(static_cast<T*>(c.out0),
-                                                             static_cast<const T*>(bt->zsum.p), B, Dout, Tout);
-        CK(cudaGetLastError());
+        if (!seg) {  // (a segmented call normalises segment by segment, inside launch_shared)
+            normalize_post_kernel<T><<<blocks, 256, 0, c.stream>>>(static_cast<T*>(c.out0),
+                                                                 static_cast<const T*>(bt->zsum.p), B, Dout, Tout);
+            CK(cudaGetLastError());
+        }
         total_kernel<T><<<(B + 127) / 128, 128, 0, c.stream>>>(static_cast<const T*>(bt->zsum.p),
                                                              static_cast<const T*>(bt->lz.p),
                                                              static_cast<T*>(c.out1), B, N1);
@@ -1133,6 +1194,57 @@ int mk_pdfposteriors_host(mk_batch* b, const void* ll, int64_t sb, int64_t sd, i
     TRY(b->h_post.ensure(post_bytes));
     TRY(b->h_logz.ensure(b->B * ts));
     cudaStream_t st = b->own_stream;
+    // Pipeline: when the whole batch is one shared-graph group and the emissions are [b][t][d] rows, the call is
+    // cut into frame segments; the copy stream brings slice k+1 in while the forward sweep runs slice k, and
+    // takes the posteriors of segment k out while the backward sweep runs segment k-1.  MK_NO_PIPELINE=1 disables.
+    const int K = int(std::min<int64_t>(mk_batch::kMaxSegments, T / 16));
+    const bool pipe = b->groups.size() == 1 && b->small.empty() && !expanded && sd == 1 && sn == D && sb == T * D &&
+                      K >= 2 && !(getenv("MK_NO_PIPELINE") && atoi(getenv("MK_NO_PIPELINE")));
+    if (pipe) {
+        if (!b->copy_stream) CK(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < K; ++k) {
+            if (!b->ev_h2d[k]) CK(cudaEventCreateWithFlags(&b->ev_h2d[k], cudaEventDisableTiming));
+            if (!b->ev_done[k]) CK(cudaEventCreateWithFlags(&b->ev_done[k], cudaEventDisableTiming));
+        }
+        cudaStream_t sc = b->copy_stream;
+        Segments seg;
+        for (int k = 0; k < K; ++k) seg.f.push_back(int(T * k / K));
+        seg.f.push_back(int(T) + 1);  // the last segment also holds the phony frame
+        const size_t row = size_t(D) * ts, pitch = size_t(T) * row;
+        for (int k = 0; k < K; ++k) {
+            const int t0 = seg.f[k], t1 = std::min<int>(seg.f[k + 1], int(T));
+            CK(cudaMemcpy2DAsync(static_cast<char*>(b->h_ll.p) + size_t(t0) * row, pitch,
+                                 static_cast<const char*>(ll) + size_t(t0) * row, pitch, size_t(t1 - t0) * row,
+                                 size_t(b->B), cudaMemcpyHostToDevice, sc));
+            CK(cudaEventRecord(b->ev_h2d[k], sc));
+        }
+        seg.before_fwd = [&](int k) -> int {
+            CK(cudaStreamWaitEvent(st, b->ev_h2d[k], 0));
+            return MK_OK;
+        };
+        const size_t frame_bytes = size_t(b->B) * Dout * ts;
+        seg.after_bwd = [&](int k) -> int {
+            const int t0 = seg.f[k], t1 = std::min<int>(seg.f[k + 1], int(T));
+            CK(cudaEventRecord(b->ev_done[k], st));
+            CK(cudaStreamWaitEvent(sc, b->ev_done[k], 0));
+            CK(cudaMemcpyAsync(static_cast<char*>(out_post) + size_t(t0) * frame_bytes,
+                               static_cast<char*>(b->h_post.p) + size_t(t0) * frame_bytes, size_t(t1 - t0) * frame_bytes,
+                               cudaMemcpyDeviceToHost, sc));
+            return MK_OK;
+        };
+        CallArgs c = mkargs(b->h_ll.p, sb, sd, sn, D, T, expanded, seqlens, b->h_post.p, b->h_logz.p, st);
+        c.seg = &seg;
+        int rc = dispatch(b, MODE_POST, c);
+        if (rc == MK_OK) {
+            cudaError_t e = cudaMemcpyAsync(out_logz, b->h_logz.p, b->B * ts, cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) rc = fail(MK_ECUDA, "cudaMemcpyAsync(logz) failed: %s", cudaGetErrorString(e));
+        }
+        cudaStreamSynchronize(st);  // (also on failure: nothing may be in flight when the lambdas go out of scope)
+        cudaStreamSynchronize(sc);
+        if (rc != MK_OK) return rc;
+        CK(cudaGetLastError());
+        return MK_OK;
+    }
     CK(cudaMemcpyAsync(b->h_ll.p, ll, in_bytes, cudaMemcpyHostToDevice, st));
     TRY(dispatch(b, MODE_POST, mkargs(b->h_ll.p, sb, sd, sn, D, T, expanded, seqlens, b->h_post.p, b->h_logz.p, st)));
     CK(cudaMemcpyAsync(out_post, b->h_post.p, post_bytes, cudaMemcpyDeviceToHost, st));

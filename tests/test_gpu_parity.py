@@ -262,6 +262,27 @@ def test_linear_copies_underflow_falls_back_exactly(torch, mm, orc, dtype):
             np.testing.assert_allclose(got[fin], oA[fin], rtol=1e-4, atol=5e-3)
 
 
+def test_more_than_one_utterance_tile(torch, mm, orc):
+    """A warp covers 128 utterances (32 lanes x 4); larger groups are worked tile by tile.  130 utterances:
+    one full tile and one with two live lanes... of which half a lane is padding."""
+    K = mm.LogSemiring[np.float32]
+    rng = np.random.default_rng(130)
+    B, T, D = 130, 16, 60
+    g = mm.graphs.denominator(K, n_tokens=400, n_pdf=D, seed=13)
+    V = (rng.standard_normal((B, T, D)) * 2).astype(np.float32)
+    lens = rng.integers(T // 2, T + 1, B).astype(np.int32)
+    b = gpu_batch(mm, [g] * B, D, "shared")
+    post, ttl = mm.pdfposteriors(b, dev(torch, V), seqlengths=lens)
+    check_posteriors(mm, orc, [g] * B, D, V, lens, post, ttl, np.float32)
+    Kt = mm.TropicalSemiring[np.float32]
+    gt = (g[0].astype(Kt), g[1])
+    bt = gpu_batch(mm, [gt] * B, D, "shared")
+    path, score = mm.bestpath(bt, dev(torch, V), seqlengths=lens)
+    opath, oscore = orc.bestpath(orc_graphs(orc, [gt] * B, D), V, lens)
+    np.testing.assert_array_equal(path.cpu().numpy(), opath)
+    np.testing.assert_array_equal(score.cpu().numpy(), oscore)
+
+
 def test_row_merging_is_transparent(torch, mm, orc):
     """The graph compiler merges runs of adjacent states with identical out-arc lists (the A/B pairs of
     the chain topology).  With and without merging (MK_NO_MERGE=1) the results agree with each other
@@ -436,6 +457,36 @@ def test_host_buffer_entry_point(torch, mm, orc):
     opath, oscore = orc.bestpath(orc_graphs(orc, [gt] * B, D), V)
     np.testing.assert_array_equal(path, opath)
     np.testing.assert_array_equal(score, oscore)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_host_pipeline_matches_single_launch(torch, mm, orc, dtype):
+    """mk_pdfposteriors_host cuts long calls into frame segments (copies overlap the sweeps, the running
+    per-utterance scalars are carried from launch to launch); MK_NO_PIPELINE=1 runs the same call in one piece.
+    Ragged lengths, a segment boundary inside the padding of some utterances."""
+    K = mm.LogSemiring[dtype]
+    rng = np.random.default_rng(66)
+    B, T, D = 8, 70, 120
+    g = mm.graphs.denominator(K, n_tokens=700, n_pdf=D, seed=6)
+    V = (rng.standard_normal((B, T, D)) * 2).astype(dtype)
+    lens = rng.integers(20, T + 1, B).astype(np.int32)
+    lens[0] = T
+    b = gpu_batch(mm, [g] * B, D, "shared")
+    out = {}
+    for flag in ("0", "1"):
+        os.environ["MK_NO_PIPELINE"] = flag
+        try:
+            post, ttl = mm.pdfposteriors(b, V.transpose(0, 2, 1), seqlengths=lens)
+            out[flag] = (np.array(post), np.array(ttl))
+        finally:
+            os.environ.pop("MK_NO_PIPELINE", None)
+    rt = 1e-5 if dtype == np.float32 else 1e-12
+    np.testing.assert_allclose(out["0"][1], out["1"][1], rtol=rt)
+    np.testing.assert_allclose(out["0"][0], out["1"][0], rtol=rt, atol=1e-9)
+    check_posteriors(mm, orc, [g] * B, D, V, lens, out["0"][0], out["0"][1], dtype)
+    dpost, dttl = mm.pdfposteriors(b, dev(torch, V), seqlengths=lens)  # device path, one launch pair
+    np.testing.assert_allclose(out["0"][1], dttl.cpu().numpy(), rtol=rt)
+    np.testing.assert_allclose(out["0"][0], dpost.cpu().numpy(), rtol=rt, atol=1e-9)
 
 
 def test_dimension_mismatch(torch, mm):
