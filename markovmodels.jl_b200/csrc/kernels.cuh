@@ -291,6 +291,40 @@ __device__ __forceinline__ V4<T> row_reduce(const Arc<T>* __restrict__ arcs, int
     return out;
 }
 
+// The same ⊕ for forward rows of the Log semiring whose in-arcs may name a merged run (index Ŝ + g): the run's
+// members are its consecutive rows, each reached with the arc's weight — exactly the un-merged graph.  The
+// α store keeps no log2 row for the virtual sources q_g (only their linear copies exist), so the rare exact
+// path expands them.  Plain two-pass loops: this code runs for a handful of rows per call.
+template <typename T>
+__device__ __noinline__ void row_reduce_runs(const Arc<T>* __restrict__ arcs, int beg, int end, const T* vec, int U4, int uoff,
+                                             const int2* __restrict__ runs, int S, T* out4) {
+    T m[4], s[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { m[j] = neg_inf<T>(); s[j] = T(0); }
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int a = beg; a < end; ++a) {
+            const Arc<T> arc = ld_arc(arcs + a);
+            int r0 = arc.idx, r1 = arc.idx + 1;
+            if (arc.idx >= S) {
+                const int2 run = __ldg(runs + (arc.idx - S));
+                r0 = run.x;
+                r1 = run.x + run.y;
+            }
+            for (int r = r0; r < r1; ++r) {
+                const V4<T> v = ld4_cg(vec + size_t(r) * U4 + uoff);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const T x = v.v[j] + arc.w;
+                    if (pass == 0) m[j] = max_(m[j], x);
+                    else if (m[j] != neg_inf<T>()) s[j] += ex2_(x - m[j]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out4[j] = (s[j] > T(0)) ? m[j] + lg2_(s[j]) : neg_inf<T>();
+}
+
 // ---- ordered integer keys: float max through integer atomicMax (works for negatives, -Inf) ----
 constexpr int kKeyMin = int(0x80000000);
 __device__ __forceinline__ int fkey(float x) {
@@ -324,6 +358,8 @@ template <typename T> struct DirPlan {
     const Arc<T>* arcs;          // un-padded arcs (w - R, kernel units) for the exact fallback
     T R;                         // bound on the ⊕ exponents (0 for Tropical)
     T H;                         // Log: the linear copy of a stored value v is 2^(v + H) (<= 2^headroom)
+    const int2* runs;            // forward plans: merged runs {first row, number of rows}; arc index Ŝ + g = run g
+    int n_states;                // Ŝ
 };
 
 // Single-pass ⊕ of an item's arcs, resolved to log2 Σ 2^(v + w) for 4 utterances.  acc is the
@@ -347,7 +383,15 @@ __device__ __noinline__ void redo_row(const DirPlan<T>* pl, int item, const T* v
     if (!need) return;
     const int2 ar = __ldg(pl->item_arcs + item);
     if (ar.y <= ar.x) return;
-    V4<T> r = row_reduce<T, SR>(pl->arcs, ar.x, ar.y, vec, U4, uoff);
+    V4<T> r;
+    if (SR == SR_LOG && pl->runs) {
+        T o4[4];
+        row_reduce_runs<T>(pl->arcs, ar.x, ar.y, vec, U4, uoff, pl->runs, pl->n_states, o4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r.v[j] = o4[j];
+    } else {
+        r = row_reduce<T, SR>(pl->arcs, ar.x, ar.y, vec, U4, uoff);
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
         if (acc4[j] < tiny) val4[j] = r.v[j] + pl->R;
@@ -562,7 +606,7 @@ template <typename T> struct SharedParams {
     const T* init_dense;                          // α̂ as a dense vector [S] (kernel units)
     const T* E;      // expanded, transposed emissions (kernel units, NOT normalised): [N1][Dh][U4]
     const T* emax;   // [N1][U4] per-frame emission maxima (kernel units), subtracted together with the shift
-    T* alpha;        // [N1][Sq][U4]  normalised a_n, then the merged-run sources q_g
+    T* alpha;        // Log: [N1][Ŝ][U4] normalised a_n; Tropical: [N1][Sq][U4], the merged-run sources q_g after the states
     T* bt;           // [2][S][U4]    b_{n+1} ⊗ e'_{n+1} ping-pong
     T* flin;         // [2][Sq][U4]   Log: linear copies 2^(a_n + H_f) of the forward vector (ping-pong), the gather source
     T* blin;         // [2][S][U4]    Log: linear copies 2^(b_{n+1} ⊗ e'_{n+1} + H_b), the gather source
@@ -612,7 +656,8 @@ template <typename T, int SR>
 __device__ __forceinline__ void fwd_combine(const SharedParams<T>& p, int m, const T* s_shift, int* s_key) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int U4 = p.U4;
-    const size_t frame = size_t(p.Sq) * U4;
+    const size_t frame = size_t(p.Sq) * U4;                          // linear copies: Ŝ + runs rows
+    const size_t frame_a = size_t(SR == SR_LOG ? p.S : p.Sq) * U4;  // α store
     const T* Em = p.E + size_t(m) * p.Dh * U4;
     const T* part = p.part + size_t(m & 1) * p.n_slots * U4;
     for (int k = warp; k < p.n_long; k += kSharedWarps) {
@@ -639,34 +684,10 @@ __device__ __forceinline__ void fwd_combine(const SharedParams<T>& p, int m, con
                 val.v[j] = val.v[j] + (e.v[j] - __ldg(p.emax + size_t(m) * U4 + uoff + j)) - s_shift[uoff + j];
                 atomicMax(&s_key[uoff + j], fkey(float(val.v[j])));
             }
-            st4_cg(p.alpha + size_t(m) * frame + size_t(r) * U4 + uoff, val);
+            st4_cg(p.alpha + size_t(m) * frame_a + size_t(r) * U4 + uoff, val);
             if (SR == SR_LOG) st_lin(p.flin + size_t(m & 1) * frame + size_t(r) * U4 + uoff, val, p.fwd.H);
         }
     }
-}
-
-// exact ⊕ of the members of a merged run (rows first, first + step, .. last of `cur_lane`), for the lanes whose
-// linear sum underflowed
-template <typename T>
-__device__ __noinline__ void run_logsum_slow(const T* cur_lane, unsigned first, unsigned last, unsigned step, const T* qlin4,
-                                             T* ql4) {
-    const T tiny = tiny_sum<T>();
-    T m[4], sum[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { m[j] = neg_inf<T>(); sum[j] = T(0); }
-    for (unsigned r = first; r <= last; r += step) {
-        const V4<T> v = ld4_cg(cur_lane + size_t(r) * 4);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) m[j] = max_(m[j], v.v[j]);
-    }
-    for (unsigned r = first; r <= last; r += step) {
-        const V4<T> v = ld4_cg(cur_lane + size_t(r) * 4);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) sum[j] += (m[j] == neg_inf<T>()) ? T(0) : ex2_(v.v[j] - m[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if (qlin4[j] < tiny) ql4[j] = (sum[j] > T(0)) ? m[j] + lg2_(sum[j]) : neg_inf<T>();
 }
 
 // Finalisers.  Item records arrive with pre-multiplied offsets (ArcSrc::item): it.x = row * U4/4,
@@ -686,7 +707,6 @@ template <typename T, int SR> struct FwdFin {
     int4 it;            // the item being streamed and its emissions, requested when the item starts
     V4<T> e;
     V4<T> qacc;         // merged run: Σ of the members' linear copies (Log) / their maximum (Tropical)
-    unsigned qfirst;    // row offset of the run's first member
     __device__ __forceinline__ FwdFin(const SharedParams<T>& p_, const T* prev_, T* cur, T* lin, T* part, const T* En,
                                       int uoff_, const T* s_shift, const T* emax_n)
         : p(p_), prev(prev_), cur_l(cur + uoff_), lin_l(lin + uoff_), part_l(part + uoff_), En_l(En + uoff_), uoff(uoff_) {
@@ -695,7 +715,6 @@ template <typename T, int SR> struct FwdFin {
             c[j] = -s_shift[uoff_ + j]; cm[j] = -__ldg(emax_n + uoff_ + j);
             mx[j] = neg_inf<T>(); qacc.v[j] = T(0);
         }
-        qfirst = 0;
     }
     template <class Src> __device__ __forceinline__ void prefetch(const Src& src, int item) {
         it = src.item(item);
@@ -713,26 +732,13 @@ template <typename T, int SR> struct FwdFin {
             if (it.w & 2) qacc.v[j] = lin.v[j];
             else qacc.v[j] = SR == SR_LOG ? qacc.v[j] + lin.v[j] : max_(qacc.v[j], lin.v[j]);
         }
-        if (it.w & 2) qfirst = unsigned(it.x);
         if (it.w & 4) {
             const unsigned qoff = unsigned(p.S + (it.w >> 8)) * unsigned(p.U4 >> 2);
             if (SR == SR_TROP) {
                 st4_cg(cur_l + size_t(qoff) * 4, qacc);
                 return;
             }
-            st4_cg(lin_l + size_t(qoff) * 4, qacc);
-            V4<T> ql;  // the log2 copy, for the exact fallback of the successors' rows
-#pragma unroll
-            for (int j = 0; j < 4; ++j) ql.v[j] = lg2_(qacc.v[j]) - p.fwd.H;
-            if (min4(qacc) < tiny_sum<T>()) {  // rare
-                T q4[4], l4[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { q4[j] = qacc.v[j]; l4[j] = ql.v[j]; }
-                run_logsum_slow<T>(cur_l, qfirst, unsigned(it.x), unsigned(p.U4 >> 2), q4, l4);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) ql.v[j] = l4[j];
-            }
-            st4_cg(cur_l + size_t(qoff) * 4, ql);
+            st4_cg(lin_l + size_t(qoff) * 4, qacc);  // (no log2 row for q_g: the exact fallback expands runs)
         }
     }
     // val: the row's normalised a_n (log2 / tropical)
@@ -923,7 +929,8 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
     int* s_next = s_key + U4;                             // [ntiles] dynamic chunk counters, one per utterance tile
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t frame = size_t(S) * U4;      // β-side vectors: Ŝ rows
-    const size_t frame_q = size_t(p.Sq) * U4;  // α store: Ŝ + merged-run rows
+    const size_t frame_q = size_t(p.Sq) * U4;  // forward vectors with the merged-run rows: Ŝ + runs
+    const size_t frame_a = SR == SR_LOG ? frame : frame_q;  // α store (Tropical gathers from it: q_g rows included)
     unsigned bar_target = 0;
 
     // This CTA's arcs stay in shared memory for the whole launch: the per-frame fence of the grid
@@ -971,7 +978,7 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
             for (int tile = 0; tile < p.ntiles; ++tile) {
                 const bool live = tile * kTileUtts + lane * 4 < U4;  // (lanes beyond the batch stay converged for the pulls)
                 const int uoff = live ? tile * kTileUtts + lane * 4 : 0;
-                FwdFin<T, SR> fin(p, p.alpha + size_t(n > 0 ? n - 1 : 0) * frame_q, p.alpha + size_t(n) * frame_q,
+                FwdFin<T, SR> fin(p, p.alpha + size_t(n > 0 ? n - 1 : 0) * frame_a, p.alpha + size_t(n) * frame_a,
                                   p.flin + size_t(n & 1) * frame_q, p.part + size_t(n & 1) * p.n_slots * U4,
                                   p.E + size_t(n) * p.Dh * U4, uoff, s_shift, p.emax + size_t(n) * U4);
                 // gather source: the previous frame's linear copies (Log) / the vector itself (Tropical)
@@ -1023,7 +1030,7 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
             __syncthreads();
         }
         // log Z = α_{N̂}[phony final] = a + Ca   (kernel units inside, natural log out)
-        const T* last = p.alpha + size_t(p.N1 - 1) * frame_q + size_t(S - 1) * U4;
+        const T* last = p.alpha + size_t(p.N1 - 1) * frame_a + size_t(S - 1) * U4;
         for (int u = threadIdx.x; u < U4; u += blockDim.x) {
             T a = __ldcg(last + u);
             double z = (a == neg_inf<T>()) ? double(a) : double(a) + s_C[u];
@@ -1066,7 +1073,7 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
             const int uoff = live ? tile * kTileUtts + lane * 4 : 0;
             BwdFin<T, SR> fin(p, p.bt + size_t((n + 1) & 1) * frame, p.bt + size_t(n & 1) * frame,
                               p.blin + size_t(n & 1) * frame, p.E + size_t(n) * p.Dh * U4,
-                              p.alpha + size_t(n) * frame_q, n, uoff, s_shift, s_g);
+                              p.alpha + size_t(n) * frame_a, n, uoff, s_shift, s_g);
             const T* gsrc = (SR == SR_LOG ? p.blin + size_t((n + 1) & 1) * frame : fin.bt_next) + uoff;
             for (;;) {
                 int wk = 0;

@@ -127,12 +127,13 @@ struct mk_graph {
     void *d_fwd_long_arcs = nullptr, *d_init_dense_s = nullptr;
     int n_long = 0, n_slots = 0;
     int n_runs = 0;  // merged runs: the forward vector has Ŝ + n_runs rows
+    int2* d_runs = nullptr;  // {first row, number of rows} of every run (exact fallback of the forward sweep)
     size_t bytes = 0;
     ~mk_graph() {
         cudaFree(d_in_ptr); cudaFree(d_out_ptr); cudaFree(d_pdf);
         cudaFree(d_in_arcs); cudaFree(d_out_arcs); cudaFree(d_init_dense);
         fwd.release(); bwd.release();
-        cudaFree(d_fwd_long); cudaFree(d_fwd_long_arcs); cudaFree(d_init_dense_s);
+        cudaFree(d_fwd_long); cudaFree(d_fwd_long_arcs); cudaFree(d_init_dense_s); cudaFree(d_runs);
     }
 };
 
@@ -390,6 +391,12 @@ static int build_graph(mk_graph* g, const int64_t* colptr, const int64_t* rowval
         }
     }
     g->n_runs = n_runs;
+    std::vector<int2> runs(n_runs);
+    for (int k = 0; k < S; ++k)
+        if (grp[k] >= 0) {
+            if (!tied[k]) runs[grp[k]] = make_int2(k, 1);
+            else runs[grp[k]].y += 1;
+        }
     // forward in-arcs with the runs' members replaced by their virtual source
     std::vector<int> in_ptr_m(S + 1, 0);
     std::vector<Arc<T>> in_arcs_m;
@@ -499,6 +506,7 @@ static int build_graph(mk_graph* g, const int64_t* colptr, const int64_t* rowval
     TRY(upload(init_s, &g->d_init_dense_s));
     TRY(upload_plan<T>(fwd, in_s, g->fwd));
     TRY(upload_plan<T>(bwd, out_s, g->bwd));
+    TRY(upload(runs, (void**)&g->d_runs));
     TRY(upload(fwd_long, (void**)&g->d_fwd_long));
     TRY(upload(fwd_long_arcs, &g->d_fwd_long_arcs));
     g->bytes = 2 * (S + 1) * sizeof(int) + 4 * nnz * sizeof(Arc<T>) + S * (sizeof(int) + 2 * sizeof(T)) +
@@ -602,7 +610,9 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     const size_t frame = size_t(S) * U4 * sizeof(T), frame_q = size_t(Sq) * U4 * sizeof(T);
     if (size_t(Sq) * U4 >= (size_t(1) << 31)) return fail(MK_ENOTSUP, "Ŝ*U exceeds 2^31 in one group");
     TRY(gr.E.ensure(size_t(N1) * Dh * U4 * sizeof(T)));
-    TRY(gr.alpha.ensure(size_t(N1) * frame_q));
+    // α store: Log keeps the states only (the q_g exist as linear copies); Tropical gathers from the store itself
+    const size_t frame_a = SR == SR_LOG ? frame : frame_q;
+    TRY(gr.alpha.ensure(size_t(N1) * frame_a));
     if (mode == MODE_POST || mode == MODE_BETA) TRY(gr.bt.ensure(2 * frame));
     if (SR == SR_LOG) {  // linear copies of the two frames in flight: the gather sources
         if (mode != MODE_BETA) TRY(gr.flin.ensure(2 * frame_q));
@@ -659,9 +669,11 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
         q.items = d.items; q.item_arcs = d.item_arcs; q.chunks = d.chunks; q.cta_chunks = d.cta_chunks;
         q.pidx = d.pidx; q.pw = static_cast<const T*>(d.pw); q.item_pa = d.item_pa;
         q.arcs = static_cast<const Arc<T>*>(d.arcs); q.R = T(d.R); q.H = T(d.H);
+        q.runs = nullptr; q.n_states = 0;
         return q;
     };
     p.fwd = plan(g->fwd); p.bwd = plan(g->bwd);
+    p.fwd.runs = g->n_runs ? g->d_runs : nullptr; p.fwd.n_states = S;
     p.n_long = g->n_long; p.fwd_long = g->d_fwd_long;
     p.fwd_long_arcs = static_cast<const Arc<T>*>(g->d_fwd_long_arcs);
     p.n_slots = g->n_slots; p.part = static_cast<T*>(gr.part.p);
@@ -750,7 +762,7 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
         dim3 ug((S + 31) / 32, (U4 + 31) / 32, N1), ub(32, 8);
         const double* C = static_cast<const double*>(gr.coff.p) + (mode == MODE_BETA ? size_t(N1) * U4 : 0);
         unpack_states_kernel<T><<<ug, ub, 0, c.stream>>>(static_cast<const T*>(gr.alpha.p), S,
-                                                        mode == MODE_BETA ? S : Sq, U4, gr.d_utt_b,
+                                                        (mode == MODE_BETA || SR == SR_LOG) ? S : Sq, U4, gr.d_utt_b,
                                                         gr.d_utt_off, C, SR == SR_LOG ? 0.6931471805599453 : 1.0,
                                                         static_cast<T*>(c.out0), bt->total);
         CK(cudaGetLastError());

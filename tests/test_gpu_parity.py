@@ -262,6 +262,39 @@ def test_linear_copies_underflow_falls_back_exactly(torch, mm, orc, dtype):
             np.testing.assert_allclose(got[fin], oA[fin], rtol=1e-4, atol=5e-3)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_underflow_fallback_expands_merged_runs(torch, mm, orc, dtype):
+    """The forward α store keeps no log2 row for the merged-run sources q_g; the exact fallback reaches a run's
+    members through the run table.  Chain-topology denominator (every token is a run of two rows) with one pdf
+    per frame 60 nats above the rest: most rows underflow in the linear domain in most frames."""
+    K = mm.LogSemiring[dtype]
+    rng = np.random.default_rng(91)
+    B, T, D = 8, 50, 40
+    g = mm.graphs.denominator(K, n_tokens=150, n_pdf=D, seed=17)
+    V = (rng.standard_normal((B, T, D)) * 2).astype(dtype)
+    for b in range(B):
+        V[b, np.arange(T), rng.integers(0, D, T)] += 60.0
+    lens = rng.integers(T - 10, T + 1, B).astype(np.int32)
+    b_ = gpu_batch(mm, [g] * B, D, "shared")
+    post, ttl = mm.pdfposteriors(b_, dev(torch, V), seqlengths=lens)
+    K64 = mm.LogSemiring[np.float64]
+    g64 = (g[0].astype(K64), g[1])
+    xpost, xttl = orc.pdfposteriors(orc_graphs(orc, [g64] * B, D), V.astype(np.float64), lens)
+    assert np.all(np.isfinite(xttl))
+    np.testing.assert_allclose(ttl.cpu().numpy(), xttl, rtol=1e-4 if dtype == np.float32 else 1e-9)
+    tol = dict(rtol=3e-4, atol=1e-6) if dtype == np.float32 else TOL[dtype]
+    np.testing.assert_allclose(post.cpu().numpy(), xpost, **tol)
+    A = mm.αrecursion(b_, dev(torch, V), seqlengths=lens).cpu().numpy()
+    og = orc_graphs(orc, [g64] * B, D)
+    for k in range(B):
+        oA, _ = orc.alpha_beta(og[k], V[k].astype(np.float64), lens[k], want_beta=False)
+        got = A[b_.offsets[k]:b_.offsets[k + 1]]
+        np.testing.assert_array_equal(np.isneginf(got), np.isneginf(oA))
+        fin = ~np.isneginf(oA)
+        np.testing.assert_allclose(got[fin], oA[fin], rtol=1e-4 if dtype == np.float32 else 1e-9,
+                                   atol=5e-3 if dtype == np.float32 else 1e-9)
+
+
 def test_more_than_one_utterance_tile(torch, mm, orc):
     """A warp covers 128 utterances (32 lanes x 4); larger groups are worked tile by tile.  130 utterances:
     one full tile and one with two live lanes... of which half a lane is padding."""
