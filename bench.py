@@ -35,8 +35,8 @@ B_PER_GPU, T_FRAMES, N_PDF, N_TOKENS, SEED = 128, 150, 3000, 15000, 303
 HBM_FALLBACK_GBS = 6650.0
 # dram__bytes_read.sum + dram__bytes_write.sum of the two shared_fb_kernel launches of ONE pdfposteriors call on
 # this workload, from the `ncu --set full` capture summarised in profiles/r01_shared_fb_kernel_ncu.md
-# (forward 0.218 + 3.470 GB, backward 2.763 + 2.542 GB); null for any other shape
-NCU_DRAM_BYTES_PER_LAUNCH = 8.993e9
+# (forward 0.219 + 2.290 GB, backward 2.760 + 2.480 GB); null for any other shape
+NCU_DRAM_BYTES_PER_LAUNCH = 7.749e9
 
 
 def workload_config(n_gpus, b_per_gpu, frames):
@@ -48,33 +48,47 @@ def workload_config(n_gpus, b_per_gpu, frames):
 
 
 class ClockSampler(threading.Thread):
-    """NVML sampler: SM clock + throttle reasons while the timed region runs."""
+    """NVML: SM clock + throttle reasons every few milliseconds while the timed region runs.  NVML is
+    initialised (and queried once: the first query is slow) by the constructor, before the timed region; the
+    thread only polls."""
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.mask, self.stop_flag, self.max_mhz, self.err = index, [], 0, False, None, None
-
-    def run(self):
+        self.samples, self.mask, self.max_mhz, self.err, self.h, self.stop_flag = [], 0, None, None, None, False
         try:
             import pynvml
+            self.nv = pynvml
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-            while not self.stop_flag:
-                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
-                try:
-                    self.mask |= pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    self.mask |= pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                time.sleep(0.005)
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self._query()  # warm the query path
+            self.samples, self.mask = [], 0
         except Exception as e:  # no NVML: report it rather than invent numbers
+            self.err = repr(e)
+
+    def _query(self):
+        self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+        try:
+            self.mask |= self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            self.mask |= self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+
+    def run(self):
+        if self.h is None:
+            return
+        try:
+            while not self.stop_flag:
+                self._query()
+                time.sleep(0.003)
+        except Exception as e:
             self.err = repr(e)
 
     def result(self):
         self.stop_flag = True
-        self.join(timeout=2)
+        if self.is_alive():
+            self.join(timeout=2)
         if self.err or not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "error": self.err or "no samples"}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
@@ -183,14 +197,14 @@ def run_ours(args):
     sync_all()
     bfsm.profile(True)
     sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
     lib.mk_launch_count(1)
+    if sampler:
+        sampler.start()  # (NVML is already initialised: the first sample lands within microseconds)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step()
-    e1.record()
+    e1.record()  # the steps were enqueued asynchronously: the GPU is inside the timed region now
     sync_all()
     launches = int(lib.mk_launch_count(0))
     clocks = sampler.result() if sampler else None
