@@ -539,7 +539,7 @@ struct mk_batch {
     int64_t small_cached_n1 = -1;
     DevBuf small_descs, small_alpha, small_ca, zsum, lz, seqlens, barrier, trace, h_ll, h_post, h_logz, h_path;
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
-    static constexpr int kMaxSegments = 8;
+    static constexpr int kMaxSegments = 16;
     cudaEvent_t ev_h2d[kMaxSegments] = {}, ev_done[kMaxSegments] = {};
     size_t max_smem_optin = 0;
     // optional timing of the dominant kernel (bench.py roofline): events around the last
@@ -1209,7 +1209,8 @@ int mk_pdfposteriors_host(mk_batch* b, const void* ll, int64_t sb, int64_t sd, i
     // Pipeline: when the whole batch is one shared-graph group and the emissions are [b][t][d] rows, the call is
     // cut into frame segments; the copy stream brings slice k+1 in while the forward sweep runs slice k, and
     // takes the posteriors of segment k out while the backward sweep runs segment k-1.  MK_NO_PIPELINE=1 disables.
-    const int K = int(std::min<int64_t>(mk_batch::kMaxSegments, T / 16));
+    int K = int(std::min<int64_t>(12, T / 8));  // (measured on the 128 x 150 x 3000 call: 8 segments 9.9 ms, 12 9.7 ms, 16 9.7 ms)
+    if (getenv("MK_SEGMENTS") && atoi(getenv("MK_SEGMENTS")) >= 1) K = std::min(K, atoi(getenv("MK_SEGMENTS")));  // (tuning)
     const bool pipe = b->groups.size() == 1 && b->small.empty() && !expanded && sd == 1 && sn == D && sb == T * D &&
                       K >= 2 && !(getenv("MK_NO_PIPELINE") && atoi(getenv("MK_NO_PIPELINE")));
     if (pipe) {

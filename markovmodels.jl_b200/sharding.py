@@ -44,7 +44,8 @@ def local_stats(post, ttl, seqlengths=None):
         stats = torch.empty(D + 2, dtype=torch.float64, device=post.device)
         stats[0] = ttl.double().sum()
         stats[1] = frames
-        stats[2:] = post.sum(dim=(0, 2), dtype=torch.float64)
+        # (reduce in the payload dtype, then widen: a float64 reduction would first copy the whole array)
+        stats[2:] = post.sum(dim=(0, 2)).double()
         return stats
     stats = np.empty(D + 2, np.float64)
     stats[0] = np.sum(ttl, dtype=np.float64)
