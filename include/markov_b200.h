@@ -46,7 +46,8 @@ enum mk_status {
 };
 
 /* Semirings.jl types the path is instantiated with (src/MarkovModels.jl:12). */
-enum mk_semiring { MK_LOG = 0, MK_TROPICAL = 1 };
+/* MK_PROB (ProbSemiring: ⊕ = +, ⊗ = *, 0̄ = 0, 1̄ = 1) is accepted by the operator-level entry points only. */
+enum mk_semiring { MK_LOG = 0, MK_TROPICAL = 1, MK_PROB = 2 };
 enum mk_dtype { MK_F32 = 0, MK_F64 = 1 };
 
 typedef struct mk_graph mk_graph; /* one compiled FSM resident on one GPU */
@@ -148,6 +149,33 @@ int mk_bestpath_host(mk_batch* b, const void* ll, int64_t stride_b, int64_t stri
 int mk_lfmmi_grad(int dtype, const void* num_post, const void* den_post, int64_t B, int64_t D,
                   int64_t N, const int32_t* seqlens_dev, double scale, void* grad,
                   int64_t stride_b, int64_t stride_n, int64_t stride_d, void* stream);
+
+/* ---- Operator level: the GPU methods of src/linalg.jl on caller-owned DEVICE arrays --------------------
+ * A = CuSparseMatrixCSR{K}: rowptr (n_rows+1), colval (nnz), nzval (nnz), Cint indices, index_base 1 as CUDA.jl
+ * stores them (0 accepted).  K ∈ {MK_LOG, MK_TROPICAL, MK_PROB} × {MK_F32, MK_F64} — the types the reference's
+ * enabled tests instantiate (test/test_linalg.jl:34-54, 88-108).  Asynchronous on `stream`, current device.
+ *
+ * mk_spmv — LinearAlgebra.mul!(c::CuVector{K}, A::CuSparseMatrixCSR{K}, b::CuVector{K})
+ *   (src/linalg.jl:163-184, kernel :213-233): c[i] = ⊕_k A[i,k] ⊗ b[k].  size(A,2) != len_b or
+ *   size(A,1) != len_c -> MK_EINVAL (DimensionMismatch, :166-167); nnz == 0 -> no launch, c untouched (:169). */
+int mk_spmv(int semiring, int dtype, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* rowptr,
+            const int32_t* colval, const void* nzval, int index_base, const void* b, int64_t len_b,
+            void* c, int64_t len_c, void* stream);
+/* mk_spmm — LinearAlgebra.mul!(C::CuMatrix{K}, A::CuSparseMatrixCSR{K}, B::CuMatrix{K}, α, β)
+ *   (src/linalg.jl:240-262, kernel :268-280): C = (β ⊗ C) ⊕ A ⊗ B with β ∈ {0, 1} as the reference's callers
+ *   use it: accumulate = 0 overwrites C (β = 0: `fill!(C, 0̄)` then ⊕=), accumulate = 1 keeps it (β = 1).
+ *   α is ignored, as in the reference.  B, C column-major with leading dimensions ldb, ldc (elements).
+ *   Dimension errors (:242-244) -> MK_EINVAL. */
+int mk_spmm(int semiring, int dtype, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* rowptr,
+            const int32_t* colval, const void* nzval, int index_base, const void* B, int64_t rows_b,
+            int64_t cols_b, int64_t ldb, void* C, int64_t rows_c, int64_t cols_c, int64_t ldc,
+            int accumulate, void* stream);
+/* mk_spvec_bcast — broadcast of a CuSparseVector{K} with a dense CuVector{K} (src/linalg.jl:287-338):
+ *   dest .= 0̄;  dest[nzind[k]] = op == 0 ? nzval[k] ⊗ y[nzind[k]]   (elmul!, :292)
+ *                                        : nzval[k] ⊘ y[nzind[k]]   (eldiv!, :294). */
+int mk_spvec_bcast(int semiring, int dtype, int op, int64_t n, int64_t nnz, const int32_t* nzind,
+                   const void* nzval, int index_base, const void* y, int64_t len_y, void* dest,
+                   int64_t len_dest, void* stream);
 
 /* Instrumentation: number of kernels this library launched on the calling thread since
  * the last reset (bench.py's gpu_launches), and workspace bytes held by a batch. */

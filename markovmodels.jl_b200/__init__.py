@@ -11,9 +11,10 @@ from ._lib import DimensionMismatch, MarkovError, build, lib  # noqa: F401
 from .fsm import FSM, nstates, rawunion, renorm, union  # noqa: F401
 from .inference import (BatchedFSM, CompiledFSM, StateMap, alpha_recursion, batch, bestpath,  # noqa: F401
                         beta_recursion, compile, expand, pdfposteriors, statemap, αrecursion, βrecursion)
-from .semirings import LogSemiring, TropicalSemiring  # noqa: F401
-from . import algorithms, graphs, lfmmi, sharding  # noqa: F401
-from .algorithms import totalweightsum  # noqa: F401
+from .semirings import LogSemiring, ProbSemiring, TropicalSemiring  # noqa: F401
+from . import algorithms, graphs, lfmmi, linalg, sharding  # noqa: F401
+from .algorithms import totalcumsum, totalsum, totalweightsum  # noqa: F401
+from .linalg import CuSparseMatrixCSR, CuSparseVector, eldiv_, elmul_, mul_  # noqa: F401
 from .lfmmi import lfmmi_grad, lfmmi_loss  # noqa: F401
 
 __version__ = "0.1.0"

@@ -86,6 +86,10 @@ SIGNATURES = {
     "mk_pdfposteriors_host": (C.c_int, [_vp] + _EMIS + [_vp, _vp]),
     "mk_bestpath_host": (C.c_int, [_vp] + _EMIS + [_vp, _vp]),
     "mk_lfmmi_grad": (C.c_int, [C.c_int, _vp, _vp, _i64, _i64, _i64, _vp, C.c_double, _vp, _i64, _i64, _i64, _vp]),
+    "mk_spmv": (C.c_int, [C.c_int, C.c_int, _i64, _i64, _i64, _vp, _vp, _vp, C.c_int, _vp, _i64, _vp, _i64, _vp]),
+    "mk_spmm": (C.c_int, [C.c_int, C.c_int, _i64, _i64, _i64, _vp, _vp, _vp, C.c_int, _vp, _i64, _i64, _i64, _vp, _i64,
+                          _i64, _i64, C.c_int, _vp]),
+    "mk_spvec_bcast": (C.c_int, [C.c_int, C.c_int, C.c_int, _i64, _i64, _vp, _vp, C.c_int, _vp, _i64, _vp, _i64, _vp]),
     "mk_launch_count": (_i64, [C.c_int]),
     "mk_batch_workspace_bytes": (_i64, [_vp]),
     "mk_batch_profile": (C.c_int, [_vp, C.c_int]),

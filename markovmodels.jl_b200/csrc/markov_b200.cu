@@ -7,6 +7,7 @@
 // CUDA kernels of kernels.cuh or fails.
 #include "../../include/markov_b200.h"
 #include "kernels.cuh"
+#include "linalg.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -942,6 +943,100 @@ static int dispatch(mk_batch* bt, Mode mode, const CallArgs& c) {
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// operator level: mul! / sparse-vector broadcast of src/linalg.jl on caller-owned device arrays
+// ------------------------------------------------------------------------------------------------
+static int check_sr_dtype(int semiring, int dtype) {
+    if (semiring != MK_LOG && semiring != MK_TROPICAL && semiring != MK_PROB)
+        return fail(MK_EINVAL, "unknown semiring %d", semiring);
+    if (dtype != MK_F32 && dtype != MK_F64) return fail(MK_EINVAL, "unknown dtype %d", dtype);
+    return MK_OK;
+}
+static int check_csr(int64_t n_rows, int64_t n_cols, int64_t nnz, const void* rowptr, const void* colval,
+                     const void* nzval, int index_base) {
+    if (n_rows < 0 || n_cols < 0 || nnz < 0) return fail(MK_EINVAL, "negative matrix dimension");
+    if (index_base != 0 && index_base != 1) return fail(MK_EINVAL, "index_base must be 0 or 1");
+    if (n_rows >= (int64_t(1) << 31) || n_cols >= (int64_t(1) << 31) || nnz >= (int64_t(1) << 31))
+        return fail(MK_ENOTSUP, "CSR dimensions exceed the Cint index type");
+    if (!rowptr || (nnz > 0 && (!colval || !nzval))) return fail(MK_EINVAL, "null CSR array");
+    return MK_OK;
+}
+static int device_sms() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+        cudaGetLastError();
+        return 0;
+    }
+    return sms;
+}
+
+template <typename T, int SR>
+static int spmv_launch(int64_t n_rows, int64_t nnz, const int32_t* rowptr, const int32_t* colval, const void* nzval,
+                       int base, const void* b, void* c, int sms, cudaStream_t st) {
+    // lanes per row from the mean row length (rows of the path's graphs: ~17 arcs; Ĉ: 1; ω as a 1-row matrix: all)
+    const double mean = double(nnz) / double(std::max<int64_t>(n_rows, 1));
+    const int lanes = mean <= 6 ? 4 : (mean <= 24 ? 8 : 32);
+    const int threads = 256;
+    const int64_t want = (n_rows * lanes + threads - 1) / threads;
+    const int blocks = int(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(sms) * 32)));  // grid-stride beyond
+    const T* v = static_cast<const T*>(nzval); const T* bb = static_cast<const T*>(b); T* cc = static_cast<T*>(c);
+    if (lanes == 4) spmv_kernel<T, SR, 4><<<blocks, threads, 0, st>>>(n_rows, rowptr, colval, v, base, bb, cc);
+    else if (lanes == 8) spmv_kernel<T, SR, 8><<<blocks, threads, 0, st>>>(n_rows, rowptr, colval, v, base, bb, cc);
+    else spmv_kernel<T, SR, 32><<<blocks, threads, 0, st>>>(n_rows, rowptr, colval, v, base, bb, cc);
+    CK(cudaGetLastError());
+    ++g_launches;
+    return MK_OK;
+}
+
+template <typename T, int SR>
+static int spmm_launch(int64_t n_rows, const int32_t* rowptr, const int32_t* colval, const void* nzval, int base,
+                       const void* B, int64_t ldb, void* C, int64_t ldc, int64_t cols, int accumulate, cudaStream_t st) {
+    dim3 grid(unsigned((n_rows + 255) / 256), unsigned(std::min<int64_t>(cols, 65535)));
+    spmm_kernel<T, SR><<<grid, 256, 0, st>>>(n_rows, rowptr, colval, static_cast<const T*>(nzval), base,
+                                             static_cast<const T*>(B), ldb, static_cast<T*>(C), ldc, cols, accumulate);
+    CK(cudaGetLastError());
+    ++g_launches;
+    return MK_OK;
+}
+
+template <typename T, int SR>
+static int spvec_launch(int op, int64_t n, int64_t nnz, const int32_t* nzind, const void* nzval, int base,
+                        const void* y, void* dest, int sms, cudaStream_t st) {
+    const T zero = SR == LSR_PROB ? T(0) : -std::numeric_limits<T>::infinity();
+    if (n > 0) {
+        const int blocks = int(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, int64_t(sms) * 16)));
+        fill_kernel<T><<<blocks, 256, 0, st>>>(static_cast<T*>(dest), n, zero);
+        CK(cudaGetLastError());
+        ++g_launches;
+    }
+    if (nnz > 0) {  // (src/linalg.jl:306: no launch for an empty sparse vector)
+        const int blocks = int(std::max<int64_t>(1, std::min<int64_t>((nnz + 255) / 256, int64_t(sms) * 16)));
+        if (op == 0)
+            spvec_bcast_kernel<T, SR, 0><<<blocks, 256, 0, st>>>(nnz, nzind, static_cast<const T*>(nzval), base,
+                                                                static_cast<const T*>(y), static_cast<T*>(dest));
+        else
+            spvec_bcast_kernel<T, SR, 1><<<blocks, 256, 0, st>>>(nnz, nzind, static_cast<const T*>(nzval), base,
+                                                                static_cast<const T*>(y), static_cast<T*>(dest));
+        CK(cudaGetLastError());
+        ++g_launches;
+    }
+    return MK_OK;
+}
+
+#define MK_SR_DISPATCH(fn, ...)                                                              \
+    do {                                                                                     \
+        if (dtype == MK_F32) {                                                               \
+            if (semiring == MK_LOG) return fn<float, LSR_LOG>(__VA_ARGS__);                  \
+            if (semiring == MK_TROPICAL) return fn<float, LSR_TROPICAL>(__VA_ARGS__);        \
+            return fn<float, LSR_PROB>(__VA_ARGS__);                                         \
+        }                                                                                    \
+        if (semiring == MK_LOG) return fn<double, LSR_LOG>(__VA_ARGS__);                     \
+        if (semiring == MK_TROPICAL) return fn<double, LSR_TROPICAL>(__VA_ARGS__);           \
+        return fn<double, LSR_PROB>(__VA_ARGS__);                                            \
+    } while (0)
+
+
 extern "C" {
 
 int mk_abi_version(void) { return MK_ABI_VERSION; }
@@ -963,6 +1058,9 @@ int mk_graph_create(mk_graph** out, int semiring, int dtype, int64_t n_states_ha
                     int64_t n_pdf_hat, int index_base, int device) {
     if (!out) return fail(MK_EINVAL, "null out");
     *out = nullptr;
+    if (semiring == MK_PROB)
+        return fail(MK_ENOTSUP, "ProbSemiring graphs are served by the operator level (mk_spmv / mk_spmm); the fused "
+                                "recursions take the same graph as LogSemiring (log.(weights))");
     if (semiring != MK_LOG && semiring != MK_TROPICAL) return fail(MK_EINVAL, "unknown semiring %d", semiring);
     if (dtype != MK_F32 && dtype != MK_F64) return fail(MK_EINVAL, "unknown dtype %d", dtype);
     if (index_base != 0 && index_base != 1) return fail(MK_EINVAL, "index_base must be 0 or 1");
@@ -1286,6 +1384,62 @@ int mk_bestpath_host(mk_batch* b, const void* ll, int64_t sb, int64_t sd, int64_
     CK(cudaMemcpyAsync(out_score, b->h_logz.p, b->B * ts, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return MK_OK;
+}
+
+int mk_spmv(int semiring, int dtype, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* rowptr,
+            const int32_t* colval, const void* nzval, int index_base, const void* b, int64_t len_b, void* c,
+            int64_t len_c, void* stream) {
+    TRY(check_sr_dtype(semiring, dtype));
+    TRY(check_csr(n_rows, n_cols, nnz, rowptr, colval, nzval, index_base));
+    if (n_cols != len_b) return fail(MK_EINVAL, "DimensionMismatch: size(A, 2) = %lld, length(b) = %lld",
+                                     (long long)n_cols, (long long)len_b);
+    if (n_rows != len_c) return fail(MK_EINVAL, "DimensionMismatch: size(A, 1) = %lld, length(c) = %lld",
+                                     (long long)n_rows, (long long)len_c);
+    const int sms = device_sms();
+    if (!sms) return fail(MK_ECUDA, "no usable CUDA device (libmarkov_b200 has no CPU fallback)");
+    if (nnz == 0 || n_rows == 0) return MK_OK;  // src/linalg.jl:169: an empty matrix launches nothing, c is untouched
+    if (!b || !c) return fail(MK_EINVAL, "null vector");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MK_SR_DISPATCH(spmv_launch, n_rows, nnz, rowptr, colval, nzval, index_base, b, c, sms, st);
+}
+
+int mk_spmm(int semiring, int dtype, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* rowptr,
+            const int32_t* colval, const void* nzval, int index_base, const void* B, int64_t rows_b, int64_t cols_b,
+            int64_t ldb, void* C, int64_t rows_c, int64_t cols_c, int64_t ldc, int accumulate, void* stream) {
+    TRY(check_sr_dtype(semiring, dtype));
+    TRY(check_csr(n_rows, n_cols, nnz, rowptr, colval, nzval, index_base));
+    if (n_cols != rows_b) return fail(MK_EINVAL, "DimensionMismatch: size(A, 2) = %lld, size(B, 1) = %lld",
+                                      (long long)n_cols, (long long)rows_b);
+    if (n_rows != rows_c) return fail(MK_EINVAL, "DimensionMismatch: size(A, 1) = %lld, size(C, 1) = %lld",
+                                      (long long)n_rows, (long long)rows_c);
+    if (cols_b != cols_c) return fail(MK_EINVAL, "DimensionMismatch: size(B, 2) = %lld, size(C, 2) = %lld",
+                                      (long long)cols_b, (long long)cols_c);
+    if (ldb < rows_b || ldc < rows_c) return fail(MK_EINVAL, "leading dimension smaller than the row count");
+    const int sms = device_sms();
+    if (!sms) return fail(MK_ECUDA, "no usable CUDA device (libmarkov_b200 has no CPU fallback)");
+    if (n_rows == 0 || cols_c == 0) return MK_OK;
+    // β = 1 with an empty A changes nothing; β = 0 still clears C (src/linalg.jl:246-249) — the kernel does both
+    if (nnz == 0 && accumulate) return MK_OK;
+    if (!C || (nnz > 0 && !B)) return fail(MK_EINVAL, "null matrix");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MK_SR_DISPATCH(spmm_launch, n_rows, rowptr, colval, nzval, index_base, B, ldb, C, ldc, cols_c, accumulate ? 1 : 0, st);
+}
+
+int mk_spvec_bcast(int semiring, int dtype, int op, int64_t n, int64_t nnz, const int32_t* nzind, const void* nzval,
+                   int index_base, const void* y, int64_t len_y, void* dest, int64_t len_dest, void* stream) {
+    TRY(check_sr_dtype(semiring, dtype));
+    if (op != 0 && op != 1) return fail(MK_EINVAL, "op must be 0 (*) or 1 (/)");
+    if (index_base != 0 && index_base != 1) return fail(MK_EINVAL, "index_base must be 0 or 1");
+    if (n < 0 || nnz < 0 || nnz > n) return fail(MK_EINVAL, "bad sparse vector sizes");
+    if (len_y != n || len_dest != n)
+        return fail(MK_EINVAL, "DimensionMismatch: sparse vector of length %lld, y %lld, dest %lld", (long long)n,
+                    (long long)len_y, (long long)len_dest);
+    if (nnz > 0 && (!nzind || !nzval || !y)) return fail(MK_EINVAL, "null array");
+    if (n > 0 && !dest) return fail(MK_EINVAL, "null destination");
+    const int sms = device_sms();
+    if (!sms) return fail(MK_ECUDA, "no usable CUDA device (libmarkov_b200 has no CPU fallback)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MK_SR_DISPATCH(spvec_launch, op, n, nnz, nzind, nzval, index_base, y, dest, sms, st);
 }
 
 }  // extern "C"

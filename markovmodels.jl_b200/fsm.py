@@ -17,7 +17,7 @@ import json
 
 import numpy as np
 
-from .semirings import LogSemiring, SemiringType, TropicalSemiring
+from .semirings import LogSemiring, ProbSemiring, SemiringType, TropicalSemiring
 
 
 def _coo_to_csc(K, n_rows, n_cols, row, col, val):
@@ -167,9 +167,10 @@ class FSM:
 
 
 def _parse_semiring(name):
-    fam = LogSemiring if name.startswith("LogSemiring") else TropicalSemiring if name.startswith("TropicalSemiring") else None
+    fam = {"LogSemiring": LogSemiring, "TropicalSemiring": TropicalSemiring,
+           "ProbSemiring": ProbSemiring}.get(name.split("{")[0])
     if fam is None:
-        raise ValueError(f"unsupported semiring {name!r} (inference path covers Log/Tropical)")
+        raise ValueError(f"unsupported semiring {name!r} (the path covers Log/Tropical/Prob)")
     return fam[np.float32 if "Float32" in name else np.float64]
 
 
@@ -187,7 +188,7 @@ def renorm(fsm):
     real = src < S  # drop the phony self-loop
     src, dst, w = src[real], dst[real], w[real]
     tot = np.full(S, K.zero, K.dtype)
-    (np.logaddexp if K.code == 0 else np.maximum).at(tot, src, w)
+    K.add_ufunc.at(tot, src, w)
     w = K.div(w, tot[src])
     fin = dst == S
     a = fsm.init_w

@@ -18,6 +18,7 @@ const LIB = "libmarkov_b200"
 
 semiring_code(::Type{<:LogSemiring}) = Cint(0)
 semiring_code(::Type{<:TropicalSemiring}) = Cint(1)
+semiring_code(::Type{<:ProbSemiring}) = Cint(2)      # operator level only (mk_spmv / mk_spmm / mk_spvec_bcast)
 dtype_code(::Type{Float32}) = Cint(0)
 dtype_code(::Type{Float64}) = Cint(1)
 payload(::Type{<:Semiring{T}}) where T = T   # val(x)::T
@@ -110,6 +111,49 @@ function bestpath(b::B200Batch{K}, lhs::CuArray{T,3}, seqlengths::Vector{<:Integ
                 b.handle, pointer(lhs), 1, B, B * D, D, N, 0, Cint.(seqlengths),
                 pointer(path), pointer(score), CUDA.stream().handle))
     permutedims(path), score
+end
+
+# ---- operator level: the methods of src/linalg.jl themselves -----------------------------------
+# These REPLACE the bodies of src/linalg.jl:163-184 (mul! SpMV), :240-262 (mul! SpMM) and :299-320
+# (_copyto! sparse-vector broadcast): same signatures, same @boundscheck behaviour (the library
+# returns 22 -> DimensionMismatch), same "empty matrix launches nothing" rule.  CuSparseMatrixCSR
+# stores Cint 1-based rowPtr / colVal — passed as they are with index_base = 1.
+import LinearAlgebra
+using CUDA.CUSPARSE: CuSparseMatrixCSR, CuSparseVector
+
+function LinearAlgebra.mul!(c::CuVector{K}, A::CuSparseMatrixCSR{K}, b::CuVector{K}) where K<:Semiring
+    check(ccall((:mk_spmv, LIB), Cint,
+                (Cint, Cint, Int64, Int64, Int64, CuPtr{Cint}, CuPtr{Cint}, CuPtr{Cvoid}, Cint,
+                 CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Int64, Ptr{Cvoid}),
+                semiring_code(K), dtype_code(payload(K)), size(A, 1), size(A, 2), length(A.nzVal),
+                pointer(A.rowPtr), pointer(A.colVal), pointer(A.nzVal), 1,
+                pointer(b), length(b), pointer(c), length(c), CUDA.stream().handle))
+    c
+end
+
+function LinearAlgebra.mul!(C::CuMatrix{K}, A::CuSparseMatrixCSR{K}, B::CuMatrix{K},
+                            α::Number, β::Number) where K<:Semiring
+    (β == 0 || β == 1) || (LinearAlgebra.rmul!(C, β); β = true)     # src/linalg.jl:246-248
+    check(ccall((:mk_spmm, LIB), Cint,
+                (Cint, Cint, Int64, Int64, Int64, CuPtr{Cint}, CuPtr{Cint}, CuPtr{Cvoid}, Cint,
+                 CuPtr{Cvoid}, Int64, Int64, Int64, CuPtr{Cvoid}, Int64, Int64, Int64, Cint, Ptr{Cvoid}),
+                semiring_code(K), dtype_code(payload(K)), size(A, 1), size(A, 2), length(A.nzVal),
+                pointer(A.rowPtr), pointer(A.colVal), pointer(A.nzVal), 1,
+                pointer(B), size(B, 1), size(B, 2), stride(B, 2),
+                pointer(C), size(C, 1), size(C, 2), stride(C, 2), β == 1 ? 1 : 0, CUDA.stream().handle))
+    C
+end
+
+# _copyto!(f, dest, x::CuSparseVector, y::CuVector) — src/linalg.jl:299-320; f is * or /
+function _copyto!(f::Union{typeof(*), typeof(/)}, dest::CuArray{K}, x::CuSparseVector{K}, y::CuVector{K}) where K<:Semiring
+    nzInd, nzVal = SparseArrays.nonzeroinds(x), SparseArrays.nonzeros(x)
+    check(ccall((:mk_spvec_bcast, LIB), Cint,
+                (Cint, Cint, Cint, Int64, Int64, CuPtr{Cint}, CuPtr{Cvoid}, Cint, CuPtr{Cvoid}, Int64,
+                 CuPtr{Cvoid}, Int64, Ptr{Cvoid}),
+                semiring_code(K), dtype_code(payload(K)), f === (*) ? 0 : 1, length(x), length(nzVal),
+                pointer(nzInd), pointer(nzVal), 1, pointer(y), length(y), pointer(dest), length(dest),
+                CUDA.stream().handle))
+    dest
 end
 
 end # module

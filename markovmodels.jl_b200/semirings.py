@@ -11,10 +11,12 @@ the payload floats.
     ⊕         ⊗      0̄      1̄
     Log       logaddexp  +   -Inf   0
     Tropical  max        +   -Inf   0      (max-plus; SURVEY.md A.1, assumption A-TROP)
+    Prob      +          *   0      1      (operator level only: mul! / broadcasts / totalsum,
+                                            test/test_linalg.jl:89, src/algorithms.jl:8-36)
 """
 import numpy as np
 
-MK_LOG, MK_TROPICAL = 0, 1
+MK_LOG, MK_TROPICAL, MK_PROB = 0, 1, 2
 MK_F32, MK_F64 = 0, 1
 
 
@@ -30,28 +32,31 @@ class SemiringType:
         if self.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
             raise TypeError(f"{name} supports Float32/Float64 payloads, got {dtype}")
         self.dtype_code = MK_F32 if self.dtype == np.float32 else MK_F64
-        self.zero = self.dtype.type(-np.inf)
-        self.one = self.dtype.type(0.0)
+        self.zero = self.dtype.type(0.0 if code == MK_PROB else -np.inf)
+        self.one = self.dtype.type(1.0 if code == MK_PROB else 0.0)
+
+    @property
+    def add_ufunc(self):
+        """The numpy ufunc of ⊕ (``.at`` / ``.reduce`` work on it)."""
+        return {MK_LOG: np.logaddexp, MK_TROPICAL: np.maximum, MK_PROB: np.add}[self.code]
 
     # scalar / elementwise host ops on payload floats (graph construction only)
     def add(self, x, y):
-        if self.code == MK_LOG:
-            return np.logaddexp(x, y).astype(self.dtype)
-        return np.maximum(x, y).astype(self.dtype)
+        return self.add_ufunc(x, y).astype(self.dtype)
 
     def mul(self, x, y):
-        return (np.asarray(x, self.dtype) + np.asarray(y, self.dtype)).astype(self.dtype)
+        x, y = np.asarray(x, self.dtype), np.asarray(y, self.dtype)
+        return (x * y if self.code == MK_PROB else x + y).astype(self.dtype)
 
     def div(self, x, y):
-        return (np.asarray(x, self.dtype) - np.asarray(y, self.dtype)).astype(self.dtype)
+        x, y = np.asarray(x, self.dtype), np.asarray(y, self.dtype)
+        return (x / y if self.code == MK_PROB else x - y).astype(self.dtype)
 
     def sum(self, x):
         x = np.asarray(x, self.dtype)
         if x.size == 0:
             return self.zero
-        if self.code == MK_LOG:
-            return self.dtype.type(np.logaddexp.reduce(x))
-        return self.dtype.type(x.max())
+        return self.dtype.type(self.add_ufunc.reduce(x))
 
     def __call__(self, x):
         """``K(x)``: payload constructor (src/fsm.jl:77 ``K(b)``)."""
@@ -82,3 +87,4 @@ class _SemiringFamily:
 
 LogSemiring = _SemiringFamily("LogSemiring", MK_LOG)
 TropicalSemiring = _SemiringFamily("TropicalSemiring", MK_TROPICAL)
+ProbSemiring = _SemiringFamily("ProbSemiring", MK_PROB)

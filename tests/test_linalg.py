@@ -1,0 +1,246 @@
+# SPDX-License-Identifier: MIT
+"""Operator level (mk_spmv / mk_spmm / mk_spvec_bcast) against the oracle — these read like the reference's
+own enabled tests, test/test_linalg.jl: "mul!" (:88-108, the same 4 x 3 matrix, dense 3 x 4 matrix and vector,
+LogSemiring / ProbSemiring / TropicalSemiring x Float32 / Float64) and the sparse-vector broadcasts (:34-54),
+where the reference compares its GPU kernels with the CPU generic path; here the CPU side is the oracle's
+CSR SpMV restatement (oracle.spmv, src/linalg.jl:163-184 contract, CPU accumulation order)."""
+import numpy as np
+import pytest
+
+from test_gpu_parity import torch  # noqa: F401  (fixture)
+
+SEMIRINGS = ["LogSemiring", "ProbSemiring", "TropicalSemiring"]
+DTYPES = [np.float32, np.float64]
+
+
+def _K(mm, name, dtype):
+    return getattr(mm, name)[dtype]
+
+
+def _rel(dtype):
+    return 1e-5 if dtype == np.float32 else 1e-12
+
+
+def _oracle_mul(orc, K, I, J, V, m, n, B):  # noqa: E741
+    """A ⊗ B column by column with the oracle's SpMV (float64 payloads)."""
+    order = np.lexsort((J, I))
+    I, J, V = np.asarray(I)[order], np.asarray(J)[order], np.asarray(V, np.float64)[order]  # noqa: E741
+    rowptr = np.concatenate(([0], np.cumsum(np.bincount(I - 1, minlength=m))))
+    B = np.asarray(B, np.float64)
+    if B.ndim == 1:
+        return orc.spmv(K.code, rowptr, J - 1, V, B)
+    return np.stack([orc.spmv(K.code, rowptr, J - 1, V, B[:, j]) for j in range(B.shape[1])], axis=1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("sr", SEMIRINGS)
+def test_mul_reference_testset(torch, mm, orc, sr, dtype):
+    """test/test_linalg.jl:88-108 verbatim: sm = sparse([1,2,2,3,4], [3,1,2,1,3], K[1,2,3,4,5], 4, 3),
+    dm = reshape(K.(1:12), 3, 4), dv = K.(1:3); mul!(similar(dm, 4, 4), sm, dm) and mul!(similar(dv, 4), sm, dv)."""
+    K = _K(mm, sr, dtype)
+    I, J, V = [1, 2, 2, 3, 4], [3, 1, 2, 1, 3], [1, 2, 3, 4, 5]  # noqa: E741
+    dm = np.arange(1, 13, dtype=np.float64).reshape(4, 3).T  # column-major reshape(1:12, 3, 4)
+    dv = np.arange(1, 4, dtype=np.float64)
+    cu_sm = mm.CuSparseMatrixCSR(K, I, J, V, 4, 3)
+    cu_dm = mm.linalg.to_colmajor(K, dm)
+    cu_dv = torch.from_numpy(dv.astype(dtype)).cuda()
+
+    cu_r = mm.mul_(mm.linalg.colmajor(K, 4, 4, fill=123.0), cu_sm, cu_dm)  # `similar`: uninitialised, β = 0 clears it
+    np.testing.assert_allclose(cu_r.cpu().numpy(), _oracle_mul(orc, K, I, J, V, 4, 3, dm), rtol=_rel(dtype))
+
+    cu_r = mm.mul_(torch.empty(4, dtype=cu_dv.dtype, device="cuda"), cu_sm, cu_dv)
+    np.testing.assert_allclose(cu_r.cpu().numpy(), _oracle_mul(orc, K, I, J, V, 4, 3, dv), rtol=_rel(dtype))
+
+
+@pytest.mark.gpu
+def test_mul_known_answers(torch, mm):
+    """Literal values for the testset above (hand-derivable): row 1 = A[1,3] ⊗ b[3], row 2 = A[2,1] ⊗ b[1] ⊕ A[2,2] ⊗ b[2]…"""
+    I, J, V = [1, 2, 2, 3, 4], [3, 1, 2, 1, 3], [1, 2, 3, 4, 5]  # noqa: E741
+    dv = torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64, device="cuda")
+    want = {"LogSemiring": [4.0, np.logaddexp(3.0, 5.0), 5.0, 8.0], "TropicalSemiring": [4.0, 5.0, 5.0, 8.0],
+            "ProbSemiring": [3.0, 8.0, 4.0, 15.0]}
+    for sr, w in want.items():
+        A = mm.CuSparseMatrixCSR(_K(mm, sr, np.float64), I, J, V, 4, 3)
+        got = mm.mul_(torch.empty(4, dtype=torch.float64, device="cuda"), A, dv)
+        np.testing.assert_allclose(got.cpu().numpy(), w, rtol=1e-14)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("sr", SEMIRINGS)
+def test_mul_random_graph_sizes(torch, mm, orc, sr, dtype):
+    """The shapes the path uses: T̂ᵀ of a denominator-like graph (≈17 arcs per row -> 8 lanes per row), a Ĉ-like
+    matrix (one entry per row -> 4 lanes), a dense-ish short-wide matrix (-> a warp per row), empty rows, 0̄ entries."""
+    K = _K(mm, sr, dtype)
+    rng = np.random.default_rng(7)
+    for m, n, per_row in ((3000, 3000, 17), (5000, 300, 1), (37, 4000, 900), (129, 65, 3)):
+        I = np.repeat(np.arange(1, m + 1), per_row)  # noqa: E741
+        J = rng.integers(1, n + 1, I.size)
+        keep = rng.random(I.size) < 0.9
+        keep[I == 2] = False  # an empty row
+        I, J = I[keep], J[keep]  # noqa: E741
+        _, first = np.unique(np.stack([I, J]), axis=1, return_index=True)  # distinct entries (no ⊕ of duplicates)
+        I, J = I[first], J[first]  # noqa: E741
+        if K.code == 2:
+            V = rng.random(I.size)
+            b = rng.random(n)
+            V[::11] = 0.0
+        else:
+            V = rng.standard_normal(I.size) * 3
+            b = rng.standard_normal(n) * 30  # a wide dynamic range: exp(b) alone would overflow Float32
+            V[::11] = -np.inf
+            b[::13] = -np.inf
+        V, b = V.astype(dtype), b.astype(dtype)
+        A = mm.CuSparseMatrixCSR(K, I, J, V, m, n)
+        got = mm.mul_(torch.full((m,), 777.0, dtype=torch.from_numpy(b).dtype, device="cuda"), A,
+                      torch.from_numpy(b).cuda()).cpu().numpy()
+        want = _oracle_mul(orc, K, I, J, V, m, n, b)
+        np.testing.assert_allclose(got, want, rtol=1e-4 if dtype == np.float32 else 1e-11, atol=1e-30)
+        assert got[1] == K.zero  # the empty row is 0̄, not the previous content
+        # matrix form, 5 columns, with a leading dimension larger than the row count, β = 0 and β = 1
+        Bm = np.stack([np.roll(b, k) for k in range(5)], axis=1)
+        cuB = mm.linalg.to_colmajor(K, Bm)
+        big = mm.linalg.colmajor(K, m + 3, 5, fill=float(K.zero))
+        C = big[:m, :]
+        assert C.stride(1) == m + 3
+        mm.mul_(C, A, cuB)
+        wantM = _oracle_mul(orc, K, I, J, V, m, n, Bm)
+        np.testing.assert_allclose(C.cpu().numpy(), wantM, rtol=1e-4 if dtype == np.float32 else 1e-11, atol=1e-30)
+        np.testing.assert_array_equal(big[m:, :].cpu().numpy(), np.full((3, 5), K.zero))  # padding rows untouched
+        mm.mul_(C, A, cuB, True, True)  # C ⊕= A ⊗ B  ->  C ⊕ C
+        twice = K.add_ufunc(wantM, wantM)
+        np.testing.assert_allclose(C.cpu().numpy(), twice, rtol=1e-4 if dtype == np.float32 else 1e-11, atol=1e-30)
+
+
+@pytest.mark.gpu
+def test_mul_log_full_range(torch, mm):
+    """⊕ of the Log semiring never exponentiates an un-shifted value: payloads around ±1e4 (exp overflows /
+    underflows in both precisions) still give max + log(count)."""
+    for dtype in DTYPES:
+        K = mm.LogSemiring[dtype]
+        for off in (1.0e4, -1.0e4):
+            A = mm.CuSparseMatrixCSR(K, [1] * 40, list(range(1, 41)), [off] * 40, 1, 40)
+            b = torch.zeros(40, dtype=torch.from_numpy(np.zeros(1, dtype)).dtype, device="cuda")
+            got = float(mm.mul_(torch.empty(1, dtype=b.dtype, device="cuda"), A, b)[0])
+            assert got == pytest.approx(off + np.log(40.0), rel=1e-6)
+
+
+@pytest.mark.gpu
+def test_mul_dimension_mismatch_and_empty(torch, mm):
+    """@boundscheck of src/linalg.jl:166-167, 242-244 -> DimensionMismatch; an empty matrix launches nothing (:169)."""
+    K = mm.LogSemiring[np.float32]
+    A = mm.CuSparseMatrixCSR(K, [1, 2], [1, 3], [0.5, 0.25], 2, 3)
+    f = lambda *s: torch.zeros(*s, dtype=torch.float32, device="cuda")  # noqa: E731
+    with pytest.raises(mm.DimensionMismatch):
+        mm.mul_(f(2), A, f(4))
+    with pytest.raises(mm.DimensionMismatch):
+        mm.mul_(f(3), A, f(3))
+    with pytest.raises(mm.DimensionMismatch):
+        mm.mul_(mm.linalg.colmajor(K, 2, 4), A, mm.linalg.colmajor(K, 3, 5))
+    with pytest.raises(mm.DimensionMismatch):
+        mm.mul_(mm.linalg.colmajor(K, 2, 4), A, mm.linalg.colmajor(K, 2, 4))
+    E = mm.CuSparseMatrixCSR(K, [], [], [], 2, 3)
+    c = torch.full((2,), 5.0, dtype=torch.float32, device="cuda")
+    n0 = mm.lib().mk_launch_count(1)
+    mm.mul_(c, E, f(3))
+    assert mm.lib().mk_launch_count(0) == 0 and n0 >= 0
+    np.testing.assert_array_equal(c.cpu().numpy(), [5.0, 5.0])
+    C = mm.linalg.colmajor(K, 2, 2, fill=5.0)
+    mm.mul_(C, E, mm.linalg.colmajor(K, 3, 2, fill=0.0))  # β = 0: fill!(C, 0̄) happens even when A is empty (:246-248)
+    np.testing.assert_array_equal(C.cpu().numpy(), np.full((2, 2), -np.inf, np.float32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("sr", SEMIRINGS)
+def test_sparse_vector_broadcast(torch, mm, sr, dtype):
+    """test/test_linalg.jl:34-54: x (sparse) .* y and x ./ y against the dense computation."""
+    K = _K(mm, sr, dtype)
+    rng = np.random.default_rng(11)
+    n = 1000
+    idx = np.sort(rng.choice(np.arange(1, n + 1), 137, replace=False))
+    xv = (rng.random(137) + 0.1).astype(dtype)
+    y = (rng.random(n) + 0.1).astype(dtype)
+    x = mm.CuSparseVector(K, idx, xv, n)
+    cu_y = torch.from_numpy(y).cuda()
+    dense = np.full(n, K.zero, dtype)
+    for op, fn in ((K.mul, mm.elmul_), (K.div, mm.eldiv_)):
+        want = dense.copy()
+        want[idx - 1] = op(xv, y[idx - 1])
+        out = torch.full((n,), 9.0, dtype=cu_y.dtype, device="cuda")
+        got = fn(out, cu_y, x) if fn is mm.elmul_ else fn(out, x, cu_y)
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-6 if dtype == np.float32 else 1e-15)
+    with pytest.raises(mm.DimensionMismatch):
+        mm.elmul_(torch.zeros(n + 1, dtype=cu_y.dtype, device="cuda"), cu_y, x)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("sr", SEMIRINGS)
+def test_totalsum_totalcumsum_vs_dense(torch, mm, sr, dtype):
+    """totalsum / totalcumsum (src/algorithms.jl:8-29) as host loops of mul! — against dense Float64 recursions in
+    the probability domain (all three semirings agree there: Log = log of Prob; Tropical = max-product)."""
+    K = _K(mm, sr, dtype)
+    KL = mm.LogSemiring[np.float64]
+    rng = np.random.default_rng(5)
+    for base in (mm.graphs.hmm3(KL, 5)[0], mm.graphs.phone_loop(KL, n_phones=4)[0],
+                 mm.graphs.numerator(KL, rng, 50, n_phones=6)[0]):
+        S = base.nstates
+        with np.errstate(divide="ignore"):
+            a, T, w = np.exp(base.α), np.exp(base.T), np.exp(base.ω)  # probabilities
+        src, dst = np.nonzero(T)
+        conv = (lambda p: p) if K.code == 2 else (lambda p: np.log(p))
+        with np.errstate(divide="ignore"):
+            fsm = mm.FSM.from_arrays(K, S, src, dst, conv(T[src, dst]), np.flatnonzero(a), conv(a[a > 0]),
+                                     np.flatnonzero(w), conv(w[w > 0]))
+        for n in (1, 2, S, S + 5):
+            v, terms = a.copy(), []
+            for i in range(1, n + 1):
+                if i > 1:
+                    v = (T * v[:, None]).max(axis=0) if K.code == 1 else T.T @ v
+                terms.append((v * w).max() if K.code == 1 else v @ w)
+            want_sum = terms[-1]
+            want_cum = max(terms) if K.code == 1 else sum(terms)
+            got_sum, got_cum = mm.totalsum(fsm, n), mm.totalcumsum(fsm, n)
+            if K.code != 2:
+                got_sum, got_cum = np.exp(got_sum), np.exp(got_cum)
+            rel = 2e-4 if dtype == np.float32 else 1e-9
+            assert got_sum == pytest.approx(want_sum, rel=rel, abs=1e-300)
+            assert got_cum == pytest.approx(want_cum, rel=rel, abs=1e-300)
+            assert mm.totalweightsum(fsm, n) == pytest.approx(mm.totalcumsum(fsm, n), rel=rel, abs=1e-6)
+
+
+def test_prob_semiring_host_ops(mm):
+    """ProbSemiring scalars: ⊕ = +, ⊗ = *, ⊘ = /, 0̄ = 0, 1̄ = 1; graphs in it are rejected by the fused
+    recursions with MK_ENOTSUP-style guidance, not silently mis-computed."""
+    K = mm.ProbSemiring[np.float64]
+    assert (K.zero, K.one) == (0.0, 1.0)
+    assert K.add(0.25, 0.5) == 0.75 and K.mul(0.25, 0.5) == 0.125 and K.div(0.25, 0.5) == 0.5
+    assert K.sum([0.1, 0.2, 0.3]) == pytest.approx(0.6)
+    f = mm.FSM.from_json('{"semiring": "ProbSemiring{Float64}", "initstates": [[1, 1.0]], "arcs": [[1,1,0.5],[1,2,0.5]],'
+                         ' "finalstates": [[2, 1.0]], "labels": [1, 2]}')
+    assert f.K == K
+    np.testing.assert_array_equal(f.T, [[0.5, 0.5], [0.0, 0.0]])
+    r = mm.renorm(mm.FSM.from_pairs(K, [(1, 2.0)], [((1, 1), 1.0), ((1, 2), 3.0)], [(2, 5.0)], [1, 2]))
+    np.testing.assert_allclose(r.T, [[0.25, 0.75], [0.0, 0.0]])
+    np.testing.assert_allclose(r.ω, [0.0, 1.0])
+    np.testing.assert_allclose(r.α, [1.0, 0.0])
+
+
+def test_operator_entry_points_reject_bad_arguments_without_a_gpu(mm):
+    """Argument validation happens before any device work, so it is checkable here: unknown semiring / dtype,
+    DimensionMismatch, bad index base."""
+    l = mm.lib()
+    assert l.mk_spmv(7, 0, 1, 1, 0, None, None, None, 1, None, 1, None, 1, None) == 22
+    assert l.mk_spmv(0, 5, 1, 1, 0, None, None, None, 1, None, 1, None, 1, None) == 22
+    import ctypes
+    rp = (ctypes.c_int32 * 3)(1, 1, 1)
+    assert l.mk_spmv(0, 0, 2, 3, 0, rp, None, None, 1, None, 4, None, 2, None) == 22  # size(A,2) != length(b)
+    assert b"DimensionMismatch" in l.mk_last_error()
+    assert l.mk_spmv(0, 0, 2, 3, 0, rp, None, None, 2, None, 3, None, 2, None) == 22  # index_base
+    assert l.mk_spmm(2, 1, 2, 3, 0, rp, None, None, 1, None, 3, 4, 3, None, 2, 5, 2, 0, None) == 22  # size(B,2) != size(C,2)
+    assert l.mk_spvec_bcast(0, 0, 2, 4, 1, None, None, 1, None, 4, None, 4, None) == 22  # op
+    if l.mk_device_count() == 0:
+        assert l.mk_spmv(0, 0, 2, 3, 0, rp, None, None, 1, None, 3, None, 2, None) == 1000  # no CPU fallback
+        assert b"no CPU fallback" in l.mk_last_error()
