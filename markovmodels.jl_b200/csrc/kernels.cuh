@@ -629,7 +629,16 @@ template <typename T> struct SharedParams {
     double* carry_C; T* carry_shift;
     int ablate;        // debug builds (MK_ABLATE): 1 no gathers, 2 no finalise, 4 no chunk work, 8 no emission/α loads, 16 no stores
     int bwd_dead_ok;   // the library applied `expand`: co-unreachable rows have β = 0̄ before the last frame
+    // Ragged batches (the intent of the reference's PartialVector drafts, src/inference.jl:76-90,112-127): frames an
+    // utterance tile needs, [ntiles] device ints in [2, N1] or null (= N1 everywhere).  Past its sequence length an
+    // utterance only carries the phony final state along (e_n alive on the phony pdf only, 1̄ self-loop), so a tile
+    // whose longest utterance has L frames stops after frame L (0-based) in the forward sweep and starts there — with
+    // the reference's B[:,end] = 1̄ — in the backward sweep: exactly the values the full sweep would produce.
+    const int* tile_n1;
 };
+template <typename T> __device__ __forceinline__ int tile_limit(const SharedParams<T>& p, int tile) {
+    return p.tile_n1 ? __ldg(p.tile_n1 + tile) : p.N1;
+}
 
 template <typename T> __device__ __forceinline__ V4<T> ld4_nc(const T* p);
 template <> __device__ __forceinline__ V4<float> ld4_nc<float>(const float* p) {
@@ -665,7 +674,7 @@ __device__ __forceinline__ void fwd_combine(const SharedParams<T>& p, int m, con
         const int r = lr.x;
         for (int tile = 0; tile < p.ntiles; ++tile) {
             const int uoff = tile * kTileUtts + lane * 4;
-            if (uoff >= U4) continue;
+            if (uoff >= U4 || m >= tile_limit(p, tile)) continue;
             V4<T> e = ld4_nc<T>(Em + size_t(lr.w) * U4 + uoff);
             V4<T> val;
             if (m == 0) {
@@ -964,6 +973,7 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
                 __syncthreads();
             }
             for (int u = threadIdx.x; u < U4; u += blockDim.x) {
+                if (n >= tile_limit(p, u / kTileUtts)) { s_key[u] = kKeyMin; continue; }  // Ca, shift stay at the tile's last frame
                 T sh = T(0);
                 if (n >= 1) sh = shift_from_key<SR, T>(max(__ldcg(p.gkey + size_t(n - 1) * U4 + u), s_key[u]));
                 s_shift[u] = sh;
@@ -976,6 +986,7 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
             // Utterance tiles in turn; inside a tile the warps pull the CTA's chunks dynamically, largest first.
             // The finaliser (lane pointers, per-utterance scalars, running maxima) is set up once per tile.
             for (int tile = 0; tile < p.ntiles; ++tile) {
+                if (n >= tile_limit(p, tile)) continue;  // ragged batch: this tile's utterances are all finished
                 const bool live = tile * kTileUtts + lane * 4 < U4;  // (lanes beyond the batch stay converged for the pulls)
                 const int uoff = live ? tile * kTileUtts + lane * 4 : 0;
                 FwdFin<T, SR> fin(p, p.alpha + size_t(n > 0 ? n - 1 : 0) * frame_a, p.alpha + size_t(n) * frame_a,
@@ -1030,8 +1041,8 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
             __syncthreads();
         }
         // log Z = α_{N̂}[phony final] = a + Ca   (kernel units inside, natural log out)
-        const T* last = p.alpha + size_t(p.N1 - 1) * frame_a + size_t(S - 1) * U4;
         for (int u = threadIdx.x; u < U4; u += blockDim.x) {
+            const T* last = p.alpha + size_t(tile_limit(p, u / kTileUtts) - 1) * frame_a + size_t(S - 1) * U4;
             T a = __ldcg(last + u);
             double z = (a == neg_inf<T>()) ? double(a) : double(a) + s_C[u];
             int b = p.utt_b[u];
@@ -1054,8 +1065,10 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
     double* Cb = p.Coff + size_t(p.N1) * U4;
     for (int n = p.n_hi - 1; n >= p.n_lo; --n) {
         for (int u = threadIdx.x; u < U4; u += blockDim.x) {
+            const int lim = tile_limit(p, u / kTileUtts);
+            if (n >= lim) continue;  // this tile's backward sweep starts at frame lim - 1
             T sh = T(0);
-            if (n < p.N1 - 1) {
+            if (n < lim - 1) {
                 sh = shift_from_key<SR, T>(__ldcg(gkey_b + size_t(n + 1) * U4 + u));
                 s_C[u] += double(sh) + double(__ldg(p.emax + size_t(n + 1) * U4 + u));
             }
@@ -1069,6 +1082,8 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
         for (int t = threadIdx.x; t < p.ntiles; t += blockDim.x) s_next[t] = c0;
         __syncthreads();
         for (int tile = 0; tile < p.ntiles; ++tile) {  // (as in the forward sweep)
+            const int lim = tile_limit(p, tile);
+            if (n >= lim) continue;
             const bool live = tile * kTileUtts + lane * 4 < U4;
             const int uoff = live ? tile * kTileUtts + lane * 4 : 0;
             BwdFin<T, SR> fin(p, p.bt + size_t((n + 1) & 1) * frame, p.bt + size_t(n & 1) * frame,
@@ -1083,7 +1098,7 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
                 if (MK_ABL(p, 4)) continue;
                 const int4 ch = bwd_src.chunk(wk);
                 if (live) {
-                    if (n == p.N1 - 1) {
+                    if (n == lim - 1) {
                         for (int i = ch.z; i < ch.w; ++i) {
                             fin.prefetch(bwd_src, i);
                             V4<T> beta;
@@ -1365,13 +1380,16 @@ template <typename T> __global__ void normalize_post_kernel(T* post, const T* zs
     }
 }
 // logz[b] = lz[b] + log(min_n zsum[n][b])
-template <typename T> __global__ void total_kernel(const T* zsum, const T* lz, T* logz, int B, int N1) {
+// (nlimit: frames that were evaluated for utterance b — its tile's limit in a ragged batch — or null = N1)
+template <typename T>
+__global__ void total_kernel(const T* zsum, const T* lz, T* logz, int B, int N1, const int* nlimit) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     T l = lz[b];
     if (l == neg_inf<T>()) { logz[b] = l; return; }
     T mn = zsum[b];
-    for (int n = 1; n < N1; ++n) mn = fmin(mn, zsum[size_t(n) * B + b]);
+    const int nl = nlimit ? nlimit[b] : N1;
+    for (int n = 1; n < nl; ++n) mn = fmin(mn, zsum[size_t(n) * B + b]);
     logz[b] = mn > T(0) ? l + T(log(double(mn))) : neg_inf<T>();
 }
 

@@ -525,7 +525,8 @@ struct Group {  // utterances sharing one graph, run by shared_fb_kernel
     bool vec4 = false;
     int* d_utt_b = nullptr;
     long long* d_utt_off = nullptr;
-    DevBuf E, emax, emax_key, alpha, bt, flin, blin, part, gkey, coff, lz2, carry;
+    DevBuf E, emax, emax_key, alpha, bt, flin, blin, part, gkey, coff, lz2, carry, tile_n1;
+    std::vector<int> h_tile_n1;  // ragged batches: frames each utterance tile needs (staging for tile_n1)
 };
 
 struct mk_batch {
@@ -538,7 +539,9 @@ struct mk_batch {
     std::vector<int> small;  // utterances run by small_fb_kernel
     int small_smax = 0;
     int64_t small_cached_n1 = -1;
-    DevBuf small_descs, small_alpha, small_ca, zsum, lz, seqlens, barrier, trace, h_ll, h_post, h_logz, h_path;
+    DevBuf small_descs, small_alpha, small_ca, zsum, lz, seqlens, barrier, trace, h_ll, h_post, h_logz, h_path, zlimit;
+    std::vector<int> h_zlimit;  // ragged batches: frames evaluated per utterance (staging for zlimit)
+    bool ragged_cut = false;    // the current call stops at least one utterance tile early
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
     static constexpr int kMaxSegments = 16;
     cudaEvent_t ev_h2d[kMaxSegments] = {}, ev_done[kMaxSegments] = {};
@@ -553,10 +556,10 @@ struct mk_batch {
         for (auto& gr : groups) {
             cudaFree(gr.d_utt_b); cudaFree(gr.d_utt_off);
             gr.E.release(); gr.alpha.release(); gr.bt.release(); gr.flin.release(); gr.blin.release();
-            gr.part.release(); gr.gkey.release(); gr.coff.release(); gr.emax.release(); gr.emax_key.release(); gr.lz2.release(); gr.carry.release();
+            gr.part.release(); gr.gkey.release(); gr.coff.release(); gr.emax.release(); gr.emax_key.release(); gr.lz2.release(); gr.carry.release(); gr.tile_n1.release();
         }
         DevBuf* all[] = {&small_descs, &small_alpha, &small_ca, &zsum, &lz, &seqlens, &barrier, &trace,
-                         &h_ll, &h_post, &h_logz, &h_path};
+                         &h_ll, &h_post, &h_logz, &h_path, &zlimit};
         for (DevBuf* d : all) d->release();
         if (own_stream) cudaStreamDestroy(own_stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -593,6 +596,11 @@ struct Segments {
     std::vector<int> f;  // frame boundaries: f[0] = 0 < f[1] < ... < f[K] = N̂
     std::function<int(int)> before_fwd, after_bwd;
 };
+
+static bool ragged_cut_enabled() {
+    const char* e = getenv("MK_RAGGED_CUT");
+    return !(e && e[0] == '0');
+}
 
 struct CallArgs {
     const void* ll; int64_t sb, sd, sn, D, T; int expanded; const int32_t* seqlens;
@@ -696,6 +704,28 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     p.n_lo = 0; p.n_hi = N1;
     p.do_fwd = p.do_bwd = p.do_post = 0;
     p.bwd_dead_ok = c.expanded ? 0 : 1;
+    // Ragged batch: an utterance tile (128 consecutive utterances of the group) whose longest
+    // sequence has L < T frames runs frames 0..L only.  Callers that sort their batches by length get the full benefit;
+    // any order is correct.  MK_RAGGED_CUT=0 disables it (the tests compare both).
+    p.tile_n1 = nullptr;
+    if (mode == MODE_POST && c.seqlens && !c.expanded && ragged_cut_enabled()) {
+        gr.h_tile_n1.assign(p.ntiles, 2);
+        bool cut = false;
+        for (int t = 0; t < p.ntiles; ++t) {
+            int lim = 2;
+            const size_t k1 = std::min(gr.utts.size(), size_t(t + 1) * kTileUtts);
+            for (size_t k = size_t(t) * kTileUtts; k < k1; ++k) lim = std::max(lim, c.seqlens[gr.utts[k]] + 1);
+            gr.h_tile_n1[t] = lim = std::min(lim, N1);
+            cut = cut || lim < N1;
+            for (size_t k = size_t(t) * kTileUtts; k < k1; ++k) bt->h_zlimit[gr.utts[k]] = lim;
+        }
+        if (cut) {
+            TRY(gr.tile_n1.ensure(p.ntiles * sizeof(int)));
+            CK(cudaMemcpyAsync(gr.tile_n1.p, gr.h_tile_n1.data(), p.ntiles * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+            p.tile_n1 = static_cast<const int*>(gr.tile_n1.p);
+            bt->ragged_cut = true;
+        }
+    }
     p.ablate = getenv("MK_ABLATE") ? atoi(getenv("MK_ABLATE")) : 0;
 #ifdef MK_ABLATE
     { int ns = (p.ablate & 16) ? 1 : 0; CK(cudaMemcpyToSymbol(g_no_stores, &ns, sizeof ns)); }
@@ -860,6 +890,8 @@ template <typename T, int SR> static int run(mk_batch* bt, Mode mode, const Call
         CK(cudaMemsetAsync(bt->zsum.p, 0, size_t(N1) * B * sizeof(T), c.stream));
     }
     const Segments* seg = (c.seg && bt->groups.size() == 1 && bt->small.empty()) ? c.seg : nullptr;
+    bt->ragged_cut = false;
+    bt->h_zlimit.assign(B, N1);
     for (auto& gr : bt->groups) TRY((launch_shared<T, SR>(bt, gr, mode, c, Dh, N1, Dout, Tout, d_seqlens, seg)));
     TRY((launch_small<T, SR>(bt, mode, c, Dh, N1, Dout, Tout, d_seqlens)));
 
@@ -871,9 +903,15 @@ template <typename T, int SR> static int run(mk_batch* bt, Mode mode, const Call
                                                                  static_cast<const T*>(bt->zsum.p), B, Dout, Tout);
             CK(cudaGetLastError());
         }
+        const int* zlimit = nullptr;
+        if (bt->ragged_cut) {  // frames past a tile's limit were never evaluated: keep them out of minimum(sums)
+            TRY(bt->zlimit.ensure(B * sizeof(int)));
+            CK(cudaMemcpyAsync(bt->zlimit.p, bt->h_zlimit.data(), B * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+            zlimit = static_cast<const int*>(bt->zlimit.p);
+        }
         total_kernel<T><<<(B + 127) / 128, 128, 0, c.stream>>>(static_cast<const T*>(bt->zsum.p),
                                                              static_cast<const T*>(bt->lz.p),
-                                                             static_cast<T*>(c.out1), B, N1);
+                                                             static_cast<T*>(c.out1), B, N1, zlimit);
         CK(cudaGetLastError());
         g_launches += 2;
     }

@@ -522,6 +522,82 @@ def test_host_pipeline_matches_single_launch(torch, mm, orc, dtype):
     np.testing.assert_allclose(out["0"][0], dpost.cpu().numpy(), rtol=rt, atol=1e-9)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("order", ["sorted", "shuffled"])
+def test_ragged_tiles_stop_early(torch, mm, orc, dtype, order):
+    """SURVEY.md §8f rank 4 (the intent of the PartialVector drafts, src/inference.jl:76-90,112-127): in a ragged batch an
+    utterance tile (128 utterances) whose longest sequence has L < T frames runs frames 0..L only — forward sweep stops
+    there, backward sweep starts there with B[:,end] = 1̄.  Same results as the full sweeps (MK_RAGGED_CUT=0) and as the
+    oracle; device path, host pipeline (frame segments), and lengths down to 1."""
+    K = mm.LogSemiring[dtype]
+    rng = np.random.default_rng(77)
+    B, T, D = 300, 36, 60   # three tiles: 128 + 128 + 44
+    g = mm.graphs.denominator(K, n_tokens=400, n_pdf=D, seed=17)
+    V = (rng.standard_normal((B, T, D)) * 2).astype(dtype)
+    lens = np.sort(rng.integers(1, T + 1, B))[::-1].astype(np.int32)
+    lens[0] = T
+    lens[-1] = 1
+    if order == "shuffled":
+        lens = rng.permutation(lens).astype(np.int32)
+        lens[200:] = np.minimum(lens[200:], 9)   # the last tile still stops early
+    b = gpu_batch(mm, [g] * B, D, "shared")
+    out = {}
+    for flag in ("1", "0"):
+        os.environ["MK_RAGGED_CUT"] = flag
+        try:
+            post, ttl = mm.pdfposteriors(b, dev(torch, V), seqlengths=lens)
+            out[flag] = (post.cpu().numpy(), ttl.cpu().numpy())
+        finally:
+            os.environ.pop("MK_RAGGED_CUT", None)
+    rt = 2e-5 if dtype == np.float32 else 1e-11
+    np.testing.assert_allclose(out["1"][1], out["0"][1], rtol=rt)
+    np.testing.assert_allclose(out["1"][0], out["0"][0], rtol=rt, atol=1e-9)
+    check_posteriors(mm, orc, [g] * B, D, V, lens, out["1"][0], out["1"][1], dtype)
+    for n in range(B):  # nothing past an utterance's length, every real frame sums to 1
+        assert not out["1"][0][n, :, lens[n]:].any()
+        np.testing.assert_allclose(out["1"][0][n, :, :lens[n]].sum(axis=0), 1.0, rtol=1e-4)
+    # host-buffer entry point: the same call cut into frame segments
+    hpost, httl = mm.pdfposteriors(b, V.transpose(0, 2, 1), seqlengths=lens)
+    np.testing.assert_allclose(np.array(httl), out["1"][1], rtol=rt)
+    np.testing.assert_allclose(np.array(hpost), out["1"][0], rtol=rt, atol=1e-9)
+    # the other entry points are unaffected by a previous cut call on the same batch
+    A = mm.αrecursion(b, dev(torch, V), seqlengths=lens).cpu().numpy()
+    og = orc_graphs(orc, [g], D)[0]
+    for k in (0, 150, B - 1):
+        oA = orc.alpha_beta(og, V[k], lens[k], want_beta=False)[0]
+        assert_states_close(A[b.offsets[k]:b.offsets[k + 1]], oA, dtype)
+
+
+def test_ragged_cut_saves_frames(torch, mm):
+    """The cut is visible in the kernel time: 4 tiles of which 3 stop after a quarter of the frames."""
+    K = mm.LogSemiring[np.float32]
+    rng = np.random.default_rng(78)
+    B, T, D = 512, 64, 200
+    g = mm.graphs.denominator(K, n_tokens=3000, n_pdf=D, seed=18)
+    V = torch.from_numpy((rng.standard_normal((B, T, D)) * 2).astype(np.float32)).cuda().permute(0, 2, 1)
+    lens = np.full(B, T // 4, np.int32)
+    lens[:128] = T
+    b = gpu_batch(mm, [g] * B, D, "shared")
+    ms = {}
+    for flag in ("1", "0"):
+        os.environ["MK_RAGGED_CUT"] = flag
+        try:
+            for _ in range(2):
+                mm.pdfposteriors(b, V, seqlengths=lens)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                mm.pdfposteriors(b, V, seqlengths=lens)
+            e1.record()
+            torch.cuda.synchronize()
+            ms[flag] = e0.elapsed_time(e1) / 3
+        finally:
+            os.environ.pop("MK_RAGGED_CUT", None)
+    print(f"ragged cut: {ms['1']:.3f} ms vs {ms['0']:.3f} ms per call")
+    assert ms["1"] < 0.8 * ms["0"], ms
+
+
 def test_dimension_mismatch(torch, mm):
     """@boundscheck ... throw(DimensionMismatch()) (src/linalg.jl:166-167)."""
     K = mm.LogSemiring[np.float32]
