@@ -12,7 +12,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libmarkov_b200.so")
+# MARKOV_B200_LIB selects another build of the same ABI (A/B timing of kernel variants, tools/ab_variants.py)
+LIB_PATH = os.environ.get("MARKOV_B200_LIB") or os.path.join(CSRC, "libmarkov_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "markov_b200.h")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

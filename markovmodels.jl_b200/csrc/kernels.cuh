@@ -320,6 +320,7 @@ __device__ __noinline__ void row_reduce_runs(const Arc<T>* __restrict__ arcs, in
                 }
             }
         }
+        if (m[0] == neg_inf<T>() && m[1] == neg_inf<T>() && m[2] == neg_inf<T>() && m[3] == neg_inf<T>()) break;  // a dead row
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) out4[j] = (s[j] > T(0)) ? m[j] + lg2_(s[j]) : neg_inf<T>();
@@ -394,7 +395,7 @@ __device__ __noinline__ void redo_row(const DirPlan<T>* pl, int item, const T* v
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-        if (acc4[j] < tiny) val4[j] = r.v[j] + pl->R;
+        if ((acc4[j] < tiny) && ((live >> j) & 1u)) val4[j] = r.v[j] + pl->R;
 }
 template <typename T> __device__ __forceinline__ unsigned live_mask(const V4<T>& e) {
     unsigned m = 0;
@@ -402,20 +403,46 @@ template <typename T> __device__ __forceinline__ unsigned live_mask(const V4<T>&
     for (int j = 0; j < 4; ++j) m |= (e.v[j] != neg_inf<T>()) ? (1u << j) : 0u;
     return m;
 }
+// [U4] ints in the CTA's shared-memory scalar block (after s_key, see shared_fb_kernel): exactness flags of the frame
+__device__ __forceinline__ int* exact_flags(int U4, size_t tsize) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    return reinterpret_cast<int*>(smem_raw + size_t(U4) * (2 * sizeof(double) + 3 * tsize + sizeof(int)));
+}
+// The rare part of resolve_sum, out of line: which utterances really need the exact path?  Not those whose emission is
+// 0̄, and not those whose all-zero sum is exact by construction: the per-frame, per-utterance flags in shared memory
+// (exact_flags) say whether the gather source of this frame lives on the seed states only — bit5: the frame after α̂
+// (forward) / the frame before an utterance's phony frames (backward); bit6: the frames after an utterance's first
+// phony frame (forward) — and the same bits of item.w say that this item has no arc from such a state.  In a ragged
+// batch the finished utterances would otherwise send the 146 segments of the phony final state's row through the
+// serial exact path in every frame (measured: 5x per frame).
 template <typename T, int SR>
-__device__ __forceinline__ V4<T> resolve_sum(const V4<T>& acc, const V4<T>& e, bool need_all, bool dead,
+__device__ __noinline__ V4<T> resolve_slow(V4<T> acc, V4<T> val, unsigned live, int item_w, const DirPlan<T>* pl, int item,
+                                           const T* vec, int U4, int uoff) {
+    const int4 xf = *reinterpret_cast<const int4*>(exact_flags(U4, sizeof(T)) + uoff);
+    const int xw[4] = {xf.x, xf.y, xf.z, xf.w};
+    unsigned need = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (acc.v[j] < tiny_sum<T>() && ((live >> j) & 1u) && !((item_w & xw[j] & 96) && acc.v[j] == T(0))) need |= 1u << j;
+    if (need) {
+        T a4[4], v4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { a4[j] = acc.v[j]; v4[j] = val.v[j]; }
+        redo_row<T, SR>(pl, item, vec, U4, uoff, a4, need, v4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) val.v[j] = v4[j];
+    }
+    return val;
+}
+template <typename T, int SR>
+__device__ __forceinline__ V4<T> resolve_sum(const V4<T>& acc, const V4<T>& e, bool need_all, bool dead, int item_w,
                                              const DirPlan<T>& pl, int item, const T* vec, int U4, int uoff) {
     if (SR == SR_TROP) return acc;
     V4<T> val;
 #pragma unroll
     for (int j = 0; j < 4; ++j) val.v[j] = lg2_(acc.v[j]) + pl.R;  // acc == 0 -> -Inf
-    if (min4(acc) < tiny_sum<T>() && !dead) {  // rare (a statically dead row: the all-zero sum is exact)
-        T a4[4], v4[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { a4[j] = acc.v[j]; v4[j] = val.v[j]; }
-        redo_row<T, SR>(&pl, item, vec, U4, uoff, a4, need_all ? 15u : live_mask(e), v4);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) val.v[j] = v4[j];
+    if (min4(acc) < tiny_sum<T>() && !dead) {
+        val = resolve_slow<T, SR>(acc, val, need_all ? 15u : live_mask(e), item_w, &pl, item, vec, U4, uoff);
     }
     return val;
 }
@@ -635,6 +662,7 @@ template <typename T> struct SharedParams {
     // whose longest utterance has L frames stops after frame L (0-based) in the forward sweep and starts there — with
     // the reference's B[:,end] = 1̄ — in the backward sweep: exactly the values the full sweep would produce.
     const int* tile_n1;
+    const int* seqlens;  // device [B] sequence lengths, or null (= Tn for every utterance); meaningful when bwd_dead_ok
 };
 template <typename T> __device__ __forceinline__ int tile_limit(const SharedParams<T>& p, int tile) {
     return p.tile_n1 ? __ldg(p.tile_n1 + tile) : p.N1;
@@ -752,6 +780,7 @@ template <typename T, int SR> struct FwdFin {
     }
     // val: the row's normalised a_n (log2 / tropical)
     __device__ __forceinline__ void store(V4<T>& val) {
+        if (MK_ABL(p, 128) && all_zero_bar(val) && !(it.w & 1)) return;
 #pragma unroll
         for (int j = 0; j < 4; ++j) mx[j] = max_(mx[j], val.v[j]);
         st4_cg(cur_l + size_t(unsigned(it.x)) * 4, val);
@@ -768,7 +797,8 @@ template <typename T, int SR> struct FwdFin {
     }
     __device__ __forceinline__ void operator()(int item, const V4<T>& acc) {
         // item.w bit3: no initial state reaches this row — α = 0̄ in every frame; bit4: the row has no arcs
-        V4<T> val = resolve_sum<T, SR>(acc, e, false, it.w & 24, p.fwd, item, prev, p.U4, uoff);  // T̂ᵀ A[:,n-1] (:70)
+        V4<T> val = resolve_sum<T, SR>(acc, e, false, (it.w & 24) || MK_ABL(p, 64), it.w, p.fwd, item, prev, p.U4,
+                                       uoff);  // T̂ᵀ A[:,n-1] (:70)
         if (it.z >= 0) {  // segment of a long row: partial ⊕ only
             st4_cg(part_l + size_t(it.z) * p.U4, val);
             return;
@@ -831,6 +861,8 @@ template <typename T, int SR> struct BwdFin {
                 zs[j] = lin_add<SR>(zs[j], pg.v[j]);
             }
             const int pdf = it.z;
+            if (MK_ABL(p, 256) && pg.v[0] == T(0) && pg.v[1] == T(0) && pg.v[2] == T(0) && pg.v[3] == T(0)) {
+            } else
             if (post_on && pdf < p.D) {
                 T* dst = post_l + size_t(pdf) * p.B;
                 if (p.post_vec4 && SR == SR_LOG) {
@@ -862,8 +894,8 @@ template <typename T, int SR> struct BwdFin {
     __device__ __forceinline__ void operator()(int item, const V4<T>& acc) {
         // an explicit β output needs β_n even where e_n = 0̄ kills α_n and b_n ⊗ e_n
         // item.w bit3: the phony final state is unreachable from this row — β = 0̄ (under `expand` emissions)
-        V4<T> beta = resolve_sum<T, SR>(acc, e, p.beta_out != nullptr, ((it.w & 8) && p.bwd_dead_ok) || (it.w & 16), p.bwd, item,
-                                        bt_next, p.U4, uoff);  // (:106-107)
+        V4<T> beta = resolve_sum<T, SR>(acc, e, p.beta_out != nullptr, ((it.w & 8) && p.bwd_dead_ok) || (it.w & 16) || MK_ABL(p, 64),
+                                        it.w, p.bwd, item, bt_next, p.U4, uoff);  // (:106-107)
 #pragma unroll
         for (int j = 0; j < 4; ++j) beta.v[j] += c[j];
         last = beta;
@@ -919,7 +951,7 @@ __host__ __device__ inline size_t arc_cache_bytes(int cap, int items, int chunks
     return size_t(cap) * (4 + tsize) + ((size_t(items) * 24 + 15) & ~size_t(15)) + size_t(chunks) * 16;
 }
 __host__ __device__ inline size_t shared_scalars_bytes(int U4, size_t tsize) {
-    return (size_t(U4) * (2 * sizeof(double) + 3 * tsize + sizeof(int)) + size_t((U4 + 127) / 128) * sizeof(int) + 16 + 15) &
+    return (size_t(U4) * (2 * sizeof(double) + 3 * tsize + 2 * sizeof(int)) + size_t((U4 + 127) / 128) * sizeof(int) + 16 + 15) &
            ~size_t(15);
 }
 
@@ -935,7 +967,8 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
     T* s_g = s_shift + U4;                                // [U4] Ca_n + Cb_n - log Z
     T* s_z = s_g + U4;                                    // [U4] per-frame posterior mass
     int* s_key = reinterpret_cast<int*>(s_z + U4);        // [U4] running maxima
-    int* s_next = s_key + U4;                             // [ntiles] dynamic chunk counters, one per utterance tile
+    int* s_exact = s_key + U4;                            // [U4] exactness flags of the frame (resolve_sum, exact_flags())
+    int* s_next = s_exact + U4;                           // [ntiles] dynamic chunk counters, one per utterance tile
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t frame = size_t(S) * U4;      // β-side vectors: Ŝ rows
     const size_t frame_q = size_t(p.Sq) * U4;  // forward vectors with the merged-run rows: Ŝ + runs
@@ -974,6 +1007,11 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
             }
             for (int u = threadIdx.x; u < U4; u += blockDim.x) {
                 if (n >= tile_limit(p, u / kTileUtts)) { s_key[u] = kKeyMin; continue; }  // Ca, shift stay at the tile's last frame
+                {   // is the gather source α_{n-1} confined to the seed states?  (only meaningful under `expand`)
+                    const int b = p.utt_b[u];
+                    const int L = (b >= 0 && p.seqlens) ? __ldg(p.seqlens + b) : p.Tn;
+                    s_exact[u] = (n == 1 ? 32 : 0) | ((p.bwd_dead_ok && n - 1 >= L) ? 64 : 0);
+                }
                 T sh = T(0);
                 if (n >= 1) sh = shift_from_key<SR, T>(max(__ldcg(p.gkey + size_t(n - 1) * U4 + u), s_key[u]));
                 s_shift[u] = sh;
@@ -1067,6 +1105,11 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
         for (int u = threadIdx.x; u < U4; u += blockDim.x) {
             const int lim = tile_limit(p, u / kTileUtts);
             if (n >= lim) continue;  // this tile's backward sweep starts at frame lim - 1
+            {   // is the gather source b_{n+1} ⊗ e_{n+1} confined to the phony final state?
+                const int b = p.utt_b[u];
+                const int L = (b >= 0 && p.seqlens) ? __ldg(p.seqlens + b) : p.Tn;
+                s_exact[u] = (p.bwd_dead_ok && n + 1 >= L) ? 32 : 0;
+            }
             T sh = T(0);
             if (n < lim - 1) {
                 sh = shift_from_key<SR, T>(__ldcg(gkey_b + size_t(n + 1) * U4 + u));

@@ -147,6 +147,8 @@ struct mk_graph {
 // kernels.cuh DirPlan): every chunk spans a multiple of four arcs, every item owns >= 1 arc.
 constexpr int kItemDead = 8;    // item.w bit3 (both sweeps): statically dead row, see kernels.cuh
 constexpr int kItemEmpty = 16;  // item.w bit4 (both sweeps): the row has no arcs
+constexpr int kItemNoSeed = 32;  // item.w bit5: forward — no in-arc from an initial state; backward — no arc into the phony final state
+constexpr int kItemNoFinalPred = 64;  // item.w bit6 (forward): no in-arc from the phony final state (every row but the phony state's self-loop segment)
 constexpr double kItemCost = 12.0;
 constexpr int kLongRow = 128;
 constexpr int kMinSegment = 64;
@@ -196,7 +198,12 @@ static void build_plan(const std::vector<int>& ptr, const std::vector<Arc<T>>& a
         const int seg = std::max(kMinSegment, (deg + kMaxSlotsPerRow - 1) / kMaxSlotsPerRow);
         const int pseudo_beg = int(long_arcs.size());
         for (int a = beg; a < end; a += seg) {
-            d.items.push_back(make_int4(r, pdf[r], n_slots, 0));
+            // (segments of a long row: bit6 per segment — the phony final state's in-arcs are all the final weights
+            // plus its own self-loop, and only the segment holding the self-loop ever sees a live source once an
+            // utterance is past its last frame)
+            bool from_final = false;
+            for (int k = a; k < std::min(end, a + seg); ++k) from_final = from_final || arcs[k].idx == S - 1;
+            d.items.push_back(make_int4(r, pdf[r], n_slots, from_final ? 0 : kItemNoFinalPred));
             d.item_arcs.push_back(make_int2(a, std::min(end, a + seg)));
             Arc<T> pa;
             std::memset(&pa, 0, sizeof pa);
@@ -448,6 +455,16 @@ static int build_graph(mk_graph* g, const int64_t* colptr, const int64_t* rowval
         // a row without arcs sums to 0̄ whatever the emissions are
         if (in_ptr_m[s + 1] == in_ptr_m[s]) gf_fwd[s] |= kItemEmpty;
         if (out_ptr[s + 1] == out_ptr[s]) gf_bwd[s] |= kItemEmpty;
+        // rows whose ⊕ is exactly 0̄ in the frame after α̂ / the frame before the phony frames (kernels.cuh, exact0)
+        bool seeded = false;
+        for (int a = in_ptr[s]; a < in_ptr[s + 1] && !seeded; ++a) seeded = init[in_arcs[a].idx] > ninf && in_arcs[a].w > ninf;
+        if (!seeded) gf_fwd[s] |= kItemNoSeed;
+        bool from_final = false;
+        for (int a = in_ptr[s]; a < in_ptr[s + 1] && !from_final; ++a) from_final = in_arcs[a].idx == S - 1 && in_arcs[a].w > ninf;
+        if (!from_final) gf_fwd[s] |= kItemNoFinalPred;
+        bool to_final = false;
+        for (int a = out_ptr[s]; a < out_ptr[s + 1] && !to_final; ++a) to_final = out_arcs[a].idx == S - 1 && out_arcs[a].w > ninf;
+        if (!to_final) gf_bwd[s] |= kItemNoSeed;
     }
 
     // Bounds for the single-pass ⊕ (kernels.cuh): stored a_n <= max(log max column-sum, max α̂),
@@ -708,6 +725,7 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     // sequence has L < T frames runs frames 0..L only.  Callers that sort their batches by length get the full benefit;
     // any order is correct.  MK_RAGGED_CUT=0 disables it (the tests compare both).
     p.tile_n1 = nullptr;
+    p.seqlens = d_seqlens;
     if (mode == MODE_POST && c.seqlens && !c.expanded && ragged_cut_enabled()) {
         gr.h_tile_n1.assign(p.ntiles, 2);
         bool cut = false;
@@ -1030,9 +1048,10 @@ static int spmv_launch(int64_t n_rows, int64_t nnz, const int32_t* rowptr, const
 template <typename T, int SR>
 static int spmm_launch(int64_t n_rows, const int32_t* rowptr, const int32_t* colval, const void* nzval, int base,
                        const void* B, int64_t ldb, void* C, int64_t ldc, int64_t cols, int accumulate, cudaStream_t st) {
-    dim3 grid(unsigned((n_rows + 255) / 256), unsigned(std::min<int64_t>(cols, 65535)));
-    spmm_kernel<T, SR><<<grid, 256, 0, st>>>(n_rows, rowptr, colval, static_cast<const T*>(nzval), base,
-                                             static_cast<const T*>(B), ldb, static_cast<T*>(C), ldc, cols, accumulate);
+    constexpr int CJ = 8;  // columns per thread
+    dim3 grid(unsigned((n_rows + 255) / 256), unsigned(std::min<int64_t>((cols + CJ - 1) / CJ, 65535)));
+    spmm_kernel<T, SR, CJ><<<grid, 256, 0, st>>>(n_rows, rowptr, colval, static_cast<const T*>(nzval), base,
+                                                 static_cast<const T*>(B), ldb, static_cast<T*>(C), ldc, cols, accumulate);
     CK(cudaGetLastError());
     ++g_launches;
     return MK_OK;

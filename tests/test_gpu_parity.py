@@ -74,7 +74,7 @@ def dev(torch, V_btd):
     return torch.from_numpy(np.ascontiguousarray(V_btd)).cuda().permute(0, 2, 1)
 
 
-def check_posteriors(mm, orc, graphs, D, V, lens, post, ttl, dtype):
+def check_posteriors(mm, orc, graphs, D, V, lens, post, ttl, dtype, ttl_atol=0.0):
     """The parity bar.  Float64: 1e-9 against the oracle.  Float32: the oracle evaluated in Float32
     (the reference's arithmetic) carries its own rounding error — ulp(|α|) per ⊕, |α| growing with
     the frame index — so two correct Float32 evaluations cannot agree to 1e-4 on long sequences.
@@ -95,8 +95,8 @@ def check_posteriors(mm, orc, graphs, D, V, lens, post, ttl, dtype):
             cache[id(f)] = (f.astype(K64), p)
         g64.append(cache[id(f)])
     xpost, xttl = orc.pdfposteriors(orc_graphs(orc, g64, D), V.astype(np.float64), lens)
-    np.testing.assert_allclose(ttl, xttl, rtol=1e-4)
-    np.testing.assert_allclose(ttl, ottl, rtol=1e-4)
+    np.testing.assert_allclose(ttl, xttl, rtol=1e-4, atol=ttl_atol)
+    np.testing.assert_allclose(ttl, ottl, rtol=1e-4, atol=ttl_atol)
     np.testing.assert_allclose(post, xpost, **TOL[dtype])                       # (i)
     ref_err = np.abs(opost - xpost).max()
     assert np.abs(post - opost).max() <= 2 * ref_err + 1e-6, (np.abs(post - opost).max(), ref_err)  # (ii)
@@ -552,7 +552,8 @@ def test_ragged_tiles_stop_early(torch, mm, orc, dtype, order):
     rt = 2e-5 if dtype == np.float32 else 1e-11
     np.testing.assert_allclose(out["1"][1], out["0"][1], rtol=rt)
     np.testing.assert_allclose(out["1"][0], out["0"][0], rtol=rt, atol=1e-9)
-    check_posteriors(mm, orc, [g] * B, D, V, lens, out["1"][0], out["1"][1], dtype)
+    # (one- and two-frame utterances have |log Z| < 0.1: Float32 rounding of the emissions alone is 1e-5 absolute)
+    check_posteriors(mm, orc, [g] * B, D, V, lens, out["1"][0], out["1"][1], dtype, ttl_atol=2e-5)
     for n in range(B):  # nothing past an utterance's length, every real frame sums to 1
         assert not out["1"][0][n, :, lens[n]:].any()
         np.testing.assert_allclose(out["1"][0][n, :, :lens[n]].sum(axis=0), 1.0, rtol=1e-4)
