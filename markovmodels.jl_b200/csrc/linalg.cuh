@@ -57,6 +57,7 @@ template <typename T> struct Acc<T, LSR_LOG> {
     }
     __device__ __forceinline__ T value() const { return s > T(0) ? m + lin_log(s) : lin_neg_inf<T>(); }
     __device__ __forceinline__ void add_value(T v) { add_prod(v, T(0)); }
+    __device__ __forceinline__ void spill(T& a, T& b_) const { a = m; b_ = s; }
 };
 template <typename T> struct Acc<T, LSR_TROPICAL> {
     T m;
@@ -71,6 +72,8 @@ template <typename T> struct Acc<T, LSR_TROPICAL> {
     }
     __device__ __forceinline__ T value() const { return m; }
     __device__ __forceinline__ void add_value(T v) { m = v > m ? v : m; }
+    __device__ __forceinline__ void spill(T& a, T& b_) const { a = m; b_ = T(0); }
+    __device__ __forceinline__ void merge(T om, T) { m = om > m ? om : m; }
 };
 template <typename T> struct Acc<T, LSR_PROB> {
     T s;
@@ -82,35 +85,140 @@ template <typename T> struct Acc<T, LSR_PROB> {
     }
     __device__ __forceinline__ T value() const { return s; }
     __device__ __forceinline__ void add_value(T v) { s += v; }
+    __device__ __forceinline__ void spill(T& a, T& b_) const { a = s; b_ = T(0); }
+    __device__ __forceinline__ void merge(T os, T) { s += os; }
 };
 
 // c[r] = ⊕_k nzval[k] ⊗ b[colval[k]] — LANES lanes per row (the reference spends a whole warp per row,
 // src/linalg.jl:213-233; rows of the path's graphs hold ~17 arcs, so the host picks 4/8/32 from nnz / rows).
-template <typename T, int SR, int LANES>
+// A row is taken in chunks of LANES x R arcs: every lane first requests its R (colval, nzval) pairs and the R
+// gathers from b — all in flight together — and only then folds them.  Log semiring: the chunk's maximum is made
+// group-uniform with LANES-wide shuffles, every lane adds exp(v - M) of its own arcs to a lane-local sum (one exp per
+// arc, no data-dependent branches), a later chunk rescales that sum by exp(M_old - M_new); one shuffle-sum at the end.
+template <typename T, int SR, int LANES, int R>
 __global__ void spmv_kernel(long long n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colval,
-                            const T* __restrict__ nzval, int base, const T* __restrict__ b, T* __restrict__ c) {
+                            const T* __restrict__ nzval, int base, const T* __restrict__ b, T* __restrict__ c,
+                            int long_row, int* __restrict__ worklist, int worklist_cap) {
+    constexpr int U = 1;  // rows per lane group in flight (2 measured slower: 1.02 vs 0.65 ms at cfg 3)
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = int(gid % LANES);
     const long long rows_per_pass = (long long)gridDim.x * blockDim.x / LANES;
     // every lane of a warp runs the same number of passes: the shuffles below are warp-wide
-    const long long passes = (n_rows + rows_per_pass - 1) / rows_per_pass;
-    long long r = gid / LANES;
-    for (long long it = 0; it < passes; ++it, r += rows_per_pass) {
-        Acc<T, SR> acc;
-        if (r < n_rows) {
-            const int beg = rowptr[r] - base, end = rowptr[r + 1] - base;
-            int k = beg + lane;
-            for (; k + LANES < end; k += 2 * LANES) {  // two arcs per trip: four loads and two gathers in flight
-                const int c0 = colval[k], c1 = colval[k + LANES];
-                const T w0 = nzval[k], w1 = nzval[k + LANES];
-                const T x0 = b[c0 - base], x1 = b[c1 - base];
-                acc.add_prod(w0, x0);
-                acc.add_prod(w1, x1);
+    const long long passes = (n_rows + rows_per_pass * U - 1) / (rows_per_pass * U);
+    long long r0 = gid / LANES;
+    const T zero = SR == LSR_PROB ? T(0) : lin_neg_inf<T>();
+    for (long long it = 0; it < passes; ++it, r0 += rows_per_pass * U) {
+        int beg[U], end[U], len = 0;
+        bool skip[U] = {};
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long r = r0 + u * rows_per_pass;
+            beg[u] = end[u] = 0;
+            if (r < n_rows) { beg[u] = rowptr[r] - base; end[u] = rowptr[r + 1] - base; }
+            // A row far longer than the rest (the phony final state of an FSM collects every final weight: 9 300 arcs
+            // against a mean of 17 at cfg 3) would keep one lane group busy for hundreds of chunks while the grid
+            // drains: it goes to the work list of spmv_long_kernel (a whole CTA per row) instead.
+            const bool is_long = worklist != nullptr && end[u] - beg[u] > long_row;
+            int slot = 0;
+            if (is_long && lane == 0) slot = atomicAdd(worklist, 1);
+            slot = __shfl_sync(0xffffffffu, slot, 0, LANES);  // (every lane of the warp takes part; is_long is group-uniform)
+            if (is_long && slot < worklist_cap) {
+                if (lane == 0) worklist[1 + slot] = int(r);
+                beg[u] = end[u] = 0;
+                skip[u] = true;
             }
-            if (k < end) acc.add_prod(nzval[k], b[colval[k] - base]);
+            len = max(len, end[u] - beg[u]);
         }
-        acc.template reduce<LANES>();
-        if (lane == 0 && r < n_rows) c[r] = acc.value();
+        // chunks of this warp: the longest row among the warp's groups decides (shuffles are warp-wide)
+#pragma unroll
+        for (int o = 16; o >= LANES; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+        T M[U], S[U], A[U];  // Log: running maximum (group-uniform) and lane-local scaled sum; else lane-local accumulator
+#pragma unroll
+        for (int u = 0; u < U; ++u) { M[u] = lin_neg_inf<T>(); S[u] = T(0); A[u] = zero; }
+        for (int k0 = 0; k0 < len; k0 += LANES * R) {
+            T v[U][R];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    const int k = beg[u] + k0 + q * LANES + lane;
+                    v[u][q] = zero;
+                    if (k < end[u]) {
+                        const T w = nzval[k];
+                        const T x = b[colval[k] - base];
+                        v[u][q] = SR == LSR_PROB ? w * x : w + x;
+                    }
+                }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (SR == LSR_LOG) {
+                    T m = v[u][0];
+#pragma unroll
+                    for (int q = 1; q < R; ++q) m = v[u][q] > m ? v[u][q] : m;
+#pragma unroll
+                    for (int o = LANES / 2; o > 0; o >>= 1) { const T om = __shfl_xor_sync(0xffffffffu, m, o); m = om > m ? om : m; }
+                    const T Mn = m > M[u] ? m : M[u];
+                    if (Mn > lin_neg_inf<T>()) {  // (everything seen so far is 0̄ otherwise)
+                        T sum = S[u] * lin_exp(M[u] - Mn);   // first chunk: S = 0
+#pragma unroll
+                        for (int q = 0; q < R; ++q) sum += lin_exp(v[u][q] - Mn);  // exp(-Inf) = 0 for pads and 0̄ entries
+                        S[u] = sum;
+                        M[u] = Mn;
+                    }
+                } else if (SR == LSR_TROPICAL) {
+#pragma unroll
+                    for (int q = 0; q < R; ++q) A[u] = v[u][q] > A[u] ? v[u][q] : A[u];
+                } else {
+#pragma unroll
+                    for (int q = 0; q < R; ++q) A[u] += v[u][q];
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            T out;
+            if (SR == LSR_LOG) {
+                T sum = S[u];
+#pragma unroll
+                for (int o = LANES / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                out = sum > T(0) ? M[u] + lin_log(sum) : lin_neg_inf<T>();
+            } else {
+                T acc = A[u];
+#pragma unroll
+                for (int o = LANES / 2; o > 0; o >>= 1) {
+                    const T oa = __shfl_xor_sync(0xffffffffu, acc, o);
+                    acc = SR == LSR_TROPICAL ? (oa > acc ? oa : acc) : acc + oa;
+                }
+                out = acc;
+            }
+            const long long r = r0 + u * rows_per_pass;
+            if (lane == 0 && r < n_rows && !skip[u]) c[r] = out;
+        }
+    }
+}
+
+// The long rows of spmv_kernel's work list ({count, rows...}): one CTA of 256 threads per row, grid-stride over the list.
+template <typename T, int SR>
+__global__ void spmv_long_kernel(const int* __restrict__ worklist, int worklist_cap, const int32_t* __restrict__ rowptr,
+                                 const int32_t* __restrict__ colval, const T* __restrict__ nzval, int base,
+                                 const T* __restrict__ b, T* __restrict__ c) {
+    __shared__ T sm[8], ss[8];
+    const int count = min(worklist[0], worklist_cap);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = blockIdx.x; i < count; i += gridDim.x) {
+        const int r = worklist[1 + i];
+        const int beg = rowptr[r] - base, end = rowptr[r + 1] - base;
+        Acc<T, SR> acc;
+        for (int k = beg + threadIdx.x; k < end; k += blockDim.x) acc.add_prod(nzval[k], b[colval[k] - base]);
+        acc.template reduce<32>();
+        if (lane == 0) acc.spill(sm[warp], ss[warp]);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            Acc<T, SR> tot;
+            for (int w = 0; w < int(blockDim.x >> 5); ++w) tot.merge(sm[w], ss[w]);
+            c[r] = tot.value();
+        }
+        __syncthreads();
     }
 }
 

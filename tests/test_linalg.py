@@ -80,6 +80,10 @@ def test_mul_random_graph_sizes(torch, mm, orc, sr, dtype):
         keep = rng.random(I.size) < 0.9
         keep[I == 2] = False  # an empty row
         I, J = I[keep], J[keep]  # noqa: E741
+        if m == 3000:  # two rows far longer than the rest (the phony final state's row of T̂ᵀ): the CTA-per-row path
+            for row, cnt in ((6, 2900), (2999, 1500)):
+                I = np.concatenate([I, np.full(cnt, row)])  # noqa: E741
+                J = np.concatenate([J, np.arange(1, cnt + 1)])
         _, first = np.unique(np.stack([I, J]), axis=1, return_index=True)  # distinct entries (no ⊕ of duplicates)
         I, J = I[first], J[first]  # noqa: E741
         if K.code == 2:
