@@ -107,14 +107,24 @@ __global__ void spmv_kernel(long long n_rows, const int32_t* __restrict__ rowptr
     const long long passes = (n_rows + rows_per_pass * U - 1) / (rows_per_pass * U);
     long long r0 = gid / LANES;
     const T zero = SR == LSR_PROB ? T(0) : lin_neg_inf<T>();
+    // (the row pointers of the next pass are requested before this pass's arcs: one round trip less per pass)
+    int nbeg[U], nend[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const long long r = r0 + u * rows_per_pass;
+        nbeg[u] = nend[u] = 0;
+        if (r < n_rows) { nbeg[u] = rowptr[r] - base; nend[u] = rowptr[r + 1] - base; }
+    }
     for (long long it = 0; it < passes; ++it, r0 += rows_per_pass * U) {
         int beg[U], end[U], len = 0;
         bool skip[U] = {};
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const long long r = r0 + u * rows_per_pass;
-            beg[u] = end[u] = 0;
-            if (r < n_rows) { beg[u] = rowptr[r] - base; end[u] = rowptr[r + 1] - base; }
+            beg[u] = nbeg[u]; end[u] = nend[u];
+            const long long rn = r + rows_per_pass * U;
+            nbeg[u] = nend[u] = 0;
+            if (rn < n_rows) { nbeg[u] = rowptr[rn] - base; nend[u] = rowptr[rn + 1] - base; }
             // A row far longer than the rest (the phony final state of an FSM collects every final weight: 9 300 arcs
             // against a mean of 17 at cfg 3) would keep one lane group busy for hundreds of chunks while the grid
             // drains: it goes to the work list of spmv_long_kernel (a whole CTA per row) instead.
@@ -262,7 +272,11 @@ __global__ void spmm_kernel(long long n_rows, const int32_t* __restrict__ rowptr
             if (j0 + jj >= n_cols_b) break;
             T* dst = C + (j0 + jj) * ldc + i;
             if (accumulate) acc[jj].add_value(*dst);
+#ifdef MK_SPMM_STCS
+            __stcs(dst, acc[jj].value());
+#else
             *dst = acc[jj].value();
+#endif
         }
     }
 }

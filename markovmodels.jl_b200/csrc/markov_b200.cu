@@ -18,6 +18,7 @@
 #include <functional>
 #include <limits>
 #include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -1031,6 +1032,30 @@ static int device_sms() {  // (cached per device: the attribute query is not fre
     return sms;
 }
 
+// Scratch for mk_spmv's long-row work list ({count, rows...}): one 256 KB buffer per (device, stream), created on first
+// use and kept for the life of the process — stream order makes reuse by consecutive calls on that stream safe, and
+// distinct streams never share one.  (The stream-ordered allocator was tried first: with the default pool's release
+// threshold of 0 a call occasionally paid a real cudaMalloc, 0.4 -> 5 ms.)
+constexpr int kSpmvWorklistCap = 1 << 16;
+static int* spmv_worklist(cudaStream_t st, int cap) {
+    struct Entry { int dev; cudaStream_t st; int* p; };
+    static std::mutex mu;
+    static std::vector<Entry> entries;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    std::lock_guard<std::mutex> lock(mu);
+    for (const Entry& e : entries)
+        if (e.dev == dev && e.st == st) return e.p;
+    if (entries.size() >= 256) return nullptr;
+    int* p = nullptr;
+    if (cudaMalloc(reinterpret_cast<void**>(&p), size_t(cap + 1) * sizeof(int)) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    entries.push_back({dev, st, p});
+    return p;
+}
+
 template <typename T, int SR>
 static int spmv_launch(int64_t n_rows, int64_t nnz, const int32_t* rowptr, const int32_t* colval, const void* nzval,
                        int base, const void* b, void* c, int sms, cudaStream_t st) {
@@ -1043,16 +1068,9 @@ static int spmv_launch(int64_t n_rows, int64_t nnz, const int32_t* rowptr, const
     const T* v = static_cast<const T*>(nzval); const T* bb = static_cast<const T*>(b); T* cc = static_cast<T*>(c);
     // rows more than 16 x longer than a lane group's chunk go to a work list and get a CTA each (stream-ordered scratch)
     const int long_row = lanes * 4 * 16;
-    const int cap = int(std::min<int64_t>(n_rows, 1 << 16));
-    int* wl = nullptr;
-    if (nnz > long_row) {
-        if (cudaMallocAsync(reinterpret_cast<void**>(&wl), size_t(cap + 1) * sizeof(int), st) != cudaSuccess) {
-            cudaGetLastError();
-            wl = nullptr;  // (no scratch: the long rows are done in place, slowly but correctly)
-        } else {
-            CK(cudaMemsetAsync(wl, 0, sizeof(int), st));
-        }
-    }
+    const int cap = int(std::min<int64_t>(n_rows, kSpmvWorklistCap));
+    int* wl = nnz > long_row ? spmv_worklist(st, kSpmvWorklistCap) : nullptr;  // (none: the long rows are done in place)
+    if (wl) CK(cudaMemsetAsync(wl, 0, sizeof(int), st));
     if (lanes == 4) spmv_kernel<T, SR, 4, 2><<<blocks, threads, 0, st>>>(n_rows, rowptr, colval, v, base, bb, cc, long_row, wl, cap);
     else if (lanes == 8) spmv_kernel<T, SR, 8, 4><<<blocks, threads, 0, st>>>(n_rows, rowptr, colval, v, base, bb, cc, long_row, wl, cap);
     else spmv_kernel<T, SR, 32, 4><<<blocks, threads, 0, st>>>(n_rows, rowptr, colval, v, base, bb, cc, long_row, wl, cap);
@@ -1062,7 +1080,6 @@ static int spmv_launch(int64_t n_rows, int64_t nnz, const int32_t* rowptr, const
         spmv_long_kernel<T, SR><<<sms, 256, 0, st>>>(wl, cap, rowptr, colval, v, base, bb, cc);
         CK(cudaGetLastError());
         ++g_launches;
-        CK(cudaFreeAsync(wl, st));
     }
     return MK_OK;
 }
@@ -1070,7 +1087,10 @@ static int spmv_launch(int64_t n_rows, int64_t nnz, const int32_t* rowptr, const
 template <typename T, int SR>
 static int spmm_launch(int64_t n_rows, const int32_t* rowptr, const int32_t* colval, const void* nzval, int base,
                        const void* B, int64_t ldb, void* C, int64_t ldc, int64_t cols, int accumulate, cudaStream_t st) {
-    constexpr int CJ = 8;  // columns per thread (16 measured slower: 1.60 vs 1.24 ms on Ĉ·V̂ at cfg 3)
+#ifndef MK_SPMM_CJ
+#define MK_SPMM_CJ 8
+#endif
+    constexpr int CJ = MK_SPMM_CJ;  // columns per thread (tools/ab_variants.py; Ĉ·V̂ at cfg 3)
     dim3 grid(unsigned((n_rows + 255) / 256), unsigned(std::min<int64_t>((cols + CJ - 1) / CJ, 65535)));
     spmm_kernel<T, SR, CJ><<<grid, 256, 0, st>>>(n_rows, rowptr, colval, static_cast<const T*>(nzval), base,
                                                  static_cast<const T*>(B), ldb, static_cast<T*>(C), ldc, cols, accumulate);
