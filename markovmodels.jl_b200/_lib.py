@@ -50,7 +50,7 @@ def build(force=False, verbose=False):
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "markov_b200.cu")]
-    for knob in ("MK_PASS_QUADS", "MK_THREADS", "MK_PROFILE_BARRIER", "MK_ABLATE", "MK_SPMM_CJ", "MK_SPMM_STCS"):  # kernel tuning knobs (defaults in kernels.cuh)
+    for knob in ("MK_PASS_QUADS", "MK_THREADS", "MK_PROFILE_BARRIER", "MK_ABLATE", "MK_SPMM_CJ", "MK_SPMM_STCS", "MK_L2_HINTS"):  # kernel tuning knobs (defaults in kernels.cuh)
         if os.environ.get(knob):
             cmd.insert(1, f"-D{knob}={os.environ[knob]}")
     if verbose:

@@ -153,6 +153,39 @@ __device__ __forceinline__ void st4_cg(double* p, const V4<double>& x) {
     __stcg(reinterpret_cast<double2*>(p) + 1, make_double2(x.v[2], x.v[3]));
 }
 
+// Stores of the backward ping-pong vectors (b ⊗ e' and its linear copies): rewritten two frames later and gathered in
+// between, they should never leave L2 — but the 2.3 GB α stream of the same sweep pushes their dirty lines out
+// (2.5 GB of write-backs per call against 0.23 GB of posteriors).  L2::evict_last keeps more of them resident, and
+// L2::evict_first on the forward sweep's α-store writes (below) leaves less of that stream in L2 when the backward
+// sweep starts: DRAM traffic per call 7.93 -> 6.64 GB, backward write-backs 2.57 -> 1.38 GB, kernel pair -0.5 %
+// (tools/ab_variants.py on one box: 7.468 / 7.441 / 7.433 ms for MK_L2_HINTS = 0 / 1 / 2; evict_first on the emission
+// and α reads as well — tried as level 3 — brought the reads UP by 0.2 GB and was dropped).  The policy operands are
+// the encodings `createpolicy.fractional.L2::evict_{last,first}.b64 p, 1.0` produces (as in CUTLASS' CacheHintSm90).
+#ifndef MK_L2_HINTS
+#define MK_L2_HINTS 2
+#endif
+#if MK_L2_HINTS >= 1
+__device__ __forceinline__ void st4_keep(float* p, const V4<float>& x) {
+    asm volatile("st.global.cg.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(x.v[0]), "f"(x.v[1]),
+                 "f"(x.v[2]), "f"(x.v[3]), "l"(0x14F0000000000000ull)  // createpolicy.fractional.L2::evict_last, 1.0
+                 : "memory");
+}
+__device__ __forceinline__ void st4_keep(double* p, const V4<double>& x) { st4_cg(p, x); }
+#else
+template <typename T> __device__ __forceinline__ void st4_keep(T* p, const V4<T>& x) { st4_cg(p, x); }
+#endif
+// The α store on the forward sweep: written once, read back milliseconds later — first in line for eviction.
+#if MK_L2_HINTS >= 2
+__device__ __forceinline__ void st4_stream(float* p, const V4<float>& x) {
+    asm volatile("st.global.cg.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(x.v[0]), "f"(x.v[1]),
+                 "f"(x.v[2]), "f"(x.v[3]), "l"(0x12F0000000000000ull)  // createpolicy.fractional.L2::evict_first, 1.0
+                 : "memory");
+}
+__device__ __forceinline__ void st4_stream(double* p, const V4<double>& x) { st4_cg(p, x); }
+#else
+template <typename T> __device__ __forceinline__ void st4_stream(T* p, const V4<T>& x) { st4_cg(p, x); }
+#endif
+
 // posterior accumulation into the (B, D, N) output: Log -> add, Tropical -> max
 __device__ __forceinline__ void red_add4(float* p, const V4<float>& x) {
 #ifdef MK_ABLATE
@@ -783,7 +816,8 @@ template <typename T, int SR> struct FwdFin {
         if (MK_ABL(p, 128) && all_zero_bar(val) && !(it.w & 1)) return;
 #pragma unroll
         for (int j = 0; j < 4; ++j) mx[j] = max_(mx[j], val.v[j]);
-        st4_cg(cur_l + size_t(unsigned(it.x)) * 4, val);
+        if (SR == SR_LOG) st4_stream(cur_l + size_t(unsigned(it.x)) * 4, val);  // (Tropical gathers from the store itself)
+        else st4_cg(cur_l + size_t(unsigned(it.x)) * 4, val);
         if (SR == SR_LOG) {
             V4<T> lin;
 #pragma unroll
@@ -882,12 +916,12 @@ template <typename T, int SR> struct BwdFin {
                 beta.v[j] += e.v[j] + cm[j];
                 mx[j] = max_(mx[j], beta.v[j]);
             }
-            st4_cg(bt_l + size_t(unsigned(it.x)) * 4, beta);
+            st4_keep(bt_l + size_t(unsigned(it.x)) * 4, beta);
             if (SR == SR_LOG) {
                 V4<T> lin;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) lin.v[j] = ex2_(beta.v[j] + p.bwd.H);
-                st4_cg(lin_l + size_t(unsigned(it.x)) * 4, lin);
+                st4_keep(lin_l + size_t(unsigned(it.x)) * 4, lin);
             }
         }
     }
