@@ -34,8 +34,8 @@ UNIT = "frames/s"
 B_PER_GPU, T_FRAMES, N_PDF, N_TOKENS, SEED = 128, 150, 3000, 15000, 303
 HBM_FALLBACK_GBS = 6650.0
 # dram__bytes_read.sum + dram__bytes_write.sum of the two shared_fb_kernel launches of ONE pdfposteriors call on
-# this workload, from the `ncu --set full` capture summarised in profiles/r01_shared_fb_kernel_ncu.md
-# (forward 0.219 + 2.290 GB, backward 2.760 + 2.480 GB); null for any other shape
+# this workload, from the ncu counters summarised in profiles/r01_shared_fb_kernel_ncu.md (end-of-round build with
+# the L2 eviction hints: forward 0.220 + 2.289 GB, backward 2.756 + 1.376 GB); null for any other shape
 NCU_DRAM_BYTES_PER_LAUNCH = 6.641e9
 
 
