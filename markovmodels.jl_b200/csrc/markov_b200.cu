@@ -545,6 +545,9 @@ struct Group {  // utterances sharing one graph, run by shared_fb_kernel
     long long* d_utt_off = nullptr;
     DevBuf E, emax, emax_key, alpha, bt, flin, blin, part, gkey, coff, lz2, carry, tile_n1;
     std::vector<int> h_tile_n1;  // ragged batches: frames each utterance tile needs (staging for tile_n1)
+    std::vector<int> h_order;    // group lane u -> utterance b of the current call (utts, or its length-sorted quads)
+    std::vector<int> h_utt_b;    // staging for d_utt_b when the order changes
+    bool permuted = false;       // d_utt_b currently holds a sorted order
 };
 
 struct mk_batch {
@@ -620,6 +623,11 @@ static bool ragged_cut_enabled() {
     return !(e && e[0] == '0');
 }
 
+static bool ragged_sort_enabled() {
+    const char* e = getenv("MK_RAGGED_SORT");
+    return !(e && e[0] == '0');
+}
+
 struct CallArgs {
     const void* ll; int64_t sb, sd, sn, D, T; int expanded; const int32_t* seqlens;
     void* out0;  // A / B / post / path
@@ -652,6 +660,33 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     TRY(gr.lz2.ensure(size_t(U4) * sizeof(double)));
     TRY(gr.coff.ensure(2 * size_t(N1) * U4 * sizeof(double)));
     TRY(gr.carry.ensure(size_t(U4) * (sizeof(double) + sizeof(T))));
+
+    // Utterance order of this call.  Ragged posteriors over several utterance tiles: the group's lane quads (4 consecutive
+    // utterances: the unit of the 16-byte posterior reductions) are sorted by length, longest first, so that the per-tile
+    // frame limits below bite whatever order the caller's batch has.  Everything downstream goes through d_utt_b (the
+    // emission transform, lz / zsum / the posterior scatter), so results land at the caller's utterance indices.
+    const bool want_cut = mode == MODE_POST && c.seqlens && !c.expanded && ragged_cut_enabled();
+    gr.h_order = gr.utts;
+    bool permute = false;
+    if (want_cut && U4 > kTileUtts && gr.utts.size() % 4 == 0 && ragged_sort_enabled()) {
+        const int nq = int(gr.utts.size() / 4);
+        std::vector<int> q(nq), key(nq, 0);
+        for (int i = 0; i < nq; ++i) {
+            q[i] = i;
+            for (int j = 0; j < 4; ++j) key[i] = std::max(key[i], int(c.seqlens[gr.utts[4 * i + j]]));
+        }
+        std::stable_sort(q.begin(), q.end(), [&](int a, int b) { return key[a] > key[b]; });
+        for (int i = 0; i < nq && !permute; ++i) permute = q[i] != i;
+        if (permute)
+            for (int i = 0; i < nq; ++i)
+                for (int j = 0; j < 4; ++j) gr.h_order[4 * i + j] = gr.utts[4 * q[i] + j];
+    }
+    if (permute || gr.permuted) {
+        gr.h_utt_b.assign(U4, -1);
+        std::copy(gr.h_order.begin(), gr.h_order.end(), gr.h_utt_b.begin());
+        CK(cudaMemcpyAsync(gr.d_utt_b, gr.h_utt_b.data(), size_t(U4) * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+        gr.permuted = permute;
+    }
 
     // frame segments of this call (one, unless the host pipeline cut it)
     std::vector<int> fb = seg ? seg->f : std::vector<int>{0, N1};
@@ -723,20 +758,21 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     p.do_fwd = p.do_bwd = p.do_post = 0;
     p.bwd_dead_ok = c.expanded ? 0 : 1;
     // Ragged batch: an utterance tile (128 consecutive utterances of the group) whose longest
-    // sequence has L < T frames runs frames 0..L only.  Callers that sort their batches by length get the full benefit;
-    // any order is correct.  MK_RAGGED_CUT=0 disables it (the tests compare both).
+    // sequence has L < T frames runs frames 0..L only.  The lane quads were sorted by length above
+    // (MK_RAGGED_SORT=0 keeps the caller's order); any order is correct.  MK_RAGGED_CUT=0 disables the limits (the tests
+    // compare both).
     p.tile_n1 = nullptr;
     p.seqlens = d_seqlens;
-    if (mode == MODE_POST && c.seqlens && !c.expanded && ragged_cut_enabled()) {
+    if (want_cut) {
         gr.h_tile_n1.assign(p.ntiles, 2);
         bool cut = false;
         for (int t = 0; t < p.ntiles; ++t) {
             int lim = 2;
-            const size_t k1 = std::min(gr.utts.size(), size_t(t + 1) * kTileUtts);
-            for (size_t k = size_t(t) * kTileUtts; k < k1; ++k) lim = std::max(lim, c.seqlens[gr.utts[k]] + 1);
+            const size_t k1 = std::min(gr.h_order.size(), size_t(t + 1) * kTileUtts);
+            for (size_t k = size_t(t) * kTileUtts; k < k1; ++k) lim = std::max(lim, c.seqlens[gr.h_order[k]] + 1);
             gr.h_tile_n1[t] = lim = std::min(lim, N1);
             cut = cut || lim < N1;
-            for (size_t k = size_t(t) * kTileUtts; k < k1; ++k) bt->h_zlimit[gr.utts[k]] = lim;
+            for (size_t k = size_t(t) * kTileUtts; k < k1; ++k) bt->h_zlimit[gr.h_order[k]] = lim;
         }
         if (cut) {
             TRY(gr.tile_n1.ensure(p.ntiles * sizeof(int)));
