@@ -248,3 +248,39 @@ def test_operator_entry_points_reject_bad_arguments_without_a_gpu(mm):
     if l.mk_device_count() == 0:
         assert l.mk_spmv(0, 0, 2, 3, 0, rp, None, None, 1, None, 3, None, 2, None) == 1000  # no CPU fallback
         assert b"no CPU fallback" in l.mk_last_error()
+
+
+def test_csr_constructor_host_logic(mm):
+    """``CuSparseMatrixCSR(K, I, J, V, m, n)`` = ``CuSparseMatrixCSR(sparse(I, J, V, m, n))``: rows sorted, columns ascending
+    inside a row, 1-based Cint rowPtr / colVal exactly as CUDA.jl stores them, duplicates combined with the semiring's ⊕
+    (Julia's `sparse` combines with +, i.e. ⊕ of the element type).  Host-side logic only (CPU tensors)."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(3)
+    m, n, nnz = 40, 23, 300
+    I = rng.integers(1, m + 1, nnz)  # noqa: E741
+    J = rng.integers(1, n + 1, nnz)
+    V = rng.random(nnz) + 0.5
+    for fam, comb in ((mm.ProbSemiring, np.add), (mm.LogSemiring, np.logaddexp), (mm.TropicalSemiring, np.maximum)):
+        K = fam[np.float64]
+        A = mm.CuSparseMatrixCSR(K, I, J, V, m, n, device="cpu")
+        rowptr, colval, nzval = A.rowPtr.numpy(), A.colVal.numpy(), A.nzVal.numpy()
+        assert rowptr.dtype == np.int32 and colval.dtype == np.int32 and rowptr[0] == 1 and rowptr[-1] == A.nnz + 1
+        dense = np.full((m, n), np.nan)
+        for i, j, v in zip(I - 1, J - 1, V):
+            dense[i, j] = v if np.isnan(dense[i, j]) else comb(dense[i, j], v)
+        got = np.full((m, n), np.nan)
+        for r in range(m):
+            cols = colval[rowptr[r] - 1:rowptr[r + 1] - 1]
+            assert (np.diff(cols) > 0).all()  # ascending, no duplicates left
+            got[r, cols - 1] = nzval[rowptr[r] - 1:rowptr[r + 1] - 1]
+        np.testing.assert_allclose(got, dense, rtol=1e-14, equal_nan=True)
+        if fam is mm.ProbSemiring:  # + is what scipy's COO -> CSR does too
+            ref = sp.coo_matrix((V, (I - 1, J - 1)), shape=(m, n)).tocsr()
+            ref.sort_indices()
+            np.testing.assert_array_equal(rowptr - 1, ref.indptr)
+            np.testing.assert_array_equal(colval - 1, ref.indices)
+            np.testing.assert_allclose(nzval, ref.data, rtol=1e-14)
+    E = mm.CuSparseMatrixCSR(mm.LogSemiring[np.float32], [], [], [], 3, 2, device="cpu")
+    np.testing.assert_array_equal(E.rowPtr.numpy(), [1, 1, 1, 1])
+    with pytest.raises(IndexError):
+        mm.CuSparseMatrixCSR(mm.LogSemiring[np.float32], [4], [1], [0.0], 3, 2, device="cpu")
