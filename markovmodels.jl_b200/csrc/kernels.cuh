@@ -1366,19 +1366,32 @@ template <typename T, int SR> __global__ void __launch_bounds__(1024, 1) small_f
     const long long a_sn = p.alpha_user ? p.alpha_sn : S;
     double* Ca = p.Ca + u.c_off;
     double C = 0.0;  // every thread tracks the same running offset
+    // A thread's first state (usually its only one: numerator graphs have a few hundred states) keeps its pdf and arc
+    // range in registers, and its emission — one dependent DRAM read per frame, the longest latency of the frame — is
+    // requested one frame ahead so that it is in flight while the current frame is computed.
+    const int s0 = threadIdx.x;
+    const bool has0 = s0 < S;
+    const int pdf0 = has0 ? u.pdf[s0] : 0;
+    const int ib0 = has0 ? u.in_ptr[s0] : 0, ie0 = has0 ? u.in_ptr[s0 + 1] : 0;
+    const int ob0 = has0 ? u.out_ptr[s0] : 0, oe0 = has0 ? u.out_ptr[s0 + 1] : 0;
 
     if (p.do_fwd) {
+        T e_ahead = has0 ? emission<T>(p.ll, p.sb, p.sd, p.sn, p.D, p.expanded, L, b, pdf0, 0) : neg_inf<T>();
         for (int n = 0; n < p.N1; ++n) {
             const T* prev = (n & 1) ? v0 : v1;
             T* cur = (n & 1) ? v1 : v0;
+            const T e0 = e_ahead;
+            if (has0 && n + 1 < p.N1) e_ahead = emission<T>(p.ll, p.sb, p.sd, p.sn, p.D, p.expanded, L, b, pdf0, n + 1);
             const T sh = n > 0 ? shift_from_key<SR, T>(collect_key(s_keys, (n - 1) & 1)) : T(0);
             C += double(sh);
             if (threadIdx.x == 0) Ca[n] = C;
             int key = kKeyMin;
             for (int s = threadIdx.x; s < S; s += blockDim.x) {
-                T e = emission<T>(p.ll, p.sb, p.sd, p.sn, p.D, p.expanded, L, b, u.pdf[s], n);
+                const bool first = s == s0;
+                T e = first ? e0 : emission<T>(p.ll, p.sb, p.sd, p.sn, p.D, p.expanded, L, b, u.pdf[s], n);
                 T acc = (n == 0) ? u.init_dense[s]
-                        : (e == neg_inf<T>()) ? e : small_row<T, SR>(u.in_arcs, u.in_ptr[s], u.in_ptr[s + 1], prev);
+                        : (e == neg_inf<T>()) ? e
+                        : small_row<T, SR>(u.in_arcs, first ? ib0 : u.in_ptr[s], first ? ie0 : u.in_ptr[s + 1], prev);
                 acc = acc + e - sh;
                 cur[s] = acc;
                 key = max(key, fkey(float(acc)));
@@ -1400,9 +1413,16 @@ template <typename T, int SR> __global__ void __launch_bounds__(1024, 1) small_f
 
     T* Bo = p.beta_out ? p.beta_out + u.out_off : nullptr;
     C = 0.0;  // now Cb
+    T e_ahead = has0 ? emission<T>(p.ll, p.sb, p.sd, p.sn, p.D, p.expanded, L, b, pdf0, p.N1 - 1) : neg_inf<T>();
+    T a_ahead = (has0 && p.do_post) ? A[size_t(p.N1 - 1) * a_sn + s0] : T(0);
     for (int n = p.N1 - 1; n >= 0; --n) {
         const T* nxt = (n & 1) ? v0 : v1;  // b_{n+1} ⊗ e_{n+1}
         T* cur = (n & 1) ? v1 : v0;
+        const T e0 = e_ahead, a0 = a_ahead;
+        if (has0 && n > 0) {  // the next frame of the sweep: emission and α row in flight during this one
+            e_ahead = emission<T>(p.ll, p.sb, p.sd, p.sn, p.D, p.expanded, L, b, pdf0, n - 1);
+            if (p.do_post) a_ahead = A[size_t(n - 1) * a_sn + s0];
+        }
         const T sh = n < p.N1 - 1 ? shift_from_key<SR, T>(collect_key(s_keys, (n + 1) & 1)) : T(0);
         C += double(sh);
         T g = T(0);
@@ -1410,15 +1430,16 @@ template <typename T, int SR> __global__ void __launch_bounds__(1024, 1) small_f
         T zs = T(0);
         int key = kKeyMin;
         for (int i = threadIdx.x; i < S; i += blockDim.x) {
-            const int pdf = u.pdf[i];
-            T e = emission<T>(p.ll, p.sb, p.sd, p.sn, p.D, p.expanded, L, b, pdf, n);
+            const bool first = i == s0;
+            const int pdf = first ? pdf0 : u.pdf[i];
+            T e = first ? e0 : emission<T>(p.ll, p.sb, p.sd, p.sn, p.D, p.expanded, L, b, pdf, n);
             const bool dead = !Bo && e == neg_inf<T>();
             T beta = (n == p.N1 - 1) ? T(0)
                      : dead ? neg_inf<T>()
-                            : small_row<T, SR>(u.out_arcs, u.out_ptr[i], u.out_ptr[i + 1], nxt) - sh;
+                            : small_row<T, SR>(u.out_arcs, first ? ob0 : u.out_ptr[i], first ? oe0 : u.out_ptr[i + 1], nxt) - sh;
             if (Bo) Bo[size_t(n) * p.beta_sn + i] = T(double(beta) + C);
             if (p.do_post && !dead) {
-                T pg = exp_(A[size_t(n) * a_sn + i] + beta + g);
+                T pg = exp_((first ? a0 : A[size_t(n) * a_sn + i]) + beta + g);
                 zs = lin_add<SR>(zs, pg);
                 if (n < p.Tn && pdf < p.D && pg > T(0)) red1<SR>(p.post + (size_t(n) * p.D + pdf) * p.B + b, pg);
             }
