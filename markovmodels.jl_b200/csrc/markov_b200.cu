@@ -1095,20 +1095,23 @@ static int* spmv_worklist(cudaStream_t st, int cap) {
 template <typename T, int SR>
 static int spmv_launch(int64_t n_rows, int64_t nnz, const int32_t* rowptr, const int32_t* colval, const void* nzval,
                        int base, const void* b, void* c, int sms, cudaStream_t st) {
-    // lanes per row from the mean row length (rows of the path's graphs: ~17 arcs; Ĉ: 1; ω as a 1-row matrix: all)
+    // lanes per row and arcs per lane and chunk from the mean row length: Ĉ-like matrices (1 arc per row) 4 x 2; the
+    // path's graphs (~17 arcs per row) 4 x 8 — 8 rows per warp with up to 32 arcs each in flight (8 lanes x 4 arcs
+    // measured 0.37 ms against 0.30 ms on the block-diagonal T̂ᵀ of cfg 3); dense-ish rows (ω as a 1-row matrix) a warp.
     const double mean = double(nnz) / double(std::max<int64_t>(n_rows, 1));
-    const int lanes = mean <= 6 ? 4 : (mean <= 24 ? 8 : 32);
+    const int lanes = mean <= 24 ? 4 : 32;
+    const int per_lane = mean <= 6 ? 2 : (mean <= 24 ? 8 : 4);
     const int threads = 256;
     const int64_t want = (n_rows * lanes + threads - 1) / threads;
     const int blocks = int(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(sms) * 32)));  // grid-stride beyond
     const T* v = static_cast<const T*>(nzval); const T* bb = static_cast<const T*>(b); T* cc = static_cast<T*>(c);
     // rows more than 16 x longer than a lane group's chunk go to a work list and get a CTA each (stream-ordered scratch)
-    const int long_row = lanes * 4 * 16;
+    const int long_row = lanes * per_lane * 16;
     const int cap = int(std::min<int64_t>(n_rows, kSpmvWorklistCap));
     int* wl = nnz > long_row ? spmv_worklist(st, kSpmvWorklistCap) : nullptr;  // (none: the long rows are done in place)
     if (wl) CK(cudaMemsetAsync(wl, 0, sizeof(int), st));
-    if (lanes == 4) spmv_kernel<T, SR, 4, 2><<<blocks, threads, 0, st>>>(n_rows, rowptr, colval, v, base, bb, cc, long_row, wl, cap);
-    else if (lanes == 8) spmv_kernel<T, SR, 8, 4><<<blocks, threads, 0, st>>>(n_rows, rowptr, colval, v, base, bb, cc, long_row, wl, cap);
+    if (lanes == 4 && per_lane == 2) spmv_kernel<T, SR, 4, 2><<<blocks, threads, 0, st>>>(n_rows, rowptr, colval, v, base, bb, cc, long_row, wl, cap);
+    else if (lanes == 4) spmv_kernel<T, SR, 4, 8><<<blocks, threads, 0, st>>>(n_rows, rowptr, colval, v, base, bb, cc, long_row, wl, cap);
     else spmv_kernel<T, SR, 32, 4><<<blocks, threads, 0, st>>>(n_rows, rowptr, colval, v, base, bb, cc, long_row, wl, cap);
     CK(cudaGetLastError());
     ++g_launches;
