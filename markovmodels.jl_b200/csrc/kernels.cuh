@@ -687,7 +687,8 @@ template <typename T> struct SharedParams {
     // its running per-utterance scalars through `carry_C` ([U4] float64) and `carry_shift` ([U4]).
     int n_lo, n_hi;
     double* carry_C; T* carry_shift;
-    int ablate;        // debug builds (MK_ABLATE): 1 no gathers, 2 no finalise, 4 no chunk work, 8 no emission/α loads, 16 no stores
+    int ablate;        // debug builds (MK_ABLATE): 1 no gathers, 2 no finalise, 4 no chunk work, 8 no emission/α loads, 16 no stores,
+                       // 64 no exact path (every all-zero sum taken at face value)
     int bwd_dead_ok;   // the library applied `expand`: co-unreachable rows have β = 0̄ before the last frame
     // Ragged batches (the intent of the reference's PartialVector drafts, src/inference.jl:76-90,112-127): frames an
     // utterance tile needs, [ntiles] device ints in [2, N1] or null (= N1 everywhere).  Past its sequence length an
@@ -813,7 +814,6 @@ template <typename T, int SR> struct FwdFin {
     }
     // val: the row's normalised a_n (log2 / tropical)
     __device__ __forceinline__ void store(V4<T>& val) {
-        if (MK_ABL(p, 128) && all_zero_bar(val) && !(it.w & 1)) return;
 #pragma unroll
         for (int j = 0; j < 4; ++j) mx[j] = max_(mx[j], val.v[j]);
         if (SR == SR_LOG) st4_stream(cur_l + size_t(unsigned(it.x)) * 4, val);  // (Tropical gathers from the store itself)
@@ -895,8 +895,6 @@ template <typename T, int SR> struct BwdFin {
                 zs[j] = lin_add<SR>(zs[j], pg.v[j]);
             }
             const int pdf = it.z;
-            if (MK_ABL(p, 256) && pg.v[0] == T(0) && pg.v[1] == T(0) && pg.v[2] == T(0) && pg.v[3] == T(0)) {
-            } else
             if (post_on && pdf < p.D) {
                 T* dst = post_l + size_t(pdf) * p.B;
                 if (p.post_vec4 && SR == SR_LOG) {
