@@ -926,7 +926,9 @@ template <typename T, int SR> struct BwdFin {
     __device__ __forceinline__ void operator()(int item, const V4<T>& acc) {
         // an explicit β output needs β_n even where e_n = 0̄ kills α_n and b_n ⊗ e_n
         // item.w bit3: the phony final state is unreachable from this row — β = 0̄ (under `expand` emissions)
-        V4<T> beta = resolve_sum<T, SR>(acc, e, p.beta_out != nullptr, ((it.w & 8) && p.bwd_dead_ok) || (it.w & 16) || MK_ABL(p, 64),
+        // (the owner of a merged run resolves the ⊕ for the rows tied to it as well: their pdfs, hence their emissions,
+        // differ from the owner's — its own 0̄ emission must not leave an underflowed sum unresolved for them)
+        V4<T> beta = resolve_sum<T, SR>(acc, e, p.beta_out != nullptr || (it.w & 2), ((it.w & 8) && p.bwd_dead_ok) || (it.w & 16) || MK_ABL(p, 64),
                                         it.w, p.bwd, item, bt_next, p.U4, uoff);  // (:106-107)
 #pragma unroll
         for (int j = 0; j < 4; ++j) beta.v[j] += c[j];
@@ -1530,9 +1532,9 @@ __global__ void lfmmi_grad_kernel(const T* num, const T* den, int B, int D, int 
 template <typename T>
 __global__ void unpack_states_kernel(const T* src, int S, int S_src /* rows per source frame */, int U4, const int* utt_b,
                                      const long long* utt_off, const double* C /* [N1][U4] */, double unit, T* dst,
-                                     long long total) {
+                                     long long total, int n0) {
     __shared__ T tile[32][33];
-    const int n = blockIdx.z, s0 = blockIdx.x * 32, u0 = blockIdx.y * 32;
+    const int n = n0 + blockIdx.z, s0 = blockIdx.x * 32, u0 = blockIdx.y * 32;
     for (int k = threadIdx.y; k < 32; k += 8) {
         int s = s0 + k, u = u0 + threadIdx.x;
         if (s < S && u < U4) tile[k][threadIdx.x] = src[(size_t(n) * S_src + s) * U4 + u];

@@ -443,12 +443,13 @@ static int build_graph(mk_graph* g, const int64_t* colptr, const int64_t* rowval
         }
     }
     // item flags (kernels.cuh): forward  bit0 = run member, bit1 = first, bit2 = last, bits 8.. = run index;
-    //                           backward bit0 = reuse the previous item's ⊕;  both: bit3 = dead row, bit4 = no arcs
+    //                           backward bit0 = reuse the previous item's ⊕, bit1 = owner of a run (its ⊕ is reused);
+    //                           both: bit3 = dead row, bit4 = no arcs
     std::vector<int> gf_fwd(S, 0), gf_bwd(S, 0);
     for (int s = 0; s < S; ++s)
         if (grp[s] >= 0) {
             gf_fwd[s] = 1 | (tied[s] ? 0 : 2) | (run_last[s] ? 4 : 0) | (grp[s] << 8);
-            gf_bwd[s] = tied[s] ? 1 : 0;
+            gf_bwd[s] = tied[s] ? 1 : 2;  // bit1: this row's ⊕ is shared by the rows tied to it
         }
     for (int s = 0; s < S; ++s) {
         if (!fwd_live[s]) gf_fwd[s] |= kItemDead;
@@ -564,6 +565,12 @@ struct mk_batch {
     std::vector<int> h_zlimit;  // ragged batches: frames evaluated per utterance (staging for zlimit)
     bool ragged_cut = false;    // the current call stops at least one utterance tile early
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+    // One in-flight call per batch: the workspaces are shared by every entry point.  Each call records `ev_last` on
+    // its stream when it has enqueued its work; a following call on ANOTHER stream (the *_host entry points run on
+    // own_stream, device calls on the caller's) waits for it before touching the workspaces.
+    cudaEvent_t ev_last = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool has_last = false;
     static constexpr int kMaxSegments = 16;
     cudaEvent_t ev_h2d[kMaxSegments] = {}, ev_done[kMaxSegments] = {};
     size_t max_smem_optin = 0;
@@ -584,6 +591,7 @@ struct mk_batch {
         for (DevBuf* d : all) d->release();
         if (own_stream) cudaStreamDestroy(own_stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (ev_last) cudaEventDestroy(ev_last);
         for (int i = 0; i < kMaxSegments; ++i) {
             if (ev_h2d[i]) cudaEventDestroy(ev_h2d[i]);
             if (ev_done[i]) cudaEventDestroy(ev_done[i]);
@@ -707,10 +715,13 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
         int* keys = static_cast<int*>(gr.emax_key.p) + size_t(n0) * U4;
         // keys start below every finite value (0x80808080 decodes to -3.4e38)
         if (SR == SR_LOG) CK(cudaMemsetAsync(keys, 0x80, size_t(nf) * U4 * sizeof(int), c.stream));
-        dim3 eg((Dh + 31) / 32, (U4 + 31) / 32, nf), eb(32, 8);
-        expand_transpose_kernel<T><<<eg, eb, 0, c.stream>>>(e);
-        CK(cudaGetLastError());
-        ++g_launches;
+        for (int z0 = 0; z0 < nf; z0 += 65535) {  // (gridDim.z is limited to 65535 frames per launch)
+            e.n0 = n0 + z0;
+            dim3 eg((Dh + 31) / 32, (U4 + 31) / 32, std::min(nf - z0, 65535)), eb(32, 8);
+            expand_transpose_kernel<T><<<eg, eb, 0, c.stream>>>(e);
+            CK(cudaGetLastError());
+            ++g_launches;
+        }
         T* emax = static_cast<T*>(gr.emax.p) + size_t(n0) * U4;
         if (SR == SR_LOG) {
             const int count = nf * U4;
@@ -796,6 +807,10 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     }
     void* args[] = {&p};
     const size_t scal = shared_scalars_bytes(U4, sizeof(T));
+    if (scal + 16 * 1024 > bt->max_smem_optin)
+        return fail(MK_ENOTSUP, "%d utterances share one graph: the per-utterance scalars (%zu bytes of shared memory) "
+                                "leave no room for the kernel's working set; split the batch into several mk_batch objects",
+                    U4, scal);
     const int slot = bt->prof_n % mk_batch::kProfRing;
     if (bt->profile) CK(cudaEventRecord(bt->ev0[slot], c.stream));
     for (int phase = 0; phase < 2; ++phase) {
@@ -845,14 +860,16 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     if (bt->profile) { CK(cudaEventRecord(bt->ev1[slot], c.stream)); ++bt->prof_n; }
 
     if (mode == MODE_ALPHA || mode == MODE_BETA) {
-        dim3 ug((S + 31) / 32, (U4 + 31) / 32, N1), ub(32, 8);
         const double* C = static_cast<const double*>(gr.coff.p) + (mode == MODE_BETA ? size_t(N1) * U4 : 0);
-        unpack_states_kernel<T><<<ug, ub, 0, c.stream>>>(static_cast<const T*>(gr.alpha.p), S,
-                                                        (mode == MODE_BETA || SR == SR_LOG) ? S : Sq, U4, gr.d_utt_b,
-                                                        gr.d_utt_off, C, SR == SR_LOG ? 0.6931471805599453 : 1.0,
-                                                        static_cast<T*>(c.out0), bt->total);
-        CK(cudaGetLastError());
-        ++g_launches;
+        for (int z0 = 0; z0 < N1; z0 += 65535) {  // (gridDim.z is limited to 65535 frames per launch)
+            dim3 ug((S + 31) / 32, (U4 + 31) / 32, std::min(N1 - z0, 65535)), ub(32, 8);
+            unpack_states_kernel<T><<<ug, ub, 0, c.stream>>>(static_cast<const T*>(gr.alpha.p), S,
+                                                            (mode == MODE_BETA || SR == SR_LOG) ? S : Sq, U4, gr.d_utt_b,
+                                                            gr.d_utt_off, C, SR == SR_LOG ? 0.6931471805599453 : 1.0,
+                                                            static_cast<T*>(c.out0), bt->total, z0);
+            CK(cudaGetLastError());
+            ++g_launches;
+        }
     }
     return MK_OK;
 }
@@ -1028,9 +1045,25 @@ static int dispatch(mk_batch* bt, Mode mode, const CallArgs& c) {
     if (mode == MODE_BEST && bt->semiring != MK_TROPICAL)
         return fail(MK_EINVAL, "bestpath needs TropicalSemiring graphs");
     if (mode == MODE_BEST && c.expanded) return fail(MK_EINVAL, "bestpath takes un-expanded emissions");
+    {   // order this call after the previous one on the same batch if that one ran on another stream
+        DeviceGuard guard(bt->device);
+        if (!guard.ok) return fail(MK_ECUDA, "cannot select CUDA device %d", bt->device);
+        if (!bt->ev_last) CK(cudaEventCreateWithFlags(&bt->ev_last, cudaEventDisableTiming));
+        if (bt->has_last && bt->last_stream != c.stream) CK(cudaStreamWaitEvent(c.stream, bt->ev_last, 0));
+    }
+    int rc;
     if (bt->dtype == MK_F32)
-        return bt->semiring == MK_LOG ? run<float, SR_LOG>(bt, mode, c) : run<float, SR_TROP>(bt, mode, c);
-    return bt->semiring == MK_LOG ? run<double, SR_LOG>(bt, mode, c) : run<double, SR_TROP>(bt, mode, c);
+        rc = bt->semiring == MK_LOG ? run<float, SR_LOG>(bt, mode, c) : run<float, SR_TROP>(bt, mode, c);
+    else
+        rc = bt->semiring == MK_LOG ? run<double, SR_LOG>(bt, mode, c) : run<double, SR_TROP>(bt, mode, c);
+    {   // (also after a failed call: whatever it enqueued before failing still uses the workspaces)
+        DeviceGuard guard(bt->device);
+        if (guard.ok && cudaEventRecord(bt->ev_last, c.stream) == cudaSuccess) {
+            bt->last_stream = c.stream;
+            bt->has_last = true;
+        }
+    }
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -118,8 +118,12 @@ class FSM:
     def astype(self, K):
         """The same graph with another semiring type / payload precision (``convert`` in the
         reference's tests, test/test_algorithms.jl:277)."""
+        parts = None
+        if self.parts is not None:  # a rawunion stays batchable: convert every operand once (identical operands stay identical)
+            done = {}
+            parts = [done.setdefault(id(p), p.astype(K)) for p in self.parts]
         return FSM(K, self.nstates_hat, self.init_idx, self.init_w.astype(K.dtype), self.colptr, self.rowval,
-                   self.nzval.astype(K.dtype), self.labels)
+                   self.nzval.astype(K.dtype), self.labels, parts=parts)
 
     # ---- views (src/fsm.jl:30-40) --------------------------------------------------------------
     @property

@@ -75,6 +75,8 @@ def statemap(fsm, numpdf, pdfids=None):
 
 
 def _as_statemap(fsm, Ĉ):
+    """Ĉ as a state→pdf map.  A dense Ĉ holds the payloads of ``K``: its stored entries are the ones that differ
+    from ``zero(K)`` (-Inf for Log / Tropical, 0 for Prob)."""
     if isinstance(Ĉ, StateMap):
         return Ĉ
     if hasattr(Ĉ, "tocsr"):  # scipy sparse with stored 1̄ entries
@@ -85,7 +87,7 @@ def _as_statemap(fsm, Ĉ):
     Ĉ = np.asarray(Ĉ)
     if Ĉ.ndim == 1:
         return StateMap(Ĉ, int(Ĉ[-1]))
-    fin = np.isfinite(Ĉ)
+    fin = Ĉ != fsm.K.zero
     if not np.all(fin.sum(axis=1) == 1):
         raise _lib.MarkovError(_lib.MK_ENOTSUP, "Ĉ must have exactly one 1̄ per row")
     return StateMap(fin.argmax(axis=1), Ĉ.shape[1] - 1)
@@ -210,20 +212,22 @@ def _as_batch(x, Ĉs, B):
 # ---------------------------------------------------------------------------------------------
 def expand(V, seqlength=None, K=None):
     """``expand`` (src/inference.jl:54-60): D x N payload matrix -> (D+1) x (N+1) with the phony
-    pdf row and phony frame column.  Works on numpy arrays and torch tensors."""
+    pdf row and phony frame column, filled with ``zero(K)`` / ``one(K)`` (default: the Log / Tropical
+    payloads -Inf / 0; ``K=ProbSemiring[...]`` gives 0 / 1).  Works on numpy arrays and torch tensors."""
     is_t = type(V).__module__.startswith("torch")
     D, N = V.shape
     L = N if seqlength is None else int(seqlength)
+    zero, one = (-float("inf"), 0.0) if K is None else (float(K.zero), float(K.one))
     if is_t:
         torch = _torch()
-        out = torch.full((D + 1, N + 1), -float("inf"), dtype=V.dtype, device=V.device)
+        out = torch.full((D + 1, N + 1), zero, dtype=V.dtype, device=V.device)
         out[:D, :L] = V[:, :L]
-        out[D, L:] = 0.0
+        out[D, L:] = one
         return out
     V = np.asarray(V)
-    out = np.full((D + 1, N + 1), -np.inf, V.dtype)
+    out = np.full((D + 1, N + 1), zero, V.dtype)
     out[:D, :L] = V[:, :L]
-    out[D, L:] = 0.0
+    out[D, L:] = one
     return out
 
 
@@ -324,6 +328,24 @@ def βrecursion(x, V, Ĉs=None, seqlengths=None):
     return _state_recursion("mk_beta", x, V, Ĉs, seqlengths)
 
 
+def _check_out(buf, shape, dtype, on_device, name):
+    """A caller-supplied output buffer must be exactly what the kernels write: payload dtype, shape, contiguous, on
+    the side (device / host) of the emissions.  Anything else would be a silent out-of-bounds write."""
+    if on_device:
+        if not (type(buf).__module__.startswith("torch") and buf.is_cuda):
+            raise TypeError(f"out: {name} must be a CUDA tensor for device emissions")
+        ok = buf.is_contiguous()
+    else:
+        if not isinstance(buf, np.ndarray):
+            raise TypeError(f"out: {name} must be a numpy array for host emissions")
+        ok = buf.flags.c_contiguous and buf.flags.writeable
+    if buf.dtype != dtype:
+        raise TypeError(f"out: {name} has dtype {buf.dtype}, the semiring's payload type is {dtype}")
+    if tuple(buf.shape) != tuple(shape) or not ok:
+        raise _lib.DimensionMismatch(_lib.MK_EINVAL, f"out: {name} must be a contiguous {tuple(shape)} array, got "
+                                                     f"{tuple(buf.shape)}{'' if ok else ' (not contiguous)'}")
+
+
 def pdfposteriors(x, V, Ĉs=None, seqlengths=None, out=None):
     """``pdfposteriors(fsm, V̂s, Ĉs)`` (src/inference.jl:145-161).
 
@@ -344,7 +366,8 @@ def pdfposteriors(x, V, Ĉs=None, seqlengths=None, out=None):
         torch = _torch()
         if out is not None:
             post, ttl = out
-            assert post.is_cuda and post.is_contiguous() and tuple(post.shape) == (To, Do, b.B)
+            _check_out(post, (To, Do, b.B), _tdtype(b.K), True, "post")
+            _check_out(ttl, (b.B,), _tdtype(b.K), True, "ttl")
         else:
             post = torch.empty((To, Do, b.B), dtype=_tdtype(b.K), device="cuda")
             ttl = torch.empty((b.B,), dtype=_tdtype(b.K), device="cuda")
@@ -353,7 +376,8 @@ def pdfposteriors(x, V, Ĉs=None, seqlengths=None, out=None):
         return post.permute(2, 1, 0), ttl
     if out is not None:
         post, ttl = out
-        assert post.flags.c_contiguous and post.shape == (To, Do, b.B) and post.dtype == b.K.dtype
+        _check_out(post, (To, Do, b.B), b.K.dtype, False, "post")
+        _check_out(ttl, (b.B,), b.K.dtype, False, "ttl")
     else:
         post = np.empty((To, Do, b.B), b.K.dtype)
         ttl = np.empty((b.B,), b.K.dtype)

@@ -17,27 +17,49 @@ Two independent restatements:
 be built with gcc/g++.
 """
 import ctypes as C
+import hashlib
 import os
+import platform
 import subprocess
 
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "oracle.cpp")
-LIB = os.path.join(_HERE, "_build", "liboracle.so")
 _lib = None
 
 
+def _cpu_signature():
+    """The build is -march=native, so the library is tied to the host CPU: the file name carries
+    a hash of the CPU model and its ISA flags, and a box with another CPU compiles its own copy."""
+    model, flags = platform.machine(), ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name") and "@" not in model:
+                model += "@" + line.split(":", 1)[1].strip()
+            elif line.startswith("flags"):
+                flags = " ".join(sorted(line.split(":", 1)[1].split()))
+                break
+    except OSError:
+        pass
+    return hashlib.sha1((model + "|" + flags).encode()).hexdigest()[:12]
+
+
+LIB = os.path.join(_HERE, "_build", f"liboracle_{_cpu_signature()}.so")
+
+
 def build(force=False):
-    """g++ -O2 -fopenmp (no -march=native: the .so travels to a different host; no
-    -ffast-math: -Inf arithmetic must be IEEE)."""
+    """g++ -O3 -march=native -fopenmp for THIS host's CPU; no -ffast-math: -Inf arithmetic
+    must be IEEE (and -O3 -march=native without it keeps the scalar ⊕ order of oracle.cpp)."""
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = ["g++", "-O2", "-fopenmp", "-fno-fast-math", "-std=c++17", "-shared", "-fPIC", "-o", LIB, SRC]
+    cmd = ["g++", "-O3", "-march=native", "-fopenmp", "-fno-fast-math", "-ffp-contract=off", "-std=c++17", "-shared",
+           "-fPIC", "-o", LIB + ".tmp", SRC]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    os.replace(LIB + ".tmp", LIB)  # (atomic: xdist workers / torchrun ranks may build at the same time)
     return LIB
 
 
@@ -71,7 +93,12 @@ def lib():
 
 
 def num_threads():
-    return lib().orc_num_threads()
+    """Host threads the CPU legs use: the cores this process may run on.  NOT omp_get_max_threads():
+    torchrun exports OMP_NUM_THREADS=1, which would silently turn the all-core baseline into a 1-core one."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 class OracleGraph:
@@ -125,7 +152,7 @@ def pdfposteriors(graphs, V_btd, seqlengths=None, threads=0):
     ttl = np.zeros(B, K.dtype)
     rc = lib().orc_pdfposteriors(K.dtype_code, K.code, B, arr, V.ctypes.data, D, T, D,
                                  None if sl is None else sl.ctypes.data, post.ctypes.data, ttl.ctypes.data,
-                                 threads)
+                                 threads if threads > 0 else num_threads())
     if rc:
         raise ValueError("DimensionMismatch in oracle pdfposteriors")
     return post.transpose(2, 1, 0), ttl
@@ -136,7 +163,8 @@ def bestpath(graphs, V_btd, seqlengths=None, threads=0):
     path = np.zeros((B, T), np.int32)
     score = np.zeros(B, K.dtype)
     rc = lib().orc_bestpath(K.dtype_code, B, arr, V.ctypes.data, D, T, D,
-                            None if sl is None else sl.ctypes.data, path.ctypes.data, score.ctypes.data, threads)
+                            None if sl is None else sl.ctypes.data, path.ctypes.data, score.ctypes.data,
+                            threads if threads > 0 else num_threads())
     if rc:
         raise ValueError("DimensionMismatch in oracle bestpath")
     return path, score
