@@ -177,14 +177,20 @@ def run_ours(args):
     Vd = V.permute(0, 2, 1)                                        # (B, D, T) view the API takes
     post = torch.empty((T, D, B), device="cuda")
     ttl = torch.empty((B,), device="cuda")
-    post_bdn = post.permute(2, 1, 0)
     lib = mm.lib()
     last = {}
 
+    # the data-parallel exchange: [Σ logZ, #frames, pdf occupancy[D]] (~24 KB) written by the library itself
+    # (mk_pdfposteriors_stats) and summed over the ranks by its own NCCL binding (mk_allreduce_stats) on the same
+    # stream: no eager reduction, no host synchronisation inside a step
+    stats = torch.zeros(D + 2, dtype=torch.float64, device="cuda")
+    comm = mm.sharding.Communicator(rank, world, local) if world > 1 else None
+
     def step():
-        mm.pdfposteriors(bfsm, Vd, out=(post, ttl))
-        # the data-parallel exchange: one all-reduce of [Σ logZ, #frames, pdf occupancy[D]] (~24 KB)
-        last["stats"] = mm.sharding.allreduce_stats(mm.sharding.local_stats(post_bdn, ttl))
+        mm.pdfposteriors(bfsm, Vd, out=(post, ttl), stats=stats)
+        if comm is not None:
+            comm.allreduce_(stats)
+        last["stats"] = stats
 
     def sync_all():
         torch.cuda.synchronize()

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define MK_ABI_VERSION 1
+#define MK_ABI_VERSION 2
 
 enum mk_status {
     MK_OK = 0,
@@ -119,6 +119,16 @@ int mk_pdfposteriors(mk_batch* b, const void* ll, int64_t stride_b, int64_t stri
                      int64_t stride_n, int64_t D, int64_t T, int expanded,
                      const int32_t* seqlens, void* out_post, void* out_logz, void* stream);
 
+/* pdfposteriors + the statistics a data-parallel training step exchanges (the accumulation the
+ * reference's caller does on the host, examples/test_cuda.jl:140-152).  out_stats: DEVICE float64
+ * [D + 2], overwritten with {Σ_b logZ_b, Σ_b frames of b, occupancy[d] = Σ_{b,n} out_post[b,d,n]};
+ * the occupancy falls out of the normalisation pass over out_post, no extra pass.  NULL = not
+ * wanted (then identical to mk_pdfposteriors). */
+int mk_pdfposteriors_stats(mk_batch* b, const void* ll, int64_t stride_b, int64_t stride_d,
+                           int64_t stride_n, int64_t D, int64_t T, int expanded,
+                           const int32_t* seqlens, void* out_post, void* out_logz,
+                           double* out_stats, void* stream);
+
 /* bestpath   — absent from the 0.10.0 sources (src/MarkovModels.jl:56-57 are commented
  * exports); historical signature test/test_algorithms.jl:279-281.  Tropical graphs only,
  * expanded must be 0.  out_path: int32 [B][T] (utterance-major), 1-based state ids local
@@ -176,6 +186,25 @@ int mk_spmm(int semiring, int dtype, int64_t n_rows, int64_t n_cols, int64_t nnz
 int mk_spvec_bcast(int semiring, int dtype, int op, int64_t n, int64_t nnz, const int32_t* nzind,
                    const void* nzval, int index_base, const void* y, int64_t len_y, void* dest,
                    int64_t len_dest, void* stream);
+
+/* ---- Multi-GPU: the path shards by utterance (block-diagonal batch, src/fsmops.jl:28-36); the only
+ * exchange is ONE sum all-reduce per step of the mk_pdfposteriors_stats vector.  NCCL is
+ * bound at run time (dlopen of MK_NCCL_LIB / libnccl.so.2: the copy a CUDA.jl or PyTorch process already
+ * holds); without it these return MK_ENOTSUP.
+ *   one process per GPU:   rank 0 calls mk_comm_unique_id and hands the 128 bytes to the other ranks (file,
+ *                          MPI, a socket ...); every rank then calls mk_comm_init_rank (device -1 = current).
+ *   one process, n GPUs:   mk_comm_init fills out[0..n_gpus) with one communicator per device 0..n_gpus-1;
+ *                          mk_allreduce_stats_all enqueues the n all-reduces as one NCCL group.
+ * mk_allreduce_stats: in-place float64 sum over the ranks, asynchronous on `stream` of the communicator's
+ * device. */
+typedef struct mk_comm mk_comm;
+int mk_comm_unique_id(void* id128);
+int mk_comm_init_rank(mk_comm** out, int n_ranks, int rank, const void* id128, int device);
+int mk_comm_init(mk_comm** out, int n_gpus);
+int mk_allreduce_stats(mk_comm* c, double* stats, int64_t count, void* stream);
+int mk_allreduce_stats_all(mk_comm* const* comms, double* const* stats, int n_gpus, int64_t count,
+                           void* const* streams);
+int mk_comm_destroy(mk_comm* c);
 
 /* Instrumentation: number of kernels this library launched on the calling thread since
  * the last reset (bench.py's gpu_launches), and workspace bytes held by a batch. */

@@ -65,6 +65,22 @@ def build(force=False, verbose=False):
 
 _lib = None
 
+
+def _point_at_nccl():
+    """mk_comm_* bind libnccl at run time (dlopen); tell them where PyTorch's bundled copy lives unless the caller did."""
+    if os.environ.get("MK_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["MK_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
 _i64, _i32, _vp = C.c_int64, C.c_int32, C.c_void_p
 _EMIS = [_vp, _i64, _i64, _i64, _i64, _i64, C.c_int, C.POINTER(_i32)]  # ll, sb, sd, sn, D, T, expanded, seqlens
 
@@ -83,6 +99,7 @@ SIGNATURES = {
     "mk_alpha": (C.c_int, [_vp] + _EMIS + [_vp, _vp]),
     "mk_beta": (C.c_int, [_vp] + _EMIS + [_vp, _vp]),
     "mk_pdfposteriors": (C.c_int, [_vp] + _EMIS + [_vp, _vp, _vp]),
+    "mk_pdfposteriors_stats": (C.c_int, [_vp] + _EMIS + [_vp, _vp, _vp, _vp]),
     "mk_bestpath": (C.c_int, [_vp] + _EMIS + [_vp, _vp, _vp]),
     "mk_pdfposteriors_host": (C.c_int, [_vp] + _EMIS + [_vp, _vp]),
     "mk_bestpath_host": (C.c_int, [_vp] + _EMIS + [_vp, _vp]),
@@ -91,6 +108,12 @@ SIGNATURES = {
     "mk_spmm": (C.c_int, [C.c_int, C.c_int, _i64, _i64, _i64, _vp, _vp, _vp, C.c_int, _vp, _i64, _i64, _i64, _vp, _i64,
                           _i64, _i64, C.c_int, _vp]),
     "mk_spvec_bcast": (C.c_int, [C.c_int, C.c_int, C.c_int, _i64, _i64, _vp, _vp, C.c_int, _vp, _i64, _vp, _i64, _vp]),
+    "mk_comm_unique_id": (C.c_int, [_vp]),
+    "mk_comm_init_rank": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, _vp, C.c_int]),
+    "mk_comm_init": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "mk_allreduce_stats": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "mk_allreduce_stats_all": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), C.c_int, _i64, C.POINTER(_vp)]),
+    "mk_comm_destroy": (C.c_int, [_vp]),
     "mk_launch_count": (_i64, [C.c_int]),
     "mk_batch_workspace_bytes": (_i64, [_vp]),
     "mk_batch_profile": (C.c_int, [_vp, C.c_int]),
@@ -106,11 +129,12 @@ def lib():
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(libmarkov_b200 has no CPU fallback)")
+        _point_at_nccl()
         l = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(l, name)
             fn.restype, fn.argtypes = res, args
-        if l.mk_abi_version() != 1:
+        if l.mk_abi_version() != 2:
             raise RuntimeError("libmarkov_b200.so ABI version mismatch; rebuild")
         _lib = l
     return _lib

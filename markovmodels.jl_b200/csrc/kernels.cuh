@@ -1465,30 +1465,70 @@ template <typename T, int SR> __global__ void __launch_bounds__(1024, 1) small_f
 // ================================================================================================
 // Normalisation: Ẑ ./ sums, ttl = minimum(sums)   (src/inference.jl:157-160)
 // ================================================================================================
-// post[n][d][b] /= zsum[n][b];   grid-stride over n*D*B elements
-template <typename T> __global__ void normalize_post_kernel(T* post, const T* zsum, int B, int D, int Tn) {
-    const size_t total = size_t(Tn) * D * B;
-    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total;
-         i += size_t(gridDim.x) * blockDim.x) {
-        int b = int(i % B);
-        size_t n = i / (size_t(D) * B);
-        T z = zsum[n * B + b];
-        T v = post[i];
-        post[i] = z > T(0) ? v / z : T(0);
+// post[n][d][b] /= zsum[n][b]  (Ẑ ./ sums, :158) and, when `occ` is given, the pdf occupancy of the data-parallel
+// step statistics: occ[d] += Σ_{n,b} post[n][d][b] (float64).  One warp per pdf d and run of kNormFrames frames:
+// the lanes sweep the utterance-fastest rows (512 B at B = 128) with 16-byte accesses when B % 4 == 0, keep a partial
+// sum over the run, and issue ONE float64 atomic per (d, run) — 20 per pdf at T = 150.
+//   grid (ceil(D / warps per block), ceil(Tn / kNormFrames)), block 256
+constexpr int kNormFrames = 8;
+template <typename T>
+__global__ void normalize_post_kernel(T* post, const T* zsum, int B, int D, int Tn, double* occ) {
+    const int lane = threadIdx.x & 31, d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (d >= D) return;
+    const int n0 = blockIdx.y * kNormFrames, n1 = min(Tn, n0 + kNormFrames);
+    T sum = T(0);
+    const bool vec = sizeof(T) == 4 && (B & 3) == 0 && (reinterpret_cast<uintptr_t>(post) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(zsum) & 15) == 0;
+    for (int n = n0; n < n1; ++n) {
+        T* row = post + (size_t(n) * D + d) * B;
+        const T* z = zsum + size_t(n) * B;
+        if (vec) {
+            for (int b = lane * 4; b < B; b += 128) {
+                const float4 zz = *reinterpret_cast<const float4*>(z + b);
+                float4 v = *reinterpret_cast<float4*>(row + b);
+                v.x = zz.x > 0.f ? v.x / zz.x : 0.f; v.y = zz.y > 0.f ? v.y / zz.y : 0.f;
+                v.z = zz.z > 0.f ? v.z / zz.z : 0.f; v.w = zz.w > 0.f ? v.w / zz.w : 0.f;
+                *reinterpret_cast<float4*>(row + b) = v;
+                sum += T((v.x + v.y) + (v.z + v.w));
+            }
+        } else {
+            for (int b = lane; b < B; b += 32) {
+                const T zz = z[b];
+                const T v = zz > T(0) ? row[b] / zz : T(0);
+                row[b] = v;
+                sum += v;
+            }
+        }
     }
+    if (!occ) return;
+    double s = double(sum);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0 && s != 0.0) atomicAdd(occ + d, s);
 }
 // logz[b] = lz[b] + log(min_n zsum[n][b])
 // (nlimit: frames that were evaluated for utterance b — its tile's limit in a ragged batch — or null = N1)
+// stats (optional, float64): stats[0] += Σ_b logz[b], stats[1] += Σ_b frames of b (seqlens[b], or Tn)
 template <typename T>
-__global__ void total_kernel(const T* zsum, const T* lz, T* logz, int B, int N1, const int* nlimit) {
+__global__ void total_kernel(const T* zsum, const T* lz, T* logz, int B, int N1, const int* nlimit, double* stats,
+                             const int* seqlens, int Tn) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     T l = lz[b];
-    if (l == neg_inf<T>()) { logz[b] = l; return; }
-    T mn = zsum[b];
-    const int nl = nlimit ? nlimit[b] : N1;
-    for (int n = 1; n < nl; ++n) mn = fmin(mn, zsum[size_t(n) * B + b]);
-    logz[b] = mn > T(0) ? l + T(log(double(mn))) : neg_inf<T>();
+    T out;
+    if (l == neg_inf<T>()) {
+        out = l;
+    } else {
+        T mn = zsum[b];
+        const int nl = nlimit ? nlimit[b] : N1;
+        for (int n = 1; n < nl; ++n) mn = fmin(mn, zsum[size_t(n) * B + b]);
+        out = mn > T(0) ? l + T(log(double(mn))) : neg_inf<T>();
+    }
+    logz[b] = out;
+    if (stats) {
+        atomicAdd(stats, double(out));
+        atomicAdd(stats + 1, double(seqlens ? seqlens[b] : Tn));
+    }
 }
 
 // ================================================================================================

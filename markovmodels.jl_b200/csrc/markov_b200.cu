@@ -15,6 +15,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
+#include <memory>
+#include <mutex>
 #include <functional>
 #include <limits>
 #include <map>
@@ -640,6 +643,7 @@ struct CallArgs {
     const void* ll; int64_t sb, sd, sn, D, T; int expanded; const int32_t* seqlens;
     void* out0;  // A / B / post / path
     void* out1;  // logz / score
+    double* stats = nullptr;  // MODE_POST, optional: device float64 [D + 2] step statistics {Σ logZ, #frames, occupancy[D]}
     cudaStream_t stream;
     const Segments* seg = nullptr;  // host pipeline (single shared-graph group only)
 };
@@ -845,11 +849,11 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
                 // Ẑ ./ sums for the real frames of this segment, then hand them to the caller
                 const int t0 = fb[k], t1 = std::min(fb[k + 1], Tout);
                 if (t1 > t0) {
-                    size_t total = size_t(t1 - t0) * Dout * bt->B;
-                    int blocks = int(std::min<size_t>((total + 255) / 256, size_t(bt->n_sms) * 16));
-                    normalize_post_kernel<T><<<blocks, 256, 0, c.stream>>>(
+                    dim3 ng((Dout + 7) / 8, (t1 - t0 + kNormFrames - 1) / kNormFrames);
+                    normalize_post_kernel<T><<<ng, 256, 0, c.stream>>>(
                         static_cast<T*>(c.out0) + size_t(t0) * Dout * bt->B,
-                        static_cast<const T*>(bt->zsum.p) + size_t(t0) * bt->B, int(bt->B), Dout, t1 - t0);
+                        static_cast<const T*>(bt->zsum.p) + size_t(t0) * bt->B, int(bt->B), Dout, t1 - t0,
+                        c.stats ? c.stats + 2 : nullptr);
                     CK(cudaGetLastError());
                     ++g_launches;
                 }
@@ -960,6 +964,7 @@ template <typename T, int SR> static int run(mk_batch* bt, Mode mode, const Call
         if (!c.out1) return fail(MK_EINVAL, "null logz buffer");
         CK(cudaMemsetAsync(c.out0, 0, size_t(Tout) * Dout * B * sizeof(T), c.stream));
         CK(cudaMemsetAsync(bt->zsum.p, 0, size_t(N1) * B * sizeof(T), c.stream));
+        if (c.stats) CK(cudaMemsetAsync(c.stats, 0, size_t(Dout + 2) * sizeof(double), c.stream));
     }
     const Segments* seg = (c.seg && bt->groups.size() == 1 && bt->small.empty()) ? c.seg : nullptr;
     bt->ragged_cut = false;
@@ -968,11 +973,11 @@ template <typename T, int SR> static int run(mk_batch* bt, Mode mode, const Call
     TRY((launch_small<T, SR>(bt, mode, c, Dh, N1, Dout, Tout, d_seqlens)));
 
     if (mode == MODE_POST) {
-        size_t total = size_t(Tout) * Dout * B;
-        int blocks = int(std::min<size_t>((total + 255) / 256, size_t(bt->n_sms) * 16));
         if (!seg) {  // (a segmented call normalises segment by segment, inside launch_shared)
-            normalize_post_kernel<T><<<blocks, 256, 0, c.stream>>>(static_cast<T*>(c.out0),
-                                                                 static_cast<const T*>(bt->zsum.p), B, Dout, Tout);
+            dim3 ng((Dout + 7) / 8, (Tout + kNormFrames - 1) / kNormFrames);
+            normalize_post_kernel<T><<<ng, 256, 0, c.stream>>>(static_cast<T*>(c.out0),
+                                                             static_cast<const T*>(bt->zsum.p), B, Dout, Tout,
+                                                             c.stats ? c.stats + 2 : nullptr);
             CK(cudaGetLastError());
         }
         const int* zlimit = nullptr;
@@ -983,7 +988,8 @@ template <typename T, int SR> static int run(mk_batch* bt, Mode mode, const Call
         }
         total_kernel<T><<<(B + 127) / 128, 128, 0, c.stream>>>(static_cast<const T*>(bt->zsum.p),
                                                              static_cast<const T*>(bt->lz.p),
-                                                             static_cast<T*>(c.out1), B, N1, zlimit);
+                                                             static_cast<T*>(c.out1), B, N1, zlimit, c.stats,
+                                                             c.expanded ? nullptr : d_seqlens, Tout);
         CK(cudaGetLastError());
         g_launches += 2;
     }
@@ -1451,6 +1457,13 @@ int mk_pdfposteriors(mk_batch* b, const void* ll, int64_t sb, int64_t sd, int64_
                      int expanded, const int32_t* seqlens, void* out_post, void* out_logz, void* stream) {
     return dispatch(b, MODE_POST, mkargs(ll, sb, sd, sn, D, T, expanded, seqlens, out_post, out_logz, stream));
 }
+int mk_pdfposteriors_stats(mk_batch* b, const void* ll, int64_t sb, int64_t sd, int64_t sn, int64_t D, int64_t T,
+                           int expanded, const int32_t* seqlens, void* out_post, void* out_logz, double* out_stats,
+                           void* stream) {
+    CallArgs c = mkargs(ll, sb, sd, sn, D, T, expanded, seqlens, out_post, out_logz, stream);
+    c.stats = out_stats;
+    return dispatch(b, MODE_POST, c);
+}
 int mk_bestpath(mk_batch* b, const void* ll, int64_t sb, int64_t sd, int64_t sn, int64_t D, int64_t T,
                 int expanded, const int32_t* seqlens, int32_t* out_path, void* out_score, void* stream) {
     return dispatch(b, MODE_BEST, mkargs(ll, sb, sd, sn, D, T, expanded, seqlens, out_path, out_score, stream));
@@ -1611,6 +1624,152 @@ int mk_spvec_bcast(int semiring, int dtype, int op, int64_t n, int64_t nnz, cons
     if (!sms) return fail(MK_ECUDA, "no usable CUDA device (libmarkov_b200 has no CPU fallback)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MK_SR_DISPATCH(spvec_launch, op, n, nnz, nzind, nzval, index_base, y, dest, sms, st);
+}
+
+// ---- data-parallel exchange: NCCL, bound at run time (no link-time dependency) -------------------------------
+// The only cross-GPU step of the path is ONE sum all-reduce of the step statistics.  libnccl is looked
+// up with dlopen: MK_NCCL_LIB, then the sonames a CUDA.jl / PyTorch process already has loaded.
+namespace {
+struct NcclId { char internal[128]; };
+typedef void* NcclComm;
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(NcclComm*, int, NcclId, int) = nullptr;
+    int (*CommInitAll)(NcclComm*, int, const int*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string why;
+};
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {getenv("MK_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            if (!n || !*n) continue;
+            api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.h) break;
+            api.why = dlerror();
+        }
+        if (!api.h) return;
+        auto sym = [&](const char* n) { void* p = dlsym(api.h, n); if (!p) { api.why = std::string("missing symbol ") + n; } return p; };
+        api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+        api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+        api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(sym("ncclCommInitAll"));
+        api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+        api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+        api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+        api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+        api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+        if (!api.GetUniqueId || !api.CommInitRank || !api.CommInitAll || !api.AllReduce || !api.CommDestroy ||
+            !api.GroupStart || !api.GroupEnd || !api.GetErrorString) {
+            dlclose(api.h);
+            api.h = nullptr;
+        }
+    });
+    return &api;
+}
+int need_nccl(NcclApi** out) {
+    NcclApi* a = nccl_api();
+    if (!a->h) return fail(MK_ENOTSUP, "libnccl is not available (%s); set MK_NCCL_LIB", a->why.c_str());
+    *out = a;
+    return MK_OK;
+}
+#define NCK(api, call)                                                                                   \
+    do {                                                                                                 \
+        int r_ = (call);                                                                                 \
+        if (r_ != 0) return fail(MK_ECUDA, "%s failed: %s", #call, (api)->GetErrorString(r_));           \
+    } while (0)
+}  // namespace
+
+struct mk_comm {
+    NcclComm comm = nullptr;
+    int device = 0, n_ranks = 1, rank = 0;
+};
+
+int mk_comm_unique_id(void* id128) {
+    if (!id128) return fail(MK_EINVAL, "null id buffer");
+    NcclApi* a;
+    TRY(need_nccl(&a));
+    NcclId id;
+    NCK(a, a->GetUniqueId(&id));
+    std::memcpy(id128, &id, sizeof id);
+    return MK_OK;
+}
+
+int mk_comm_init_rank(mk_comm** out, int n_ranks, int rank, const void* id128, int device) {
+    if (!out || !id128) return fail(MK_EINVAL, "null argument");
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(MK_EINVAL, "rank %d outside [0, %d)", rank, n_ranks);
+    NcclApi* a;
+    TRY(need_nccl(&a));
+    if (device < 0) CK(cudaGetDevice(&device));
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(MK_ECUDA, "cannot select CUDA device %d", device);
+    NcclId id;
+    std::memcpy(&id, id128, sizeof id);
+    std::unique_ptr<mk_comm> c(new mk_comm);
+    c->device = device; c->n_ranks = n_ranks; c->rank = rank;
+    NCK(a, a->CommInitRank(&c->comm, n_ranks, id, rank));
+    *out = c.release();
+    return MK_OK;
+}
+
+int mk_comm_init(mk_comm** out, int n_gpus) {
+    if (!out || n_gpus < 1) return fail(MK_EINVAL, "bad arguments");
+    NcclApi* a;
+    TRY(need_nccl(&a));
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess || have < n_gpus)
+        return fail(MK_ECUDA, "%d CUDA devices requested, %d usable", n_gpus, have);
+    std::vector<NcclComm> comms(n_gpus);
+    std::vector<int> devs(n_gpus);
+    for (int i = 0; i < n_gpus; ++i) devs[i] = i;
+    NCK(a, a->CommInitAll(comms.data(), n_gpus, devs.data()));
+    for (int i = 0; i < n_gpus; ++i) {
+        out[i] = new mk_comm;
+        out[i]->comm = comms[i]; out[i]->device = i; out[i]->n_ranks = n_gpus; out[i]->rank = i;
+    }
+    return MK_OK;
+}
+
+int mk_allreduce_stats(mk_comm* c, double* stats, int64_t count, void* stream) {
+    if (!c || !c->comm) return fail(MK_EINVAL, "null communicator");
+    if (!stats || count < 0) return fail(MK_EINVAL, "bad buffer");
+    if (count == 0) return MK_OK;
+    NcclApi* a;
+    TRY(need_nccl(&a));
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return fail(MK_ECUDA, "cannot select CUDA device %d", c->device);
+    NCK(a, a->AllReduce(stats, stats, size_t(count), /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm,
+                        static_cast<cudaStream_t>(stream)));
+    return MK_OK;
+}
+
+int mk_allreduce_stats_all(mk_comm* const* comms, double* const* stats, int n_gpus, int64_t count, void* const* streams) {
+    if (!comms || !stats || n_gpus < 1) return fail(MK_EINVAL, "bad arguments");
+    NcclApi* a;
+    TRY(need_nccl(&a));
+    NCK(a, a->GroupStart());
+    int rc = MK_OK;
+    for (int i = 0; i < n_gpus && rc == MK_OK; ++i)
+        rc = mk_allreduce_stats(comms[i], stats[i], count, streams ? streams[i] : nullptr);
+    NCK(a, a->GroupEnd());
+    return rc;
+}
+
+int mk_comm_destroy(mk_comm* c) {
+    if (!c) return MK_OK;
+    NcclApi* a = nccl_api();
+    if (a->h && c->comm) {
+        DeviceGuard guard(c->device);
+        a->CommDestroy(c->comm);
+    }
+    delete c;
+    return MK_OK;
 }
 
 }  // extern "C"

@@ -346,14 +346,16 @@ def _check_out(buf, shape, dtype, on_device, name):
                                                      f"{tuple(buf.shape)}{'' if ok else ' (not contiguous)'}")
 
 
-def pdfposteriors(x, V, Ĉs=None, seqlengths=None, out=None):
+def pdfposteriors(x, V, Ĉs=None, seqlengths=None, out=None, stats=None):
     """``pdfposteriors(fsm, V̂s, Ĉs)`` (src/inference.jl:145-161).
 
     Returns ``(post, ttl)``: ``post`` is the ``(B, D, N)`` array of pdf posteriors (exp domain,
     utterance index fastest in memory, as the reference lays it out) and ``ttl`` the ``B``
     total log-likelihoods.  ``out=(post_buf, ttl_buf)`` supplies the output storage: contiguous
     ``(N, D, B)`` and ``(B,)`` buffers of the payload dtype (device tensors for device input,
-    e.g. pinned numpy arrays for host input)."""
+    e.g. pinned numpy arrays for host input).  ``stats`` (device input only): a float64 CUDA tensor
+    of ``D + 2`` entries that receives the data-parallel step statistics ``[Σ logZ, #frames,
+    occupancy[D]]`` (``mk_pdfposteriors_stats``; see :mod:`sharding`)."""
     B = len(V) if isinstance(V, (list, tuple)) else V.shape[0]
     b = _as_batch(x, Ĉs, B)
     e = _emissions(V, b.K, b.n_pdf_hat)
@@ -371,9 +373,16 @@ def pdfposteriors(x, V, Ĉs=None, seqlengths=None, out=None):
         else:
             post = torch.empty((To, Do, b.B), dtype=_tdtype(b.K), device="cuda")
             ttl = torch.empty((b.B,), dtype=_tdtype(b.K), device="cuda")
-        _lib.check(l.mk_pdfposteriors(b._h, e.ptr, *e.strides, e.D, e.T, e.expanded, _slp(sl),
-                                      post.data_ptr(), ttl.data_ptr(), _stream()))
+        sp = None
+        if stats is not None:
+            if not (stats.is_cuda and stats.dtype == torch.float64 and stats.is_contiguous() and stats.numel() == Do + 2):
+                raise _lib.DimensionMismatch(_lib.MK_EINVAL, f"stats must be a contiguous float64 CUDA tensor of {Do + 2} entries")
+            sp = stats.data_ptr()
+        _lib.check(l.mk_pdfposteriors_stats(b._h, e.ptr, *e.strides, e.D, e.T, e.expanded, _slp(sl),
+                                            post.data_ptr(), ttl.data_ptr(), sp, _stream()))
         return post.permute(2, 1, 0), ttl
+    if stats is not None:
+        raise TypeError("stats= needs device emissions (the host-buffer call returns posteriors to the host)")
     if out is not None:
         post, ttl = out
         _check_out(post, (To, Do, b.B), b.K.dtype, False, "post")

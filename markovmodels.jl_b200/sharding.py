@@ -8,8 +8,59 @@ contiguous slice of the batch and a replica of the shared (denominator) graph, e
 posteriors stay on the owning GPU, and the only exchange is ONE all-reduce per step of
 ``[Σ_b logZ_b, #frames, pdf occupancy[D]]`` (~12 KB; NCCL over NVLink on GPUs, gloo in the CPU
 tests).  No collective touches the recursion itself.
+
+On GPUs nothing of this runs in Python or in eager torch: ``pdfposteriors(..., stats=buf)`` makes the library
+write the statistics (the occupancy falls out of its normalisation pass), and :class:`Communicator` is the
+library's own NCCL binding (``mk_comm_init_rank`` / ``mk_allreduce_stats``), enqueued on the same stream —
+one launch, no host synchronisation.  ``local_stats`` / ``allreduce_stats`` are the host-side / gloo forms
+of the same two steps.
 """
+import ctypes as C
+
 import numpy as np
+
+from . import _lib
+
+
+class Communicator:
+    """One NCCL communicator per rank through the C ABI (``mk_comm_*``): what a Julia host would ``ccall``.
+    The 128-byte unique id travels from rank 0 to the others through ``torch.distributed`` here (any channel
+    works: a file, MPI, a socket)."""
+
+    def __init__(self, rank, world, device=-1, group=None):
+        import torch
+        import torch.distributed as dist
+        l = _lib.lib()
+        ident = (C.c_char * 128)()
+        if rank == 0:
+            _lib.check(l.mk_comm_unique_id(ident))
+        if world > 1:
+            box = [bytes(ident.raw) if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0, group=group)
+            ident = (C.c_char * 128).from_buffer_copy(box[0])
+        h = C.c_void_p()
+        _lib.check(l.mk_comm_init_rank(C.byref(h), world, rank, ident, device))
+        self._h, self.rank, self.world = h, rank, world
+
+    def allreduce_(self, stats):
+        """In-place float64 sum over the ranks, asynchronous on the current torch stream."""
+        import torch
+        if not (stats.is_cuda and stats.dtype == torch.float64 and stats.is_contiguous()):
+            raise TypeError("stats must be a contiguous float64 CUDA tensor")
+        _lib.check(_lib.lib().mk_allreduce_stats(self._h, stats.data_ptr(), stats.numel(),
+                                                 torch.cuda.current_stream().cuda_stream))
+        return stats
+
+    def close(self):
+        if self._h:
+            _lib.lib().mk_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def shard_bounds(n_utts, rank, world):

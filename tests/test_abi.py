@@ -23,7 +23,7 @@ def test_header_symbols_exported(mm):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     from markov_b200 import _lib
     assert set(_lib.SIGNATURES) == declared
-    assert lib.mk_abi_version() == 1
+    assert lib.mk_abi_version() == 2
 
 
 def test_no_cpu_fallback(mm):
@@ -137,3 +137,18 @@ def test_semiring_descriptors(mm):
     assert K.zero == -np.inf and K.one == 0.0 and repr(K) == "LogSemiring{Float32}"
     assert K.add(2.0, 3.0) == pytest.approx(3.3132617, rel=1e-6)
     assert mm.TropicalSemiring[np.float64].add(2.0, 3.0) == 3.0
+
+
+def test_comm_exports_validate_arguments(mm):
+    """The multi-GPU exports of SURVEY.md 8(b) exist and reject bad arguments without a GPU."""
+    import ctypes as C
+    from markov_b200 import _lib
+    lib = mm.lib()
+    assert lib.mk_comm_unique_id(None) == _lib.MK_EINVAL
+    h = C.c_void_p()
+    ident = (C.c_char * 128)()
+    assert lib.mk_comm_init_rank(C.byref(h), 2, 5, ident, -1) == _lib.MK_EINVAL      # rank outside [0, n_ranks)
+    assert lib.mk_comm_init_rank(None, 1, 0, ident, -1) == _lib.MK_EINVAL
+    assert lib.mk_allreduce_stats(None, None, 4, None) == _lib.MK_EINVAL
+    assert lib.mk_comm_destroy(None) == _lib.MK_OK
+    assert b"communicator" in lib.mk_last_error() or b"null" in lib.mk_last_error()

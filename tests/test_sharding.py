@@ -70,3 +70,36 @@ def test_two_rank_allreduce_matches_single_process(tmp_path):
     np.testing.assert_array_equal(s0, s1)  # every rank holds the reduced statistics
     np.testing.assert_allclose(s0, full, rtol=1e-12, atol=1e-12)
     assert s0[1] == full[1] and abs(s0[2:].sum() - full[1]) < 1e-6  # occupancy sums to #frames
+
+
+@pytest.mark.gpu
+def test_library_step_statistics_match_the_host_form():
+    """mk_pdfposteriors_stats writes [Σ logZ, #frames, occupancy[D]] itself; same numbers as local_stats on the outputs
+    (shared-graph and per-utterance kernels, ragged lengths), and a 1-rank communicator leaves them unchanged."""
+    import torch
+    import markov_b200 as mm
+    K = mm.LogSemiring[np.float32]
+    rng = np.random.default_rng(5)
+    D, T = 60, 40
+    den, den_pdf = mm.graphs.denominator(K, n_tokens=1500, n_pdf=D, seed=2)
+    cden = mm.compile(den, mm.statemap(den, D, den_pdf))
+    nums = [mm.graphs.numerator(K, rng, D, n_phones=6) for _ in range(3)]
+    cn = [mm.compile(f, mm.statemap(f, D, p)) for f, p in nums]
+    for graphs in ([cden] * 12, cn, [cden] * 8 + cn):
+        B = len(graphs)
+        V = torch.from_numpy((rng.standard_normal((B, T, D)) * 2).astype(np.float32)).cuda().permute(0, 2, 1)
+        lens = rng.integers(T // 2, T + 1, B).astype(np.int32)
+        stats = torch.full((D + 2,), 7.0, dtype=torch.float64, device="cuda")   # (overwritten, not accumulated)
+        post, ttl = mm.pdfposteriors(mm.batch(*graphs), V, seqlengths=lens, stats=stats)
+        want = mm.sharding.local_stats(post, ttl, lens)
+        torch.testing.assert_close(stats, want, rtol=1e-5, atol=1e-4)
+        assert float(stats[1]) == float(lens.sum())
+        np.testing.assert_allclose(float(stats[2:].sum()), float(lens.sum()), rtol=1e-4)   # posteriors sum to 1 per frame
+    comm = mm.sharding.Communicator(0, 1)
+    before = stats.clone()
+    comm.allreduce_(stats)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(stats, before, rtol=0, atol=0)
+    comm.close()
+    with pytest.raises(TypeError):
+        mm.pdfposteriors(mm.batch(*cn), V[:3].cpu().numpy(), seqlengths=lens[:3], stats=stats)
