@@ -155,6 +155,35 @@ def run_reference(args):
                 "reference cannot run in this image"}))
 
 
+def bind_rank_to_cores(torch, local, n_local):
+    """One core set per rank, on the NUMA node of the rank's GPU when sysfs says which: the ranks' launch threads
+    stop competing for the same cores, and the pinned host buffers of the e2e leg (first touched after this) land in
+    memory local to the GPU's PCIe root.  Returns a short description for the JSON line."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return "unbound"
+    near = []
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/local_cpulist"
+        for part in open(path).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            near.extend(range(int(lo), int(hi or lo) + 1))
+        near = [c for c in near if c in allowed]
+    except Exception:
+        near = []
+    pool = near if len(near) >= n_local else allowed
+    # the ranks that share this pool take disjoint slices of it
+    per = max(1, len(pool) // n_local)
+    mine = pool[(local % n_local) * per:(local % n_local) * per + per] or pool
+    try:
+        os.sched_setaffinity(0, mine)
+    except OSError:
+        return "unbound"
+    return f"{len(mine)} cores ({'GPU-local NUMA node' if near and pool is near else 'even split'})"
+
+
 def run_ours(args):
     import torch
     import markov_b200 as mm
@@ -164,6 +193,9 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (libmarkov_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
+    binding = "unbound"
+    if world > 1 and os.environ.get("MK_BENCH_BIND", "1") != "0":
+        binding = bind_rank_to_cores(torch, local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -200,12 +232,15 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step()
-    sync_all()
+    # Everything slow and rank-specific happens BEFORE the barrier that opens the timed region: NVML initialisation on
+    # rank 0 takes tens of milliseconds, and a rank that enters the region late makes every other rank wait for it in
+    # the first all-reduce (round 1 measured exactly that: +1.9 ms per step at N = 8, none of it in the exchange).
     bfsm.profile(True)
     sampler = ClockSampler(local) if rank == 0 else None
     lib.mk_launch_count(1)
     if sampler:
         sampler.start()  # (NVML is already initialised: the first sample lands within microseconds)
+    sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -287,6 +322,7 @@ def run_ours(args):
                              "the L2 gathers of state vectors per warp and the per-frame grid barrier (DESIGN.md "
                              "section 4, profiles/)"},
         "mean_logz": logz_mean,
+        "host_binding": binding,
     }
     if world == 1 and not args.skip_cpu_baseline:
         import oracle
