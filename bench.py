@@ -120,35 +120,45 @@ def cpu_sample(fsm, pdfids, n_utts, frames, threads, seed=SEED):
 
 def run_reference(args):
     """The reference's own CPU algorithm for the path (oracle port: the reference is Julia and
-    cannot run here) on all host cores; rank 0 only."""
+    cannot run here) on the host cores; rank 0 only.  Two figures: ALL cores this process may use (one
+    full-length utterance per core and step — torchrun's OMP_NUM_THREADS=1 is ignored on purpose) = the
+    line's `value`, and ONE core (faithful to the reference, whose src/ has no threads)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     import markov_b200 as mm
     import oracle
     K, (fsm, pdfids) = build_graph(mm)
     threads = oracle.num_threads()
-    # bounded sample: one utterance per thread; frames chosen so that warmup+steps end in ~2-3 min
-    # (one 150-frame utterance takes ~6.5 s on one core)
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    frames = int(min(T_FRAMES, max(10, T_FRAMES * budget / 8.0)))
+    frames = T_FRAMES  # full 150-frame utterances (about 7 s each on one core: a step is one utterance per core)
     og = oracle.OracleGraph(fsm, pdfids, N_PDF)
     rng = np.random.default_rng(SEED)
     V = (rng.standard_normal((threads, frames, N_PDF)) * 2).astype(np.float32)
-    for _ in range(args.warmup):
+    t0 = time.perf_counter()
+    oracle.pdfposteriors([og], V[:1], threads=1)
+    single = frames / (time.perf_counter() - t0)
+    # bounded: the whole run (warm-up included) stays within a few minutes whatever --steps says
+    est_step = frames / single * 1.3
+    steps = max(1, min(args.steps, int(150.0 / est_step) - 1))
+    warmup = 1 if args.warmup > 0 else 0
+    for _ in range(warmup):
         oracle.pdfposteriors([og] * threads, V, threads=threads)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         oracle.pdfposteriors([og] * threads, V, threads=threads)
     dt = time.perf_counter() - t0
-    value = args.steps * threads * frames / dt
-    sample = f"{threads} utterances x {frames} frames of the workload per step (one utterance per thread)"
+    value = steps * threads * frames / dt
+    sample = (f"{threads} utterances x {frames} frames of the workload per step, one utterance per core, {steps} timed "
+              f"step(s) (bounded from --steps {args.steps})")
     cfg = workload_config(args.gpus, B_PER_GPU, T_FRAMES)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * dt / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": cfg,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "single_thread": {"value": single, "unit": UNIT, "cores": 1,
+                                           "sample": f"1 utterance x {frames} frames"},
+                         "build": oracle.build_flags()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "oracle port (C++ restatement of src/inference.jl, OpenMP over utterances); the Julia "
@@ -300,6 +310,16 @@ def run_ours(args):
     units = B * T
     achieved = bytes_per_unit * units / (kernel_ms * 1e-3) / 1e9
     peak, which = hbm_peak()
+    # the SFU half of the roofline: 2(nnz + S) + S MUFU operations per frame.utterance for the log-domain
+    # arithmetic of the reference (one ex2 per arc and one lg2 per row in each sweep, one ex2 per state for gamma),
+    # against the ex2 rate measured on this GPU just now
+    import ctypes
+    sfu_peak = ctypes.c_double(0.0)
+    mm._lib.check(lib.mk_measure_sfu_peak(local, ctypes.byref(sfu_peak)))
+    nnz_hat = int(fsm.nnz_hat)
+    sfu_per_unit = 2 * (nnz_hat + fsm.nstates_hat) + fsm.nstates_hat
+    t_hbm = bytes_per_unit * units / (peak * 1e9)
+    t_sfu = sfu_per_unit * units / sfu_peak.value
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -318,9 +338,18 @@ def run_ours(args):
                                "launches, timed together)", "kernel_ms": kernel_ms,
                      "bytes_per_frame_utt": bytes_per_unit, "units_per_launch": units,
                      "kernel_share_of_step": kernel_ms / (ms_total / args.steps),
-                     "note": "HBM is not the binding ceiling of this kernel: the recursion is bound by the latency of "
-                             "the L2 gathers of state vectors per warp and the per-frame grid barrier (DESIGN.md "
-                             "section 4, profiles/)"},
+                     "sfu": {"ops_per_frame_utt": sfu_per_unit, "algorithmic_ops_per_launch": sfu_per_unit * units,
+                             "achieved": sfu_per_unit * units / (kernel_ms * 1e-3) / 1e12, "peak": sfu_peak.value / 1e12,
+                             "unit": "Tops/s", "frac": t_sfu / (kernel_ms * 1e-3),
+                             "peak_source": "mk_measure_sfu_peak (ex2.approx micro-kernel, measured in this run)",
+                             "note": "operations of the reference's log-domain arithmetic; the kernel itself accumulates "
+                                     "linear copies with FFMAs and issues MUFU work per state only (DESIGN.md section 4)"},
+                     "t_hbm_ms": 1e3 * t_hbm, "t_sfu_ms": 1e3 * t_sfu,
+                     "binding_ceiling": "sfu" if t_sfu > t_hbm else "hbm",
+                     "frac_of_binding_ceiling": max(t_hbm, t_sfu) / (kernel_ms * 1e-3),
+                     "note": "roofline time = max(t_HBM, t_SFU) (BASELINE.md section 3); `frac` is the HBM fraction. The "
+                             "kernel is bound by instructions issued per warp and the per-frame grid barrier, not by "
+                             "HBM, SFU or the latency of the L2 gathers (DESIGN.md section 4, profiles/)"},
         "mean_logz": logz_mean,
         "host_binding": binding,
     }
@@ -329,13 +358,61 @@ def run_ours(args):
         threads = oracle.num_threads()
         n_utts, frames = threads, T
         v = cpu_sample(fsm, pdfids, n_utts, frames, threads)
+        v1 = cpu_sample(fsm, pdfids, 1, frames, 1)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                "sample": f"{n_utts} utterances x {frames} frames of the workload, one utterance per "
-                                         f"thread (OpenMP), C++ oracle port of src/inference.jl"}
+                                         f"thread (OpenMP), C++ oracle port of src/inference.jl",
+                               "single_thread": {"value": v1, "unit": UNIT, "cores": 1,
+                                                 "sample": f"1 utterance x {frames} frames"},
+                               "build": oracle.build_flags()}
     print(json.dumps(out))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_bestpath(args):
+    """BASELINE.json configs[4]: TropicalSemiring Viterbi bestpath on the denominator graph, B = 512, T = 500, one GPU
+    (a parity-test shape of the headline metric; printed as its own line on request)."""
+    import torch
+    import markov_b200 as mm
+    torch.cuda.set_device(0)
+    B, T, D = (512, 500, N_PDF) if args.batch == B_PER_GPU and args.frames == T_FRAMES else (args.batch, args.frames, N_PDF)
+    K = mm.TropicalSemiring[np.float32]
+    fsm, pdfids = mm.graphs.denominator(K, n_tokens=N_TOKENS, n_pdf=N_PDF, seed=SEED)
+    bfsm = mm.batch(*[mm.compile(fsm, mm.statemap(fsm, D, pdfids))] * B)
+    V = (torch.randn((B, T, D), generator=torch.Generator(device="cuda").manual_seed(505), device="cuda") * 2).permute(0, 2, 1)
+    lib = mm.lib()
+    for _ in range(max(args.warmup, 3)):
+        path, score = mm.bestpath(bfsm, V)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    lib.mk_launch_count(1)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        path, score = mm.bestpath(bfsm, V)   # two calls in flight without a host synchronisation: the call is asynchronous
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    peak, which = hbm_peak()
+    # SURVEY.md 8d: w*D̂ emissions + 4*Ŝ tropical alpha (stored instead of back-pointers) + the path entry
+    bytes_per_unit = 4 * (D + 1) + 4 * fsm.nstates_hat + 4
+    achieved = bytes_per_unit * B * T / (ms * 1e-3) / 1e9
+    print(json.dumps({
+        "metric": "TropicalSemiring Viterbi bestpath frames/sec (batch x T)", "value": B * T / (ms * 1e-3), "unit": UNIT,
+        "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[4]: TropicalSemiring Viterbi bestpath on the synthetic denominator "
+                               "graph (30000 states, 3000 pdfs)", "batch_per_gpu": B, "frames": T,
+                   "l2": "inputs larger than L2 (tropical alpha store %.1f GB)" % (bfsm.workspace_bytes() / 1e9)},
+        "gpu_launches": int(lib.mk_launch_count(0)), "clocks": sampler.result(),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "bytes_per_frame_utt": bytes_per_unit, "units_per_launch": B * T,
+                     "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})",
+                     "kernel": "shared_fb_kernel<float, Tropical> forward sweep + backtrace_kernel (whole call timed)"},
+        "workspace_bytes": int(bfsm.workspace_bytes()), "mean_score": float(score.mean())}))
 
 
 def main():
@@ -347,9 +424,13 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="utterances per GPU")
     ap.add_argument("--frames", type=int, default=T_FRAMES)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="posteriors", choices=["posteriors", "bestpath"],
+                    help="posteriors = the headline metric (default); bestpath = BASELINE.json configs[4], its own line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "bestpath":
+        run_bestpath(args)
     else:
         world = int(os.environ.get("WORLD_SIZE", "1"))
         if args.gpus != world and world == 1 and args.gpus > 1:

@@ -215,6 +215,9 @@ int64_t mk_batch_workspace_bytes(const mk_batch* b);
  * mk_batch_kernel_ms waits for and returns the durations of the most recent launches (up to
  * `cap`, oldest first).  Enabling resets the ring. */
 int mk_batch_profile(mk_batch* b, int enable);
+/* The MUFU (exp2) rate of `device` (-1 = current), measured with a micro-kernel: the peak the SFU half of the
+ * roofline (roofline time = max(t_HBM, t_SFU)) is quoted against.  Synchronous, ~10 ms. */
+int mk_measure_sfu_peak(int device, double* ops_per_second);
 int mk_batch_kernel_ms(mk_batch* b, float* ms, int cap, int* n);
 
 #ifdef __cplusplus

@@ -117,6 +117,7 @@ SIGNATURES = {
     "mk_launch_count": (_i64, [C.c_int]),
     "mk_batch_workspace_bytes": (_i64, [_vp]),
     "mk_batch_profile": (C.c_int, [_vp, C.c_int]),
+    "mk_measure_sfu_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "mk_batch_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]),
 }
 

@@ -1634,4 +1634,22 @@ __global__ void backtrace_kernel(const TraceDesc<T>* descs, int nutts, const T* 
     }
 }
 
+
+// ================================================================================================
+// MUFU (SFU) peak: the SFU half of the roofline (roofline time = max(t_HBM, t_SFU)) is quoted against
+// the ex2 rate MEASURED on the box, not a data-sheet number.  Eight independent ex2 chains per thread.
+// ================================================================================================
+__global__ void sfu_peak_kernel(float* out, int iters) {
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = -0.001f * float(threadIdx.x + k);
+    for (int i = 0; i < iters; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[k]));
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace mk

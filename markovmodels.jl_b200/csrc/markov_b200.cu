@@ -547,7 +547,9 @@ struct Group {  // utterances sharing one graph, run by shared_fb_kernel
     bool vec4 = false;
     int* d_utt_b = nullptr;
     long long* d_utt_off = nullptr;
-    DevBuf E, emax, emax_key, alpha, bt, flin, blin, part, gkey, coff, lz2, carry, tile_n1;
+    DevBuf E, emax, emax_key, alpha, bt, flin, blin, part, gkey, coff, lz2, carry, tile_n1, trace;
+    std::vector<unsigned char> h_trace;  // back-trace descriptors (bestpath), uploaded once
+    size_t trace_tsize = 0;
     std::vector<int> h_tile_n1;  // ragged batches: frames each utterance tile needs (staging for tile_n1)
     std::vector<int> h_order;    // group lane u -> utterance b of the current call (utts, or its length-sorted quads)
     std::vector<int> h_utt_b;    // staging for d_utt_b when the order changes
@@ -566,6 +568,9 @@ struct mk_batch {
     int64_t small_cached_n1 = -1;
     DevBuf small_descs, small_alpha, small_ca, zsum, lz, seqlens, barrier, trace, h_ll, h_post, h_logz, h_path, zlimit;
     std::vector<int> h_zlimit;  // ragged batches: frames evaluated per utterance (staging for zlimit)
+    std::vector<unsigned char> h_trace;  // back-trace descriptors of the per-utterance kernel's utterances (bestpath)
+    int64_t trace_n1 = -1;
+    size_t trace_tsize = 0;
     bool ragged_cut = false;    // the current call stops at least one utterance tile early
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
     // One in-flight call per batch: the workspaces are shared by every entry point.  Each call records `ev_last` on
@@ -587,7 +592,7 @@ struct mk_batch {
         for (auto& gr : groups) {
             cudaFree(gr.d_utt_b); cudaFree(gr.d_utt_off);
             gr.E.release(); gr.alpha.release(); gr.bt.release(); gr.flin.release(); gr.blin.release();
-            gr.part.release(); gr.gkey.release(); gr.coff.release(); gr.emax.release(); gr.emax_key.release(); gr.lz2.release(); gr.carry.release(); gr.tile_n1.release();
+            gr.part.release(); gr.gkey.release(); gr.coff.release(); gr.emax.release(); gr.emax_key.release(); gr.lz2.release(); gr.carry.release(); gr.tile_n1.release(); gr.trace.release();
         }
         DevBuf* all[] = {&small_descs, &small_alpha, &small_ca, &zsum, &lz, &seqlens, &barrier, &trace,
                          &h_ll, &h_post, &h_logz, &h_path, &zlimit};
@@ -995,47 +1000,53 @@ template <typename T, int SR> static int run(mk_batch* bt, Mode mode, const Call
     }
     if (mode == MODE_BEST) {
         if (!c.out1) return fail(MK_EINVAL, "null score buffer");
-        std::vector<TraceDesc<T>> descs;
-        descs.reserve(B);
-        // every utterance's α lives in one of the workspaces; describe them relative to one base
-        // pointer per launch: two launches (shared groups use per-group buffers).
+        // Back-trace descriptors: static per batch (graph pointers, strides of the α workspaces), so they are built and
+        // uploaded once — per group at the first bestpath call, for the per-utterance kernel again when N̂ changes — from
+        // host vectors the batch owns; the call enqueues kernels only and never synchronises the host.
         for (auto& gr : bt->groups) {
-            descs.clear();
-            for (size_t k = 0; k < gr.utts.size(); ++k) {
-                TraceDesc<T> d;
-                d.in_ptr = gr.g->d_in_ptr; d.in_arcs = static_cast<const Arc<T>*>(gr.g->d_in_arcs);
-                d.base = (long long)k; d.sn = (long long)(gr.g->S + gr.g->n_runs) * gr.U4; d.ss = gr.U4;
-                d.S = int(gr.g->S); d.b = gr.utts[k];
-                descs.push_back(d);
+            const int n = int(gr.utts.size());
+            if (gr.trace_tsize != sizeof(T)) {
+                std::vector<TraceDesc<T>> descs(n);
+                for (int k = 0; k < n; ++k) {
+                    TraceDesc<T>& d = descs[k];
+                    d.in_ptr = gr.g->d_in_ptr; d.in_arcs = static_cast<const Arc<T>*>(gr.g->d_in_arcs);
+                    d.base = (long long)k; d.sn = (long long)(gr.g->S + gr.g->n_runs) * gr.U4; d.ss = gr.U4;
+                    d.S = int(gr.g->S); d.b = gr.utts[k];
+                }
+                gr.h_trace.resize(descs.size() * sizeof(TraceDesc<T>));
+                std::memcpy(gr.h_trace.data(), descs.data(), gr.h_trace.size());
+                TRY(gr.trace.ensure(gr.h_trace.size()));
+                CK(cudaMemcpyAsync(gr.trace.p, gr.h_trace.data(), gr.h_trace.size(), cudaMemcpyHostToDevice, c.stream));
+                gr.trace_tsize = sizeof(T);
             }
-            size_t bytes = descs.size() * sizeof(TraceDesc<T>);
-            TRY(bt->trace.ensure(bytes));
-            CK(cudaMemcpyAsync(bt->trace.p, descs.data(), bytes, cudaMemcpyHostToDevice, c.stream));
-            CK(cudaStreamSynchronize(c.stream));
-            int n = int(descs.size());
             backtrace_kernel<T><<<(n * 32 + 127) / 128, 128, 0, c.stream>>>(
-                static_cast<const TraceDesc<T>*>(bt->trace.p), n, static_cast<const T*>(gr.alpha.p), N1, Tout,
+                static_cast<const TraceDesc<T>*>(gr.trace.p), n, static_cast<const T*>(gr.alpha.p), N1, Tout,
                 d_seqlens, static_cast<int*>(c.out0), static_cast<T*>(c.out1));
             CK(cudaGetLastError());
             ++g_launches;
-            CK(cudaStreamSynchronize(c.stream));  // bt->trace is reused by the next group
         }
         if (!bt->small.empty()) {
-            descs.clear();
-            long long off = 0;
-            for (int b : bt->small) {
-                mk_graph* g = bt->graphs[b];
-                TraceDesc<T> d;
-                d.in_ptr = g->d_in_ptr; d.in_arcs = static_cast<const Arc<T>*>(g->d_in_arcs);
-                d.base = off; d.sn = g->S; d.ss = 1; d.S = int(g->S); d.b = b;
-                off += (long long)N1 * g->S;
-                descs.push_back(d);
+            const int n = int(bt->small.size());
+            if (bt->trace_n1 != N1 || bt->trace_tsize != sizeof(T)) {
+                std::vector<TraceDesc<T>> descs;
+                descs.reserve(n);
+                long long off = 0;
+                for (int b : bt->small) {
+                    mk_graph* g = bt->graphs[b];
+                    TraceDesc<T> d;
+                    d.in_ptr = g->d_in_ptr; d.in_arcs = static_cast<const Arc<T>*>(g->d_in_arcs);
+                    d.base = off; d.sn = g->S; d.ss = 1; d.S = int(g->S); d.b = b;
+                    off += (long long)N1 * g->S;
+                    descs.push_back(d);
+                }
+                // (a previous call may still read the old table: the upload is ordered after it on the call's stream,
+                // and dispatch() orders calls on different streams)
+                bt->h_trace.resize(descs.size() * sizeof(TraceDesc<T>));
+                std::memcpy(bt->h_trace.data(), descs.data(), bt->h_trace.size());
+                TRY(bt->trace.ensure(bt->h_trace.size()));
+                CK(cudaMemcpyAsync(bt->trace.p, bt->h_trace.data(), bt->h_trace.size(), cudaMemcpyHostToDevice, c.stream));
+                bt->trace_n1 = N1; bt->trace_tsize = sizeof(T);
             }
-            size_t bytes = descs.size() * sizeof(TraceDesc<T>);
-            TRY(bt->trace.ensure(bytes));
-            CK(cudaMemcpyAsync(bt->trace.p, descs.data(), bytes, cudaMemcpyHostToDevice, c.stream));
-            CK(cudaStreamSynchronize(c.stream));
-            int n = int(descs.size());
             backtrace_kernel<T><<<(n * 32 + 127) / 128, 128, 0, c.stream>>>(
                 static_cast<const TraceDesc<T>*>(bt->trace.p), n, static_cast<const T*>(bt->small_alpha.p), N1,
                 Tout, d_seqlens, static_cast<int*>(c.out0), static_cast<T*>(c.out1));
@@ -1409,6 +1420,35 @@ int mk_debug_barrier_profile(unsigned long long* out /* [148*4] */) {
     return MK_OK;
 }
 #endif
+
+int mk_measure_sfu_peak(int device, double* ops_per_second) {
+    if (!ops_per_second) return fail(MK_EINVAL, "null result pointer");
+    if (device < 0) CK(cudaGetDevice(&device));
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(MK_ECUDA, "cannot select CUDA device %d", device);
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int blocks = sms * 2, threads = 1024, iters = 4096;
+    float* out = nullptr;
+    CK(cudaMalloc(&out, sizeof(float) * blocks * threads));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float best = 0.f;
+    for (int rep = 0; rep < 4; ++rep) {  // (the first launch warms the clocks up)
+        CK(cudaEventRecord(e0, nullptr));
+        sfu_peak_kernel<<<blocks, threads>>>(out, iters);
+        CK(cudaEventRecord(e1, nullptr));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && (best == 0.f || ms < best)) best = ms;
+        ++g_launches;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *ops_per_second = double(blocks) * threads * iters * 8 / (double(best) * 1e-3);
+    return MK_OK;
+}
 
 int mk_batch_profile(mk_batch* b, int enable) {
     if (!b) return fail(MK_EINVAL, "null batch");

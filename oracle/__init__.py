@@ -48,14 +48,21 @@ def _cpu_signature():
 LIB = os.path.join(_HERE, "_build", f"liboracle_{_cpu_signature()}.so")
 
 
+CXXFLAGS = ["-O3", "-march=native", "-fopenmp", "-fno-fast-math", "-ffp-contract=off", "-std=c++17"]
+
+
+def build_flags():
+    """The compiler line of the CPU legs, for the bench JSON."""
+    return "g++ " + " ".join(CXXFLAGS)
+
+
 def build(force=False):
     """g++ -O3 -march=native -fopenmp for THIS host's CPU; no -ffast-math: -Inf arithmetic
     must be IEEE (and -O3 -march=native without it keeps the scalar ⊕ order of oracle.cpp)."""
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = ["g++", "-O3", "-march=native", "-fopenmp", "-fno-fast-math", "-ffp-contract=off", "-std=c++17", "-shared",
-           "-fPIC", "-o", LIB + ".tmp", SRC]
+    cmd = ["g++"] + CXXFLAGS + ["-shared", "-fPIC", "-o", LIB + ".tmp", SRC]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)

@@ -443,6 +443,33 @@ def test_bestpath_vs_oracle(torch, mm, orc, dtype, force):
         assert np.all(opath[k, :lens[k]] > 0) and np.all(opath[k, lens[k]:] == 0)
 
 
+def test_bestpath_calls_queue_without_host_sync(torch, mm, orc):
+    """mk_bestpath is asynchronous (include/markov_b200.h): several calls with different inputs and frame counts are
+    enqueued back to back on a side stream — nothing waits for the GPU in between — and every one of them is right."""
+    K = mm.TropicalSemiring[np.float32]
+    rng = np.random.default_rng(77)
+    D = 80
+    den = mm.graphs.denominator(K, n_tokens=400, n_pdf=D, seed=9)
+    loop = mm.graphs.phone_loop(K, n_phones=9)
+    loop = (loop[0], loop[1] % D)
+    graphs = [den] * 8 + [loop] * 2     # shared-graph group + per-utterance kernel (whose trace table depends on N̂)
+    B = len(graphs)
+    b = gpu_batch(mm, graphs, D)
+    og = orc_graphs(orc, graphs, D)
+    cases = [(rng.standard_normal((B, T, D)) * 2).astype(np.float32) for T in (30, 45, 30)]
+    st = torch.cuda.Stream()
+    outs = []
+    with torch.cuda.stream(st):
+        devs = [dev(torch, V) for V in cases]
+        for Vd in devs:
+            outs.append(mm.bestpath(b, Vd))
+    st.synchronize()
+    for V, (path, score) in zip(cases, outs):
+        opath, oscore = orc.bestpath(og, V)
+        np.testing.assert_array_equal(path.cpu().numpy(), opath)
+        np.testing.assert_array_equal(score.cpu().numpy(), oscore)
+
+
 def test_bestpath_ties_take_smallest_predecessor(torch, mm, orc):
     """Two exactly tied branches 1->2->4 and 1->3->4: the path goes through state 2."""
     K = mm.TropicalSemiring[np.float32]
