@@ -287,10 +287,38 @@ def run_ours(args):
     for _ in range(args.steps):
         step_e2e()
     torch.cuda.synchronize()
+    single_t = torch.tensor([time.perf_counter() - t0], device="cuda")
+    # The same steps double-buffered: two batch objects (one graph) alternate, step k+1's host-to-device copy and
+    # forward sweep overlap step k's device-to-host copy (PCIe is full duplex).  Every step still copies its inputs
+    # in from pinned memory and its posteriors and log-likelihoods out, and the host reads each result.
+    bf2 = [bfsm, mm.batch(*[cfsm] * B)]
+    post_h2 = torch.empty((T, D, B), pin_memory=True)
+    ttl_h2 = torch.empty((B,), pin_memory=True)
+    outs = [(post_np, ttl_np), (post_h2.numpy(), ttl_h2.numpy())]
+    checks = []
+
+    def run_pipelined(n):
+        for k in range(n):
+            j = k & 1
+            if k >= 2:
+                bf2[j].wait()
+                checks.append(float(outs[j][1].sum()))
+            mm.pdfposteriors(bf2[j], Vh_np, out=outs[j], wait=False)
+        for k in range(max(0, n - 2), n):
+            bf2[k & 1].wait()
+            checks.append(float(outs[k & 1][1].sum()))
+
+    run_pipelined(3)
+    sync_all()
+    t0 = time.perf_counter()
+    run_pipelined(args.steps)
+    torch.cuda.synchronize()
     e2e_t = torch.tensor([time.perf_counter() - t0], device="cuda")
     if dist is not None:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_t)
+        dist.all_reduce(single_t, op=dist.ReduceOp.MAX)
+    e2e_s, single_s = float(e2e_t), float(single_t)
+    torch.testing.assert_close(torch.from_numpy(outs[1][1]).cuda(), ttl, rtol=1e-5, atol=1e-3)
     h2d = Vh.numel() * 4
     d2h = (post_h.numel() + ttl_h.numel()) * 4
     # the two paths must agree
@@ -326,7 +354,12 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(world, B, T),
         "e2e": {"value": frames_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps},
+                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
+                "how": "host buffers through mk_pdfposteriors_host_begin / mk_batch_wait, two batches in flight "
+                       "(double-buffered): every step copies its inputs in and its results out inside the timed region",
+                "single_call": {"value": frames_total * args.steps / single_s, "unit": UNIT,
+                                "ms_per_step": 1e3 * single_s / args.steps,
+                                "how": "one blocking mk_pdfposteriors_host call per step (latency of a lone call)"}},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -145,6 +145,15 @@ int mk_bestpath(mk_batch* b, const void* ll, int64_t stride_b, int64_t stride_d,
 int mk_pdfposteriors_host(mk_batch* b, const void* ll, int64_t stride_b, int64_t stride_d,
                           int64_t stride_n, int64_t D, int64_t T, int expanded,
                           const int32_t* seqlens, void* out_post, void* out_logz);
+/* The same call split in two, for callers that keep several batches in flight (double buffering: one
+ * mk_batch per buffer — they share the graph — so that the next batch's host-to-device copy and forward sweep
+ * overlap this batch's device-to-host copy; PCIe is full duplex).  _begin enqueues the copies and kernels on
+ * the batch's own streams and returns; the host buffers must stay valid and untouched (PINNED memory, or the
+ * copies are not asynchronous) until mk_batch_wait(b) has returned. */
+int mk_pdfposteriors_host_begin(mk_batch* b, const void* ll, int64_t stride_b, int64_t stride_d,
+                                int64_t stride_n, int64_t D, int64_t T, int expanded,
+                                const int32_t* seqlens, void* out_post, void* out_logz);
+int mk_batch_wait(mk_batch* b);
 int mk_bestpath_host(mk_batch* b, const void* ll, int64_t stride_b, int64_t stride_d,
                      int64_t stride_n, int64_t D, int64_t T, int expanded,
                      const int32_t* seqlens, int32_t* out_path, void* out_score);

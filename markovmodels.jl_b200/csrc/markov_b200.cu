@@ -572,6 +572,7 @@ struct mk_batch {
     int64_t trace_n1 = -1;
     size_t trace_tsize = 0;
     bool ragged_cut = false;    // the current call stops at least one utterance tile early
+    bool host_pending = false;  // a mk_pdfposteriors_host_begin call has not been waited for
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
     // One in-flight call per batch: the workspaces are shared by every entry point.  Each call records `ev_last` on
     // its stream when it has enqueued its work; a following call on ANOTHER stream (the *_host entry points run on
@@ -1513,13 +1514,37 @@ static int64_t extent(int64_t B, int64_t D, int64_t T, int64_t sb, int64_t sd, i
     return (B - 1) * sb + (D - 1) * sd + (T - 1) * sn + 1;
 }
 
+static int posteriors_host(mk_batch* b, const void* ll, int64_t sb, int64_t sd, int64_t sn, int64_t D, int64_t T,
+                           int expanded, const int32_t* seqlens, void* out_post, void* out_logz, bool wait);
+
 int mk_pdfposteriors_host(mk_batch* b, const void* ll, int64_t sb, int64_t sd, int64_t sn, int64_t D,
                           int64_t T, int expanded, const int32_t* seqlens, void* out_post, void* out_logz) {
+    return posteriors_host(b, ll, sb, sd, sn, D, T, expanded, seqlens, out_post, out_logz, true);
+}
+int mk_pdfposteriors_host_begin(mk_batch* b, const void* ll, int64_t sb, int64_t sd, int64_t sn, int64_t D,
+                                int64_t T, int expanded, const int32_t* seqlens, void* out_post, void* out_logz) {
+    return posteriors_host(b, ll, sb, sd, sn, D, T, expanded, seqlens, out_post, out_logz, false);
+}
+int mk_batch_wait(mk_batch* b) {
+    if (!b) return fail(MK_EINVAL, "null batch");
+    DeviceGuard guard(b->device);
+    if (!guard.ok) return fail(MK_ECUDA, "cannot select CUDA device %d", b->device);
+    if (b->own_stream) CK(cudaStreamSynchronize(b->own_stream));
+    if (b->copy_stream) CK(cudaStreamSynchronize(b->copy_stream));
+    b->host_pending = false;
+    return MK_OK;
+}
+
+static int posteriors_host(mk_batch* b, const void* ll, int64_t sb, int64_t sd, int64_t sn, int64_t D, int64_t T,
+                           int expanded, const int32_t* seqlens, void* out_post, void* out_logz, bool wait) {
     if (!b) return fail(MK_EINVAL, "null batch");
     if (!ll || !out_post || !out_logz) return fail(MK_EINVAL, "null buffer");
     if (sb < 0 || sd < 0 || sn < 0 || D <= 0 || T <= 0) return fail(MK_EINVAL, "bad strides/dims");
     DeviceGuard guard(b->device);
     if (!guard.ok) return fail(MK_ECUDA, "cannot select CUDA device %d", b->device);
+    // one call per batch at a time: the staging buffers and workspaces belong to the batch (several batches overlap)
+    if (b->host_pending) TRY(mk_batch_wait(b));
+    b->host_pending = !wait;
     const size_t ts = tsize(b->dtype);
     const int64_t Dout = expanded ? D - 1 : D, Tout = expanded ? T - 1 : T;
     const size_t in_bytes = size_t(extent(b->B, D, T, sb, sd, sn)) * ts;
@@ -1574,8 +1599,10 @@ int mk_pdfposteriors_host(mk_batch* b, const void* ll, int64_t sb, int64_t sd, i
             cudaError_t e = cudaMemcpyAsync(out_logz, b->h_logz.p, b->B * ts, cudaMemcpyDeviceToHost, st);
             if (e != cudaSuccess) rc = fail(MK_ECUDA, "cudaMemcpyAsync(logz) failed: %s", cudaGetErrorString(e));
         }
-        cudaStreamSynchronize(st);  // (also on failure: nothing may be in flight when the lambdas go out of scope)
-        cudaStreamSynchronize(sc);
+        if (wait || rc != MK_OK) {  // (the lambdas only enqueue work during dispatch; a failed call drains what it enqueued)
+            cudaStreamSynchronize(st);
+            cudaStreamSynchronize(sc);
+        }
         if (rc != MK_OK) return rc;
         CK(cudaGetLastError());
         return MK_OK;
@@ -1584,7 +1611,7 @@ int mk_pdfposteriors_host(mk_batch* b, const void* ll, int64_t sb, int64_t sd, i
     TRY(dispatch(b, MODE_POST, mkargs(b->h_ll.p, sb, sd, sn, D, T, expanded, seqlens, b->h_post.p, b->h_logz.p, st)));
     CK(cudaMemcpyAsync(out_post, b->h_post.p, post_bytes, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out_logz, b->h_logz.p, b->B * ts, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    if (wait) CK(cudaStreamSynchronize(st));
     return MK_OK;
 }
 

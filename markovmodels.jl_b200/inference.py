@@ -154,6 +154,11 @@ class BatchedFSM:
         _lib.check(_lib.lib().mk_batch_create(C.byref(h), arr, self.B))
         self._h = h
 
+    def wait(self):
+        """Complete a ``pdfposteriors(..., wait=False)`` call on this batch (``mk_batch_wait``)."""
+        _lib.check(_lib.lib().mk_batch_wait(self._h))
+        self._keep = None
+
     def workspace_bytes(self):
         return int(_lib.lib().mk_batch_workspace_bytes(self._h))
 
@@ -346,7 +351,7 @@ def _check_out(buf, shape, dtype, on_device, name):
                                                      f"{tuple(buf.shape)}{'' if ok else ' (not contiguous)'}")
 
 
-def pdfposteriors(x, V, Ĉs=None, seqlengths=None, out=None, stats=None):
+def pdfposteriors(x, V, Ĉs=None, seqlengths=None, out=None, stats=None, wait=True):
     """``pdfposteriors(fsm, V̂s, Ĉs)`` (src/inference.jl:145-161).
 
     Returns ``(post, ttl)``: ``post`` is the ``(B, D, N)`` array of pdf posteriors (exp domain,
@@ -355,7 +360,9 @@ def pdfposteriors(x, V, Ĉs=None, seqlengths=None, out=None, stats=None):
     ``(N, D, B)`` and ``(B,)`` buffers of the payload dtype (device tensors for device input,
     e.g. pinned numpy arrays for host input).  ``stats`` (device input only): a float64 CUDA tensor
     of ``D + 2`` entries that receives the data-parallel step statistics ``[Σ logZ, #frames,
-    occupancy[D]]`` (``mk_pdfposteriors_stats``; see :mod:`sharding`)."""
+    occupancy[D]]`` (``mk_pdfposteriors_stats``; see :mod:`sharding`).  ``wait=False`` (host input with
+    ``out=`` PINNED buffers only): enqueue the copies and kernels and return; ``x.wait()`` completes the call
+    (``mk_pdfposteriors_host_begin`` / ``mk_batch_wait`` — double buffering with two ``batch`` objects)."""
     B = len(V) if isinstance(V, (list, tuple)) else V.shape[0]
     b = _as_batch(x, Ĉs, B)
     e = _emissions(V, b.K, b.n_pdf_hat)
@@ -390,6 +397,13 @@ def pdfposteriors(x, V, Ĉs=None, seqlengths=None, out=None, stats=None):
     else:
         post = np.empty((To, Do, b.B), b.K.dtype)
         ttl = np.empty((b.B,), b.K.dtype)
+    if not wait:
+        if out is None:
+            raise TypeError("wait=False needs out= (pinned host buffers that outlive the call)")
+        b._keep = (e, sl, post, ttl)   # the host arrays stay referenced until wait()
+        _lib.check(l.mk_pdfposteriors_host_begin(b._h, e.ptr, *e.strides, e.D, e.T, e.expanded, _slp(sl),
+                                                 post.ctypes.data, ttl.ctypes.data))
+        return post.transpose(2, 1, 0), ttl
     _lib.check(l.mk_pdfposteriors_host(b._h, e.ptr, *e.strides, e.D, e.T, e.expanded, _slp(sl),
                                        post.ctypes.data, ttl.ctypes.data))
     return post.transpose(2, 1, 0), ttl

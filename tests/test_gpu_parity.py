@@ -549,6 +549,30 @@ def test_host_pipeline_matches_single_launch(torch, mm, orc, dtype):
     np.testing.assert_allclose(out["0"][0], dpost.cpu().numpy(), rtol=rt, atol=1e-9)
 
 
+def test_host_calls_overlap_across_batches(torch, mm, orc):
+    """mk_pdfposteriors_host_begin / mk_batch_wait: two batch objects (one graph) keep a call each in flight, on pinned
+    host buffers; same results as the blocking call, and a second begin on a busy batch waits for the first."""
+    K = mm.LogSemiring[np.float32]
+    rng = np.random.default_rng(91)
+    B, T, D = 8, 64, 100
+    g = mm.graphs.denominator(K, n_tokens=600, n_pdf=D, seed=8)
+    bs = [gpu_batch(mm, [g] * B, D, "shared") for _ in range(2)]
+    Vs = [torch.from_numpy((rng.standard_normal((B, T, D)) * 2).astype(np.float32)).pin_memory() for _ in range(3)]
+    outs = [(torch.empty((T, D, B)).pin_memory(), torch.empty((B,)).pin_memory()) for _ in range(3)]
+    with pytest.raises(TypeError):
+        mm.pdfposteriors(bs[0], Vs[0].numpy().transpose(0, 2, 1), wait=False)   # needs out=
+    for k in range(3):   # k = 2 reuses batch 0 while its first call may still run: the library waits for it
+        mm.pdfposteriors(bs[k & 1], Vs[k].numpy().transpose(0, 2, 1), out=(outs[k][0].numpy(), outs[k][1].numpy()), wait=False)
+    bs[0].wait(); bs[1].wait()
+    for k in range(3):
+        post, ttl = mm.pdfposteriors(bs[0], Vs[k].numpy().transpose(0, 2, 1))   # blocking call, library-owned outputs
+        # (the per-pdf sums are float atomics: their order, hence the last bits, differ from run to run)
+        np.testing.assert_allclose(outs[k][1].numpy(), np.asarray(ttl), rtol=1e-6)
+        np.testing.assert_allclose(outs[k][0].numpy().transpose(2, 1, 0), np.asarray(post), rtol=1e-5, atol=1e-9)
+    check_posteriors(mm, orc, [g] * B, D, Vs[2].numpy(), np.full(B, T, np.int32), outs[2][0].numpy().transpose(2, 1, 0),
+                     outs[2][1].numpy(), np.float32)
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("order", ["sorted", "shuffled"])
 def test_ragged_tiles_stop_early(torch, mm, orc, dtype, order):
