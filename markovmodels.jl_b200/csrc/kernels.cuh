@@ -214,6 +214,17 @@ template <int SR, typename T> __device__ __forceinline__ T lin_add(T a, T b) {
     return SR == SR_LOG ? a + b : max_(a, b);
 }
 
+// CTA barrier that does not require the warps to arrive converged (barrier.sync without .aligned): used after the
+// tile loops, where the lanes beyond a partial utterance tile skip the work of the live lanes.
+__device__ __forceinline__ void cta_sync_unaligned() {
+    asm volatile("barrier.sync 0;" ::: "memory");
+    // ... and the lanes leave it together: the aligned barriers that follow (__syncthreads in the scalar phase and in
+    // grid_sync) need converged warps.  (A plain __syncwarp() here is elided by the compiler, which takes the
+    // reconvergence point after the divergent block for granted; compute-sanitizer --tool synccheck showed the lanes
+    // of a partial tile arriving at the next __syncthreads one by one.)
+    asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
+}
+
 // ---- grid barrier ------------------------------------------------------------------------------
 // Monotonic counter; the kernel is launched cooperatively (all CTAs co-resident).  Writers'
 // stores are ordered by bar.sync + fence + the atomic; the waiting thread uses an acquire load
@@ -1094,8 +1105,9 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
 #pragma unroll
                     for (int j = 0; j < 4; ++j) atomicMax(&s_key[uoff + j], fkey(float(fin.mx[j])));
                 }
+                __syncwarp();
             }
-            __syncthreads();
+            cta_sync_unaligned();
             for (int u = threadIdx.x; u < U4; u += blockDim.x) {
                 int k = s_key[u];
                 if (k != kKeyMin) atomicMax(p.gkey + size_t(n) * U4 + u, k);
@@ -1199,8 +1211,9 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
                     }
                 }
             }
+            __syncwarp();
         }
-        __syncthreads();
+        cta_sync_unaligned();
         for (int u = threadIdx.x; u < U4; u += blockDim.x) {
             int k = s_key[u];
             if (k != kKeyMin) atomicMax(gkey_b + size_t(n) * U4 + u, k);

@@ -1556,7 +1556,10 @@ static int posteriors_host(mk_batch* b, const void* ll, int64_t sb, int64_t sd, 
     // Pipeline: when the whole batch is one shared-graph group and the emissions are [b][t][d] rows, the call is
     // cut into frame segments; the copy stream brings slice k+1 in while the forward sweep runs slice k, and
     // takes the posteriors of segment k out while the backward sweep runs segment k-1.  MK_NO_PIPELINE=1 disables.
-    int K = int(std::min<int64_t>(12, T / 8));  // (measured on the 128 x 150 x 3000 call: 8 segments 9.9 ms, 12 9.7 ms, 16 9.7 ms)
+    // Segments: a lone blocking call wants many (the un-overlapped first copy in and last copy out shrink: 8 segments
+    // 9.78 ms, 12 9.59 ms on the 128 x 150 x 3000 call); calls that overlap each other want few (fewer launches, the
+    // neighbour call hides head and tail: 2 segments 8.36 ms, 4 8.27 ms, 12 8.53 ms per step, double-buffered)
+    int K = int(std::min<int64_t>(wait ? 12 : 4, T / 8));
     if (getenv("MK_SEGMENTS") && atoi(getenv("MK_SEGMENTS")) >= 1) K = std::min(K, atoi(getenv("MK_SEGMENTS")));  // (tuning)
     const bool pipe = b->groups.size() == 1 && b->small.empty() && !expanded && sd == 1 && sn == D && sb == T * D &&
                       K >= 2 && !(getenv("MK_NO_PIPELINE") && atoi(getenv("MK_NO_PIPELINE")));
