@@ -196,6 +196,30 @@ int mk_spvec_bcast(int semiring, int dtype, int op, int64_t n, int64_t nnz, cons
                    const void* nzval, int index_base, const void* y, int64_t len_y, void* dest,
                    int64_t len_dest, void* stream);
 
+/* ---- Graph preparation at the operator level (src/linalg.jl:12-157), DEVICE arrays, asynchronous on `stream` unless
+ * noted.  The payload is opaque (dtype gives the element size): these operators move semiring values, never combine
+ * them, so they serve Log / Tropical / Prob alike (test/test_linalg.jl:1-32, 56-86 instantiate all three).
+ *
+ * mk_blockdiag — SparseArrays.blockdiag(X::CuSparseMatrixCSC{K}...) (src/linalg.jl:73-100) and the CSR method
+ *   (:102-131): block i is (ptr[i] [dim_ptr[i] + 1], idx[i], val[i]) with dim_ptr = columns for CSC / rows for CSR
+ *   and dim_idx the other dimension; out_ptr has Σ dim_ptr + 1 entries, out_idx / out_val Σ nnz.  ptr / idx / val /
+ *   dim_* / nnz are HOST arrays (of device pointers / sizes).  One launch for all blocks (the reference: three copies
+ *   per block).
+ * mk_vcat_spvec — Base.vcat(X::CuSparseVector{K}...) (src/linalg.jl:137-157): nzind shifted by the lengths so far.
+ * mk_sparse_transpose — the CSC <-> CSR conversions and copy(transpose(M)) / copy(M') (src/linalg.jl:12-67), which
+ *   the reference delegates to CUSPARSE csr2csc: the arrays (ptr [n_ptr + 1], idx, val) of a matrix compressed along
+ *   its first-named dimension become the arrays compressed along the other one (out_ptr [n_idx + 1]), indices
+ *   ascending inside every output segment.  CSR(A) -> CSC(A), CSC(A) -> CSR(A), and — reading the result with the
+ *   roles swapped — CSR(A) -> CSR(Aᵀ). */
+int mk_blockdiag(int dtype, int64_t n_mats, const int32_t* const* ptr, const int32_t* const* idx,
+                 const void* const* val, const int64_t* dim_ptr, const int64_t* dim_idx, const int64_t* nnz,
+                 int index_base, int32_t* out_ptr, int32_t* out_idx, void* out_val, void* stream);
+int mk_vcat_spvec(int dtype, int64_t n_vecs, const int32_t* const* nzind, const void* const* nzval,
+                  const int64_t* len, const int64_t* nnz, int32_t* out_ind, void* out_val, void* stream);
+int mk_sparse_transpose(int dtype, int64_t n_ptr, int64_t n_idx, int64_t nnz, const int32_t* ptr,
+                        const int32_t* idx, const void* val, int index_base, int32_t* out_ptr,
+                        int32_t* out_idx, void* out_val, void* stream);
+
 /* ---- Multi-GPU: the path shards by utterance (block-diagonal batch, src/fsmops.jl:28-36); the only
  * exchange is ONE sum all-reduce per step of the mk_pdfposteriors_stats vector.  NCCL is
  * bound at run time (dlopen of MK_NCCL_LIB / libnccl.so.2: the copy a CUDA.jl or PyTorch process already

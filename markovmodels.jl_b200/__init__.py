@@ -14,7 +14,8 @@ from .inference import (BatchedFSM, CompiledFSM, StateMap, alpha_recursion, batc
 from .semirings import LogSemiring, ProbSemiring, TropicalSemiring  # noqa: F401
 from . import algorithms, graphs, lfmmi, linalg, sharding  # noqa: F401
 from .algorithms import totalcumsum, totalsum, totalweightsum  # noqa: F401
-from .linalg import CuSparseMatrixCSR, CuSparseVector, eldiv_, elmul_, mul_  # noqa: F401
+from .linalg import (CuSparseMatrixCSC, CuSparseMatrixCSR, CuSparseVector, blockdiag, copy_transpose,  # noqa: F401
+                     csr_from_csc, eldiv_, elmul_, mul_, vcat)
 from .lfmmi import lfmmi_grad, lfmmi_loss  # noqa: F401
 
 __version__ = "0.1.0"

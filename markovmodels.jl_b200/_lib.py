@@ -43,23 +43,39 @@ def _stale():
     return any(os.path.getmtime(s) > t for s in srcs)
 
 
+SOURCES = ["markov_b200.cu", "prep.cu"]
+
+
 def build(force=False, verbose=False):
     """Compile ``csrc/*.cu`` for sm_100a into ``csrc/libmarkov_b200.so`` (nvcc cross-compiles
-    without a GPU)."""
+    without a GPU): one object per translation unit, compiled side by side, then linked."""
     if not force and not _stale():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "markov_b200.cu")]
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
     for knob in ("MK_PASS_QUADS", "MK_THREADS", "MK_PROFILE_BARRIER", "MK_ABLATE", "MK_SPMM_CJ", "MK_SPMM_STCS", "MK_L2_HINTS"):  # kernel tuning knobs (defaults in kernels.cuh)
         if os.environ.get(knob):
-            cmd.insert(1, f"-D{knob}={os.environ[knob]}")
+            flags.insert(0, f"-D{knob}={os.environ[knob]}")
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        flags.insert(0, "-Xptxas=-v")
+    tag = os.path.splitext(os.path.basename(LIB_PATH))[0]
+
+    def compile_one(src):
+        obj = os.path.join(CSRC, f"{tag}.{os.path.splitext(src)[0]}.o")
+        res = subprocess.run([nvcc] + flags + ["-c", "-o", obj, os.path.join(CSRC, src)], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(len(SOURCES)) as pool:
+        done = list(pool.map(compile_one, SOURCES))
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + [o for o, _ in done],
+                         capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc (link) failed:\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stderr)
+        print("".join(err for _, err in done))
     return LIB_PATH
 
 
@@ -116,6 +132,10 @@ SIGNATURES = {
     "mk_allreduce_stats": (C.c_int, [_vp, _vp, _i64, _vp]),
     "mk_allreduce_stats_all": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), C.c_int, _i64, C.POINTER(_vp)]),
     "mk_comm_destroy": (C.c_int, [_vp]),
+    "mk_blockdiag": (C.c_int, [C.c_int, _i64, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64),
+                               C.POINTER(_i64), C.POINTER(_i64), C.c_int, _vp, _vp, _vp, _vp]),
+    "mk_vcat_spvec": (C.c_int, [C.c_int, _i64, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64), _vp, _vp, _vp]),
+    "mk_sparse_transpose": (C.c_int, [C.c_int, _i64, _i64, _i64, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
     "mk_launch_count": (_i64, [C.c_int]),
     "mk_batch_workspace_bytes": (_i64, [_vp]),
     "mk_batch_profile": (C.c_int, [_vp, C.c_int]),

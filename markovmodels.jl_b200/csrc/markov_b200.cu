@@ -43,6 +43,16 @@ static int fail(int code, const char* fmt, ...) {
     g_err = buf;
     return code;
 }
+// the same for the other translation units of the library (prep.cu)
+int mk_set_error(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    return fail(code, "%s", buf);
+}
+void mk_note_launches(int n) { g_launches += n; }
 #define CK(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \

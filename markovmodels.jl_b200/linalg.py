@@ -7,6 +7,10 @@
     mul_(c, A, b)                           ``mul!(c, A, b)``            src/linalg.jl:163-184
     mul_(C, A, B, α, β)                     ``mul!(C, A, B, α, β)``      src/linalg.jl:240-262
     elmul_(out, x, y) / eldiv_(out, x, y)   sparse-vector broadcasts     src/linalg.jl:287-338
+    blockdiag(A, B, ...)                    ``blockdiag(X::CuSparseMatrixCSR...)`` / ``CSC...``   src/linalg.jl:73-131
+    vcat(x, y, ...)                         ``vcat(X::CuSparseVector...)``                        src/linalg.jl:137-157
+    CuSparseMatrixCSC(A) / CuSparseMatrixCSR(A)   the conversions                                 src/linalg.jl:12-49
+    copy_transpose(A)                       ``copy(transpose(A))`` / ``copy(A')``                 src/linalg.jl:55-67
 
 (``!`` is not an identifier character in Python, hence the trailing underscore.)  Arrays are torch
 CUDA tensors of payload floats; matrices are column-major like Julia's (``colmajor`` allocates one;
@@ -78,6 +82,130 @@ class CuSparseMatrixCSR:
 
     def size(self, d=None):
         return self.shape if d is None else self.shape[d - 1]
+
+    @classmethod
+    def from_arrays(cls, K, rowPtr, colVal, nzVal, m, n):
+        """Wrap existing device arrays (1-based ``Cint`` indices) without copying."""
+        A = cls.__new__(cls)
+        A.K, A.shape, A.rowPtr, A.colVal, A.nzVal = K, (int(m), int(n)), rowPtr, colVal, nzVal
+        return A
+
+    def to_scipy(self):
+        """Host copy as a scipy CSR matrix of payload floats (tests)."""
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.nzVal.cpu().numpy(), self.colVal.cpu().numpy() - 1, self.rowPtr.cpu().numpy() - 1),
+                             shape=self.shape)
+
+
+class CuSparseMatrixCSC:
+    """``CuSparseMatrixCSC{K}``: ``colPtr`` (n+1), ``rowVal`` (nnz), ``nzVal`` (nnz), 1-based ``Cint`` indices.
+    ``CuSparseMatrixCSC(A::CuSparseMatrixCSR)`` converts (src/linalg.jl:32-49); ``CuSparseMatrixCSC(K, I, J, V, m, n)``
+    is ``adapt(CuArray, sparse(I, J, V, m, n))``."""
+
+    def __init__(self, K, *args, device="cuda"):
+        if isinstance(K, CuSparseMatrixCSR):   # conversion
+            A = K
+            ptr, idx, val = _sparse_transpose(A.K, A.rowPtr, A.colVal, A.nzVal, A.shape[0], A.shape[1])
+            self.K, self.shape, self.colPtr, self.rowVal, self.nzVal = A.K, A.shape, ptr, idx, val
+            return
+        I, J, V, m, n = args  # noqa: E741
+        t = CuSparseMatrixCSR(K, J, I, V, n, m, device=device)   # CSC(A) holds the arrays of CSR(Aᵀ)
+        self.K, self.shape, self.colPtr, self.rowVal, self.nzVal = K, (int(m), int(n)), t.rowPtr, t.colVal, t.nzVal
+
+    @property
+    def nnz(self):
+        return int(self.nzVal.numel())
+
+    def size(self, d=None):
+        return self.shape if d is None else self.shape[d - 1]
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csc_matrix((self.nzVal.cpu().numpy(), self.rowVal.cpu().numpy() - 1, self.colPtr.cpu().numpy() - 1),
+                             shape=self.shape)
+
+
+def _sparse_transpose(K, ptr, idx, val, n_ptr, n_idx):
+    torch = _torch()
+    out_ptr = torch.empty(n_idx + 1, dtype=torch.int32, device=val.device)
+    out_idx = torch.empty_like(idx)
+    out_val = torch.empty_like(val)
+    _lib.check(_lib.lib().mk_sparse_transpose(K.dtype_code, n_ptr, n_idx, int(val.numel()), ptr.data_ptr(), idx.data_ptr(),
+                                              val.data_ptr(), 1, out_ptr.data_ptr(), out_idx.data_ptr(), out_val.data_ptr(),
+                                              _stream()))
+    return out_ptr, out_idx, out_val
+
+
+def csr_from_csc(A):
+    """``CuSparseMatrixCSR(A::CuSparseMatrixCSC)`` (src/linalg.jl:12-30)."""
+    ptr, idx, val = _sparse_transpose(A.K, A.colPtr, A.rowVal, A.nzVal, A.shape[1], A.shape[0])
+    return CuSparseMatrixCSR.from_arrays(A.K, ptr, idx, val, *A.shape)
+
+
+def copy_transpose(A):
+    """``copy(transpose(A))`` / ``copy(A')`` (src/linalg.jl:55-67): the materialised transpose, same storage kind.
+    As in the reference, the arrays of CSR(A) are read as CSC(Aᵀ) and converted back."""
+    m, n = A.shape
+    if isinstance(A, CuSparseMatrixCSR):
+        ptr, idx, val = _sparse_transpose(A.K, A.rowPtr, A.colVal, A.nzVal, m, n)
+        return CuSparseMatrixCSR.from_arrays(A.K, ptr, idx, val, n, m)
+    ptr, idx, val = _sparse_transpose(A.K, A.colPtr, A.rowVal, A.nzVal, n, m)
+    T = CuSparseMatrixCSC.__new__(CuSparseMatrixCSC)
+    T.K, T.shape, T.colPtr, T.rowVal, T.nzVal = A.K, (n, m), ptr, idx, val
+    return T
+
+
+def blockdiag(*Ms):
+    """``blockdiag(X::CuSparseMatrixCSR{K}...)`` / ``blockdiag(X::CuSparseMatrixCSC{K}...)`` (src/linalg.jl:73-131)."""
+    import ctypes as C
+    torch = _torch()
+    if not Ms:
+        raise ValueError("blockdiag needs at least one matrix")
+    csr = isinstance(Ms[0], CuSparseMatrixCSR)
+    if any(isinstance(M, CuSparseMatrixCSR) != csr or M.K is not Ms[0].K for M in Ms):
+        raise TypeError("blockdiag: all blocks must share storage kind and semiring")
+    K, k = Ms[0].K, len(Ms)
+    ptrs = [(M.rowPtr if csr else M.colPtr) for M in Ms]
+    idxs = [(M.colVal if csr else M.rowVal) for M in Ms]
+    dim_p = [M.shape[0 if csr else 1] for M in Ms]
+    dim_i = [M.shape[1 if csr else 0] for M in Ms]
+    nnz = [M.nnz for M in Ms]
+    dev = Ms[0].nzVal.device
+    out_ptr = torch.empty(sum(dim_p) + 1, dtype=torch.int32, device=dev)
+    out_idx = torch.empty(sum(nnz), dtype=torch.int32, device=dev)
+    out_val = torch.empty(sum(nnz), dtype=_tdtype(K), device=dev)
+    vp, i64 = C.c_void_p * k, C.c_int64 * k
+    _lib.check(_lib.lib().mk_blockdiag(K.dtype_code, k, vp(*[t.data_ptr() for t in ptrs]), vp(*[t.data_ptr() for t in idxs]),
+                                       vp(*[M.nzVal.data_ptr() for M in Ms]), i64(*dim_p), i64(*dim_i), i64(*nnz), 1,
+                                       out_ptr.data_ptr(), out_idx.data_ptr(), out_val.data_ptr(), _stream()))
+    m, n = sum(M.shape[0] for M in Ms), sum(M.shape[1] for M in Ms)
+    if csr:
+        return CuSparseMatrixCSR.from_arrays(K, out_ptr, out_idx, out_val, m, n)
+    R = CuSparseMatrixCSC.__new__(CuSparseMatrixCSC)
+    R.K, R.shape, R.colPtr, R.rowVal, R.nzVal = K, (m, n), out_ptr, out_idx, out_val
+    return R
+
+
+def vcat(*xs):
+    """``vcat(X::CuSparseVector{K}...)`` (src/linalg.jl:137-157)."""
+    import ctypes as C
+    torch = _torch()
+    if not xs:
+        raise ValueError("vcat needs at least one vector")
+    K, k = xs[0].K, len(xs)
+    if any(x.K is not K for x in xs):
+        raise TypeError("vcat: all vectors must share the semiring")
+    nnz = [int(x.nzVal.numel()) for x in xs]
+    dev = xs[0].nzVal.device
+    out_ind = torch.empty(sum(nnz), dtype=torch.int32, device=dev)
+    out_val = torch.empty(sum(nnz), dtype=_tdtype(K), device=dev)
+    vp, i64 = C.c_void_p * k, C.c_int64 * k
+    _lib.check(_lib.lib().mk_vcat_spvec(K.dtype_code, k, vp(*[x.nzInd.data_ptr() for x in xs]),
+                                        vp(*[x.nzVal.data_ptr() for x in xs]), i64(*[x.n for x in xs]), i64(*nnz),
+                                        out_ind.data_ptr(), out_val.data_ptr(), _stream()))
+    r = CuSparseVector.__new__(CuSparseVector)
+    r.K, r.n, r.nzInd, r.nzVal = K, sum(x.n for x in xs), out_ind, out_val
+    return r
 
 
 class CuSparseVector:

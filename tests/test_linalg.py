@@ -284,3 +284,119 @@ def test_csr_constructor_host_logic(mm):
     np.testing.assert_array_equal(E.rowPtr.numpy(), [1, 1, 1, 1])
     with pytest.raises(IndexError):
         mm.CuSparseMatrixCSR(mm.LogSemiring[np.float32], [4], [1], [0.0], 3, 2, device="cpu")
+
+
+# ---- graph preparation: vcat / blockdiag / CSC <-> CSR / copy(transpose)  (test/test_linalg.jl:1-32, 56-86) ----------
+SEMIRINGS = ["LogSemiring", "ProbSemiring", "TropicalSemiring"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pK", SEMIRINGS)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_vcat_sparse_vectors(mm, pK, dtype):
+    """test/test_linalg.jl:1-14: vcat(cu_sv, cu_sv) against the CPU vcat of sparsevec([1, 3], K[0.1, 0.2], 3)."""
+    K = getattr(mm, pK)[dtype]
+    sv = mm.CuSparseVector(K, [1, 3], [0.1, 0.2], 3)
+    r = mm.vcat(sv, sv)
+    assert isinstance(r, mm.CuSparseVector) and r.n == 6
+    np.testing.assert_array_equal(r.nzInd.cpu().numpy(), [1, 3, 4, 6])
+    np.testing.assert_array_equal(r.nzVal.cpu().numpy(), np.asarray([0.1, 0.2, 0.1, 0.2], dtype))
+    # ragged: different lengths and an empty vector in the middle
+    a = mm.CuSparseVector(K, [2, 5], [1.5, -2.0], 5)
+    e = mm.CuSparseVector(K, [], [], 4)
+    b = mm.CuSparseVector(K, [1], [7.0], 2)
+    r = mm.vcat(a, e, b)
+    assert r.n == 11
+    np.testing.assert_array_equal(r.nzInd.cpu().numpy(), [2, 5, 10])
+    np.testing.assert_array_equal(r.nzVal.cpu().numpy(), np.asarray([1.5, -2.0, 7.0], dtype))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pK", SEMIRINGS)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_blockdiag(mm, pK, dtype):
+    """test/test_linalg.jl:16-32: blockdiag of three copies of sparse([1, 2, 2], [3, 2, 3], K[1, 2, 3], 3, 3), CSC and CSR,
+    against scipy's block_diag; plus ragged shapes with an all-zero block."""
+    import scipy.sparse as sp
+    K = getattr(mm, pK)[dtype]
+    I, J, V = [1, 2, 2], [3, 2, 3], [1.0, 2.0, 3.0]  # noqa: E741
+    csr = mm.CuSparseMatrixCSR(K, I, J, V, 3, 3)
+    csc = mm.CuSparseMatrixCSC(K, I, J, V, 3, 3)
+    want = sp.block_diag([csr.to_scipy()] * 3).toarray()
+    for blk in (csr, csc):
+        r = mm.blockdiag(blk, blk, blk)
+        assert type(r) is type(blk) and r.shape == (9, 9) and r.nnz == 9
+        np.testing.assert_array_equal(r.to_scipy().toarray(), want)
+    a = mm.CuSparseMatrixCSR(K, [1, 2, 2, 3, 4], [3, 1, 2, 1, 3], [1.0, 2.0, 3.0, 4.0, 5.0], 4, 3)
+    z = mm.CuSparseMatrixCSR(K, [], [], [], 2, 5)
+    b = mm.CuSparseMatrixCSR(K, [1], [2], [9.0], 1, 2)
+    r = mm.blockdiag(a, z, b)
+    assert r.shape == (7, 10)
+    np.testing.assert_array_equal(r.to_scipy().toarray(), sp.block_diag([a.to_scipy(), z.to_scipy(), b.to_scipy()]).toarray())
+    with pytest.raises(TypeError):
+        mm.blockdiag(csr, csc)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pK", SEMIRINGS)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_csc_csr_conversion_and_transpose(mm, pK, dtype):
+    """test/test_linalg.jl:56-86: CSC -> CSR -> CSC round trip and copy(transpose) of both storage kinds, on
+    sparse([1, 2, 2, 3, 4], [3, 1, 2, 1, 3], K[1, 2, 3, 4, 5], 4, 3)."""
+    K = getattr(mm, pK)[dtype]
+    I, J, V = [1, 2, 2, 3, 4], [3, 1, 2, 1, 3], [1.0, 2.0, 3.0, 4.0, 5.0]  # noqa: E741
+    csc = mm.CuSparseMatrixCSC(K, I, J, V, 4, 3)
+    dense = csc.to_scipy().toarray()
+    csr = mm.csr_from_csc(csc)
+    np.testing.assert_array_equal(csr.to_scipy().toarray(), dense)
+    back = mm.CuSparseMatrixCSC(csr)
+    np.testing.assert_array_equal(back.to_scipy().toarray(), dense)
+    for k in ("colPtr", "rowVal", "nzVal"):   # canonical arrays: the round trip is the identity
+        np.testing.assert_array_equal(getattr(back, k).cpu().numpy(), getattr(csc, k).cpu().numpy())
+    for M in (csc, csr):
+        t = mm.copy_transpose(M)
+        assert type(t) is type(M) and t.shape == (3, 4)
+        np.testing.assert_array_equal(t.to_scipy().toarray(), dense.T)
+    # indices come out ascending inside every segment (what CUSPARSE csr2csc gives the reference)
+    t = mm.copy_transpose(csr)
+    rp, cv = t.rowPtr.cpu().numpy() - 1, t.colVal.cpu().numpy()
+    assert all(np.all(np.diff(cv[rp[r]:rp[r + 1]]) > 0) for r in range(3))
+
+
+@pytest.mark.gpu
+def test_transpose_of_a_graph_sized_matrix_feeds_mul(mm, orc):
+    """The reference prepares T̂ᵀ with copy(T̂') (src/inference.jl:12) and multiplies with it: do the same on the synthetic
+    denominator graph (empty rows, a 9 000-arc column) and check mul! on the materialised transpose against the oracle."""
+    import torch
+    K = mm.LogSemiring[np.float32]
+    den, _ = mm.graphs.denominator(K, n_tokens=2000, n_pdf=100, seed=4)
+    src, dst, w = den.arcs_hat()
+    S = den.nstates_hat
+    T = mm.CuSparseMatrixCSR(K, src + 1, dst + 1, w, S, S)      # T̂: rows = sources
+    Tt = mm.copy_transpose(T)                                    # T̂ᵀ: rows = destinations
+    ref = mm.CuSparseMatrixCSR(K, dst + 1, src + 1, w, S, S)
+    for k in ("rowPtr", "colVal", "nzVal"):
+        np.testing.assert_array_equal(getattr(Tt, k).cpu().numpy(), getattr(ref, k).cpu().numpy())
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(S).astype(np.float32)
+    got = mm.mul_(torch.empty(S, dtype=torch.float32, device="cuda"), Tt, torch.from_numpy(x).cuda())
+    order = np.lexsort((src, dst))
+    rowptr = np.concatenate(([0], np.cumsum(np.bincount(dst, minlength=S))))
+    want = orc.spmv(K.code, rowptr, src[order], w[order].astype(np.float64), x.astype(np.float64))
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+
+
+def test_prep_operators_reject_bad_arguments(mm):
+    """No GPU needed: argument validation of the graph-preparation exports."""
+    import ctypes as C
+    from markov_b200 import _lib
+    l = mm.lib()
+    assert l.mk_vcat_spvec(7, 0, None, None, None, None, None, None, None) == _lib.MK_EINVAL       # dtype
+    assert l.mk_vcat_spvec(0, 2, None, None, None, None, None, None, None) == _lib.MK_EINVAL       # null tables
+    assert l.mk_sparse_transpose(0, -1, 3, 0, None, None, None, 1, None, None, None, None) == _lib.MK_EINVAL
+    one = (C.c_int64 * 1)(3)
+    neg = (C.c_int64 * 1)(-1)
+    p = (C.c_void_p * 1)(8)
+    out = C.c_void_p(8)
+    assert l.mk_blockdiag(0, 1, p, p, p, one, one, neg, 1, out, out, out, None) == _lib.MK_EINVAL  # negative nnz
+    assert l.mk_blockdiag(0, 1, p, p, p, one, one, one, 2, out, out, out, None) == _lib.MK_EINVAL  # index_base
