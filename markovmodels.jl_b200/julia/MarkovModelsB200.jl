@@ -82,6 +82,65 @@ function pdfposteriors(b::B200Batch{K}, V̂s::Vector{<:CuMatrix{K}}) where K
     post, ttl
 end
 
+# The same call with the statistics a data-parallel step exchanges (the accumulation the caller of
+# examples/test_cuda.jl:140-152 does on the host): stats = [Σ logZ, #frames, occupancy[1:D]] (Float64, device)
+function pdfposteriors_stats(b::B200Batch{K}, V̂s::Vector{<:CuMatrix{K}}) where K
+    T = payload(K)
+    V̂ = vcat(V̂s...)
+    B, D̂, N̂ = length(V̂s), size(V̂s[1], 1), size(V̂s[1], 2)
+    post = CUDA.zeros(T, B, D̂ - 1, N̂ - 1)
+    ttl = CUDA.zeros(T, B)
+    stats = CUDA.zeros(Float64, D̂ + 1)
+    check(ccall((:mk_pdfposteriors_stats, LIB), Cint,
+                (Ptr{Cvoid}, CuPtr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Cint, Ptr{Cint},
+                 CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Float64}, Ptr{Cvoid}),
+                b.handle, pointer(V̂), D̂, 1, B * D̂, D̂, N̂, 1, C_NULL,
+                pointer(post), pointer(ttl), pointer(stats), CUDA.stream().handle))
+    post, ttl, stats
+end
+
+# ---- multi-GPU: the batch shards by utterance; ONE sum all-reduce of `stats` per step -------------------
+# One process per GPU (e.g. under MPI.jl): rank 0 creates the NCCL id, everybody gets it, everybody joins.
+mutable struct B200Comm
+    handle::Ptr{Cvoid}
+end
+function unique_id()
+    id = zeros(UInt8, 128)
+    check(ccall((:mk_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id))
+    id
+end
+function B200Comm(nranks::Integer, rank::Integer, id::Vector{UInt8}; device::Integer = -1)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:mk_comm_init_rank, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Cint, Ptr{UInt8}, Cint), h, nranks, rank, id, device))
+    finalizer(x -> ccall((:mk_comm_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle), B200Comm(h[]))
+end
+# one process driving n GPUs: one communicator per device 0..n-1
+function B200Comm(n_gpus::Integer)
+    hs = Vector{Ptr{Cvoid}}(undef, n_gpus)
+    check(ccall((:mk_comm_init, LIB), Cint, (Ptr{Ptr{Cvoid}}, Cint), hs, n_gpus))
+    [finalizer(x -> ccall((:mk_comm_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle), B200Comm(h)) for h in hs]
+end
+function allreduce!(c::B200Comm, stats::CuVector{Float64})
+    check(ccall((:mk_allreduce_stats, LIB), Cint, (Ptr{Cvoid}, CuPtr{Float64}, Int64, Ptr{Cvoid}),
+                c.handle, pointer(stats), length(stats), CUDA.stream().handle))
+    stats
+end
+
+# ---- CPU arrays in, CPU arrays out (the reference's CPU FSM path), optionally overlapped --------------------
+# pdfposteriors on host matrices (un-expanded D x N per utterance, stacked (B, D, N) b-fastest in `lhs`); with
+# wait = false the call returns after enqueueing its copies and kernels: keep `lhs` / the outputs alive and pinned
+# (CUDA.pin) until wait(b).  Two batches built from the same compiled graph overlap each other's copies.
+function pdfposteriors_host!(post::Array{T,3}, ttl::Vector{T}, b::B200Batch{K}, lhs::Array{T,3},
+                             seqlengths::Vector{<:Integer}; wait::Bool = true) where {K,T}
+    B, D, N = size(lhs)
+    fn = wait ? :mk_pdfposteriors_host : :mk_pdfposteriors_host_begin
+    check(ccall((fn, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Cint, Ptr{Cint}, Ptr{Cvoid}, Ptr{Cvoid}),
+                b.handle, lhs, 1, B, B * D, D, N, 0, Cint.(seqlengths), post, ttl))
+    post, ttl
+end
+Base.wait(b::B200Batch) = check(ccall((:mk_batch_wait, LIB), Cint, (Ptr{Cvoid},), b.handle))
+
 # αrecursion / βrecursion (src/inference.jl:62-74, 99-110): (ΣŜ) x N̂ CuMatrix{K}
 for (fn, sym) in ((:αrecursion, :mk_alpha), (:βrecursion, :mk_beta))
     @eval function $fn(b::B200Batch{K}, V̂s::Vector{<:CuMatrix{K}}) where K
@@ -154,6 +213,76 @@ function _copyto!(f::Union{typeof(*), typeof(/)}, dest::CuArray{K}, x::CuSparseV
                 pointer(nzInd), pointer(nzVal), 1, pointer(y), length(y), pointer(dest), length(dest),
                 CUDA.stream().handle))
     dest
+end
+
+# ---- graph preparation: REPLACE the bodies of src/linalg.jl:12-157 ---------------------------------------------
+using CUDA.CUSPARSE: CuSparseMatrixCSC
+
+function _transpose_arrays(::Type{K}, ptr, idx, val, n_ptr, n_idx) where K
+    out_ptr, out_idx, out_val = CuVector{Cint}(undef, n_idx + 1), similar(idx), similar(val)
+    check(ccall((:mk_sparse_transpose, LIB), Cint,
+                (Cint, Int64, Int64, Int64, CuPtr{Cint}, CuPtr{Cint}, CuPtr{Cvoid}, Cint, CuPtr{Cint}, CuPtr{Cint},
+                 CuPtr{Cvoid}, Ptr{Cvoid}),
+                dtype_code(payload(K)), n_ptr, n_idx, length(val), pointer(ptr), pointer(idx), pointer(val), 1,
+                pointer(out_ptr), pointer(out_idx), pointer(out_val), CUDA.stream().handle))
+    out_ptr, out_idx, out_val
+end
+# CuSparseMatrixCSR(::CuSparseMatrixCSC) and back (src/linalg.jl:12-49)
+function CUDA.CUSPARSE.CuSparseMatrixCSR(M::CuSparseMatrixCSC{K}) where K <: Semiring
+    CuSparseMatrixCSR{K}(_transpose_arrays(K, M.colPtr, M.rowVal, M.nzVal, size(M, 2), size(M, 1))..., M.dims)
+end
+function CUDA.CUSPARSE.CuSparseMatrixCSC(M::CuSparseMatrixCSR{K}) where K <: Semiring
+    CuSparseMatrixCSC{K}(_transpose_arrays(K, M.rowPtr, M.colVal, M.nzVal, size(M, 1), size(M, 2))..., M.dims)
+end
+# copy(M') / copy(transpose(M)) (src/linalg.jl:55-67)
+function Base.copy(Mᵀ::Union{LinearAlgebra.Adjoint{K, <:CuSparseMatrixCSR}, LinearAlgebra.Transpose{K, <:CuSparseMatrixCSR}}) where K <: Semiring
+    M = parent(Mᵀ)
+    CuSparseMatrixCSR{K}(_transpose_arrays(K, M.rowPtr, M.colVal, M.nzVal, size(M, 1), size(M, 2))..., reverse(M.dims))
+end
+function Base.copy(Mᵀ::Union{LinearAlgebra.Adjoint{K, <:CuSparseMatrixCSC}, LinearAlgebra.Transpose{K, <:CuSparseMatrixCSC}}) where K <: Semiring
+    M = parent(Mᵀ)
+    CuSparseMatrixCSC{K}(_transpose_arrays(K, M.colPtr, M.rowVal, M.nzVal, size(M, 2), size(M, 1))..., reverse(M.dims))
+end
+
+# blockdiag (src/linalg.jl:73-131): one launch for all blocks instead of three copies per block
+function _blockdiag(::Type{K}, ptrs, idxs, vals, dim_ptr, dim_idx) where K
+    nnzs = Int64[length(v) for v in vals]
+    out_ptr = CuVector{Cint}(undef, sum(dim_ptr) + 1)
+    out_idx = CuVector{Cint}(undef, sum(nnzs))
+    out_val = CuVector{K}(undef, sum(nnzs))
+    GC.@preserve ptrs idxs vals begin
+        check(ccall((:mk_blockdiag, LIB), Cint,
+                    (Cint, Int64, Ptr{CuPtr{Cint}}, Ptr{CuPtr{Cint}}, Ptr{CuPtr{Cvoid}}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64},
+                     Cint, CuPtr{Cint}, CuPtr{Cint}, CuPtr{Cvoid}, Ptr{Cvoid}),
+                    dtype_code(payload(K)), length(ptrs), pointer.(ptrs), pointer.(idxs), pointer.(vals),
+                    Int64.(dim_ptr), Int64.(dim_idx), nnzs, 1, pointer(out_ptr), pointer(out_idx), pointer(out_val),
+                    CUDA.stream().handle))
+    end
+    out_ptr, out_idx, out_val
+end
+function SparseArrays.blockdiag(X::CuSparseMatrixCSR{K}...) where K <: Semiring
+    m, n = sum(size(x, 1) for x in X), sum(size(x, 2) for x in X)
+    CuSparseMatrixCSR{K}(_blockdiag(K, [x.rowPtr for x in X], [x.colVal for x in X], [x.nzVal for x in X],
+                                    [size(x, 1) for x in X], [size(x, 2) for x in X])..., (m, n))
+end
+function SparseArrays.blockdiag(X::CuSparseMatrixCSC{K}...) where K <: Semiring
+    m, n = sum(size(x, 1) for x in X), sum(size(x, 2) for x in X)
+    CuSparseMatrixCSC{K}(_blockdiag(K, [x.colPtr for x in X], [x.rowVal for x in X], [x.nzVal for x in X],
+                                    [size(x, 2) for x in X], [size(x, 1) for x in X])..., (m, n))
+end
+
+# vcat(::CuSparseVector...) (src/linalg.jl:137-157)
+function Base.vcat(X::CuSparseVector{K}...) where K <: Semiring
+    nnzs = Int64[length(SparseArrays.nonzeros(x)) for x in X]
+    iPtr, nzVal = CuVector{Cint}(undef, sum(nnzs)), CuVector{K}(undef, sum(nnzs))
+    inds, vals = [SparseArrays.nonzeroinds(x) for x in X], [SparseArrays.nonzeros(x) for x in X]
+    GC.@preserve inds vals begin
+        check(ccall((:mk_vcat_spvec, LIB), Cint,
+                    (Cint, Int64, Ptr{CuPtr{Cint}}, Ptr{CuPtr{Cvoid}}, Ptr{Int64}, Ptr{Int64}, CuPtr{Cint}, CuPtr{Cvoid}, Ptr{Cvoid}),
+                    dtype_code(payload(K)), length(X), pointer.(inds), pointer.(vals), Int64[length(x) for x in X], nnzs,
+                    pointer(iPtr), pointer(nzVal), CUDA.stream().handle))
+    end
+    CuSparseVector{K}(iPtr, nzVal, sum(length(x) for x in X))
 end
 
 end # module
