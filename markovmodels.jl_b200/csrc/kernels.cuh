@@ -495,6 +495,18 @@ __device__ __forceinline__ V4<T> resolve_sum(const V4<T>& acc, const V4<T>& e, b
 // The cache holds, per padded arc, the row offset pre-multiplied (idx * U4/4, in units of one
 // lane's 4 utterances) and the weight; per item its two records.
 
+// Float32 weights sit in shared memory as PAIRS {w, w} (8 bytes per arc): the operand layout of the packed
+// fma.rn.f32x2 of the Log fold below
+template <typename T> struct CacheW { static constexpr int bytes = sizeof(T) == 4 ? 8 : int(sizeof(T)); };
+__device__ __forceinline__ void lds_w4(unsigned a, float (&w)[4]) {
+    float d0, d1, d2, d3;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w[0]), "=f"(d0), "=f"(w[1]), "=f"(d1) : "r"(a));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w[2]), "=f"(d2), "=f"(w[3]), "=f"(d3) : "r"(a + 16u));
+}
+__device__ __forceinline__ void lds_w4_pairs(unsigned a, unsigned long long (&w2)[4]) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(w2[0]), "=l"(w2[1]) : "r"(a));
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(w2[2]), "=l"(w2[3]) : "r"(a + 16u));
+}
 template <typename T, bool SA> struct ArcSrc {
     const int* gidx; const T* gw;  // global
     unsigned soff, sw;             // shared addresses of (virtual) padded arc 0
@@ -548,10 +560,19 @@ template <typename T, bool SA> struct ArcSrc {
         }
     }
     __device__ __forceinline__ void weights(int aq, T (&w)[4]) const;
+    // Float32: the quad's four weights as {w, w} pairs (operands of fma.rn.f32x2)
+    __device__ __forceinline__ void weights2(int aq, unsigned long long (&w2)[4]) const {
+        if (SA) {
+            lds_w4_pairs(sw + unsigned(aq) * 8u, w2);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float w = __ldg(reinterpret_cast<const float*>(gw) + aq + k);
+                asm("mov.b64 %0, {%1, %1};" : "=l"(w2[k]) : "f"(w));
+            }
+        }
+    }
 };
-__device__ __forceinline__ void lds_w4(unsigned a, float (&w)[4]) {
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w[0]), "=f"(w[1]), "=f"(w[2]), "=f"(w[3]) : "r"(a));
-}
 __device__ __forceinline__ void lds_w4(unsigned a, double (&w)[4]) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(w[0]), "=d"(w[1]) : "r"(a));
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(w[2]), "=d"(w[3]) : "r"(a + 16u));
@@ -559,7 +580,7 @@ __device__ __forceinline__ void lds_w4(unsigned a, double (&w)[4]) {
 template <typename T, bool SA>
 __device__ __forceinline__ void ArcSrc<T, SA>::weights(int aq, T (&w)[4]) const {
     if (SA) {
-        lds_w4(sw + unsigned(aq) * unsigned(sizeof(T)), w);
+        lds_w4(sw + unsigned(aq) * unsigned(CacheW<T>::bytes), w);
     } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k) w[k] = __ldg(gw + aq + k);
@@ -579,9 +600,82 @@ __device__ __forceinline__ void ArcSrc<T, SA>::weights(int aq, T (&w)[4]) const 
 #endif
 template <typename T> struct PassOf { static constexpr int quads = sizeof(T) == 4 ? MK_PASS_QUADS : (MK_PASS_QUADS + 1) / 2; };
 
+// Float32 Log fold with Blackwell's packed FP32 pipe: the lane's four utterances are two f32x2 pairs, an arc costs two
+// fma.rn.f32x2 instead of four FFMA (sm_100+; bit-identical: each half is an IEEE fma.rn).  Gathers land as two 64-bit
+// registers, the accumulators stay packed until the item is finalised.
+#ifndef MK_FFMA2
+#define MK_FFMA2 1
+#endif
+__device__ __forceinline__ void ld2x2_cg(const float* p, unsigned long long& lo, unsigned long long& hi) {
+    asm volatile("ld.global.cg.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p));
+}
+__device__ __forceinline__ void fma2(unsigned long long& acc, unsigned long long v, unsigned long long w) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(v), "l"(w));
+}
+template <bool SA, class Fin>
+__device__ __forceinline__ void stream_items_f32x2(const ArcSrc<float, SA>& src, const int i0, const int i1,
+                                                   const float* vec_lane, Fin& fin) {
+    constexpr int kPassQuads = PassOf<float>::quads;
+    for (int item = i0; item < i1; ++item) {
+        fin.prefetch(src, item);
+        if (fin.is_passive()) {
+            fin.passive();
+            continue;
+        }
+        const int2 pa = src.item_pa(item);
+        unsigned long long acc01 = 0ull, acc23 = 0ull;
+        int a = pa.x, rem = pa.y;
+        while (rem > 0) {
+            unsigned long long v01[kPassQuads * 4], v23[kPassQuads * 4];
+#pragma unroll
+            for (int q = 0; q < kPassQuads; ++q) {
+                const int left = rem - q * 4;
+                if (left > 0) {  // warp-uniform
+                    unsigned off[4];
+                    src.offsets(a + q * 4, off);
+                    if (left >= 4) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) ld2x2_cg(vec_lane + size_t(off[k]) * 4, v01[q * 4 + k], v23[q * 4 + k]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (k < left) ld2x2_cg(vec_lane + size_t(off[k]) * 4, v01[q * 4 + k], v23[q * 4 + k]);
+                            else v01[q * 4 + k] = v23[q * 4 + k] = 0ull;  // (pad weights are 0)
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kPassQuads; ++q) {
+                if (rem - q * 4 > 0) {
+                    unsigned long long w2[4];
+                    src.weights2(a + q * 4, w2);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        fma2(acc01, v01[q * 4 + k], w2[k]);
+                        fma2(acc23, v23[q * 4 + k], w2[k]);
+                    }
+                }
+            }
+            a += kPassQuads * 4;
+            rem -= kPassQuads * 4;
+        }
+        V4<float> acc;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.v[0]), "=f"(acc.v[1]) : "l"(acc01));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.v[2]), "=f"(acc.v[3]) : "l"(acc23));
+        fin(item, acc);
+    }
+}
+
 template <typename T, int SR, bool SA, class Fin>
 __device__ __forceinline__ void stream_items(const ArcSrc<T, SA>& src, const int i0, const int i1,
                                              const T* vec_lane, Fin& fin) {
+    if constexpr (MK_FFMA2 && sizeof(T) == 4 && SR == SR_LOG) {
+#ifndef MK_ABLATE
+        stream_items_f32x2<SA>(src, i0, i1, vec_lane, fin);
+        return;
+#endif
+    }
     constexpr int kPassQuads = PassOf<T>::quads;
     for (int item = i0; item < i1; ++item) {
         fin.prefetch(src, item);  // item record, emission (and α) rows: in flight together with the gathers
@@ -969,10 +1063,10 @@ __device__ __forceinline__ ArcSrc<T, SA> make_arc_src(const DirPlan<T>& pl, int 
         if (a0 > a1) a0 = a1 = 0;
         if (i0 > i1) i0 = i1 = 0;
         unsigned* s_off = reinterpret_cast<unsigned*>(smem);
-        T* s_w = reinterpret_cast<T*>(smem + size_t(cap) * 4);
-        int4* s_items = reinterpret_cast<int4*>(smem + size_t(cap) * (4 + sizeof(T)));
-        int2* s_pa = reinterpret_cast<int2*>(smem + size_t(cap) * (4 + sizeof(T)) + size_t(cap_items) * 16);
-        int4* s_chunks = reinterpret_cast<int4*>(smem + size_t(cap) * (4 + sizeof(T)) + ((size_t(cap_items) * 24 + 15) & ~size_t(15)));
+        unsigned char* s_w = smem + size_t(cap) * 4;
+        int4* s_items = reinterpret_cast<int4*>(smem + size_t(cap) * (4 + CacheW<T>::bytes));
+        int2* s_pa = reinterpret_cast<int2*>(smem + size_t(cap) * (4 + CacheW<T>::bytes) + size_t(cap_items) * 16);
+        int4* s_chunks = reinterpret_cast<int4*>(smem + size_t(cap) * (4 + CacheW<T>::bytes) + ((size_t(cap_items) * 24 + 15) & ~size_t(15)));
         const int c0 = pl.cta_chunks[blockIdx.x], c1 = pl.cta_chunks[blockIdx.x + 1];
         for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x) s_chunks[c - c0] = pl.chunks[c];
         src.schunks = unsigned(__cvta_generic_to_shared(s_chunks)) - unsigned(c0) * 16u;
@@ -982,18 +1076,24 @@ __device__ __forceinline__ ArcSrc<T, SA> make_arc_src(const DirPlan<T>& pl, int 
         }
         for (int a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
             s_off[a - a0] = unsigned(pl.pidx[a]) * unsigned(U4q);
-            s_w[a - a0] = pl.pw[a];
+            if (sizeof(T) == 4) {
+                const T w = pl.pw[a];
+                reinterpret_cast<T*>(s_w)[2 * (a - a0)] = w;
+                reinterpret_cast<T*>(s_w)[2 * (a - a0) + 1] = w;
+            } else {
+                reinterpret_cast<T*>(s_w)[a - a0] = pl.pw[a];
+            }
         }
         src.sitems = unsigned(__cvta_generic_to_shared(s_items)) - unsigned(i0) * 16u;
         src.spa = unsigned(__cvta_generic_to_shared(s_pa)) - unsigned(i0) * 8u;
         src.soff = unsigned(__cvta_generic_to_shared(s_off)) - unsigned(a0) * 4u;
-        src.sw = unsigned(__cvta_generic_to_shared(s_w)) - unsigned(a0) * unsigned(sizeof(T));
+        src.sw = unsigned(__cvta_generic_to_shared(s_w)) - unsigned(a0) * unsigned(CacheW<T>::bytes);
     }
     return src;
 }
 // padded arcs (offset, weight; cap is a multiple of 4), then the CTA's item records
 __host__ __device__ inline size_t arc_cache_bytes(int cap, int items, int chunks, size_t tsize) {
-    return size_t(cap) * (4 + tsize) + ((size_t(items) * 24 + 15) & ~size_t(15)) + size_t(chunks) * 16;
+    return size_t(cap) * (4 + (tsize == 4 ? 8 : tsize)) + ((size_t(items) * 24 + 15) & ~size_t(15)) + size_t(chunks) * 16;
 }
 __host__ __device__ inline size_t shared_scalars_bytes(int U4, size_t tsize) {
     return (size_t(U4) * (2 * sizeof(double) + 3 * tsize + 2 * sizeof(int)) + size_t((U4 + 127) / 128) * sizeof(int) + 16 + 15) &
@@ -1068,6 +1168,9 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
             __syncthreads();
             // Utterance tiles in turn; inside a tile the warps pull the CTA's chunks dynamically, largest first.
             // The finaliser (lane pointers, per-utterance scalars, running maxima) is set up once per tile.
+#ifdef MK_PROFILE_BARRIER
+            const long long t_busy0 = clock64();
+#endif
             for (int tile = 0; tile < p.ntiles; ++tile) {
                 if (n >= tile_limit(p, tile)) continue;  // ragged batch: this tile's utterances are all finished
                 const bool live = tile * kTileUtts + lane * 4 < U4;  // (lanes beyond the batch stay converged for the pulls)
@@ -1107,6 +1210,9 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
                 }
                 __syncwarp();
             }
+#ifdef MK_PROFILE_BARRIER
+            if (lane == 0) atomicAdd(&g_prof[blockIdx.x * 4 + 3], (unsigned long long)(clock64() - t_busy0));
+#endif
             cta_sync_unaligned();
             for (int u = threadIdx.x; u < U4; u += blockDim.x) {
                 int k = s_key[u];
@@ -1170,6 +1276,9 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
         }
         for (int t = threadIdx.x; t < p.ntiles; t += blockDim.x) s_next[t] = c0;
         __syncthreads();
+#ifdef MK_PROFILE_BARRIER
+        const long long t_busy0 = clock64();
+#endif
         for (int tile = 0; tile < p.ntiles; ++tile) {  // (as in the forward sweep)
             const int lim = tile_limit(p, tile);
             if (n >= lim) continue;
@@ -1213,6 +1322,9 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
             }
             __syncwarp();
         }
+#ifdef MK_PROFILE_BARRIER
+        if (lane == 0) atomicAdd(&g_prof[blockIdx.x * 4 + 3], (unsigned long long)(clock64() - t_busy0));
+#endif
         cta_sync_unaligned();
         for (int u = threadIdx.x; u < U4; u += blockDim.x) {
             int k = s_key[u];

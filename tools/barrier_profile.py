@@ -33,7 +33,7 @@ print('slowest CTAs (work cycles/frame):', [(int(c), int(a[c, 0] / nb)) for c in
 print('fastest CTAs:', [(int(c), int(a[c, 0] / nb)) for c in order[-4:]])
 tot = a[:, :3].sum(1) / nb
 print("  total per frame", tot.mean(), "cycles =", tot.mean() / 1.965e3, "us")
-x = a[:, 3] / nb / 12
-print(f"  drain/finalise cycles per warp per frame  {x.mean():9.0f} {x.min():9.0f} {x.max():9.0f}")
+x = a[:, 3] / nb / 16
+print(f"  chunk loop, cycles per warp per frame (mean over the CTA's 16 warps)  {x.mean():9.0f} {x.min():9.0f} {x.max():9.0f}")
 w = a[:, 0] + a[:, 1]
 print("  busy (work + CTA wait) spread: min %.0f max %.0f  (max/mean %.2f)" % ((w / nb).min(), (w / nb).max(), w.max() / w.mean()))
