@@ -154,6 +154,10 @@ int mk_pdfposteriors_host_begin(mk_batch* b, const void* ll, int64_t stride_b, i
                                 int64_t stride_n, int64_t D, int64_t T, int expanded,
                                 const int32_t* seqlens, void* out_post, void* out_logz);
 int mk_batch_wait(mk_batch* b);
+/* Two batches in flight on one GPU (two streams, or two _begin calls): with overlap enabled on BOTH, the shared-graph
+ * sweeps run with half the threads per CTA, so that the two batches' cooperative kernels are co-resident on every SM
+ * and each fills the other's grid-barrier waits.  A lone batch is faster with overlap off (the default). */
+int mk_batch_set_overlap(mk_batch* b, int enable);
 int mk_bestpath_host(mk_batch* b, const void* ll, int64_t stride_b, int64_t stride_d,
                      int64_t stride_n, int64_t D, int64_t T, int expanded,
                      const int32_t* seqlens, int32_t* out_path, void* out_score);

@@ -121,6 +121,7 @@ SIGNATURES = {
     "mk_bestpath_host": (C.c_int, [_vp] + _EMIS + [_vp, _vp]),
     "mk_pdfposteriors_host_begin": (C.c_int, [_vp] + _EMIS + [_vp, _vp]),
     "mk_batch_wait": (C.c_int, [_vp]),
+    "mk_batch_set_overlap": (C.c_int, [_vp, C.c_int]),
     "mk_lfmmi_grad": (C.c_int, [C.c_int, _vp, _vp, _i64, _i64, _i64, _vp, C.c_double, _vp, _i64, _i64, _i64, _vp]),
     "mk_spmv": (C.c_int, [C.c_int, C.c_int, _i64, _i64, _i64, _vp, _vp, _vp, C.c_int, _vp, _i64, _vp, _i64, _vp]),
     "mk_spmm": (C.c_int, [C.c_int, C.c_int, _i64, _i64, _i64, _vp, _vp, _vp, C.c_int, _vp, _i64, _i64, _i64, _vp, _i64,

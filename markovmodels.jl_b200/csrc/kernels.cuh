@@ -836,7 +836,7 @@ __device__ __forceinline__ void fwd_combine(const SharedParams<T>& p, int m, con
     const size_t frame_a = size_t(SR == SR_LOG ? p.S : p.Sq) * U4;  // α store
     const T* Em = p.E + size_t(m) * p.Dh * U4;
     const T* part = p.part + size_t(m & 1) * p.n_slots * U4;
-    for (int k = warp; k < p.n_long; k += kSharedWarps) {
+    for (int k = warp; k < p.n_long; k += int(blockDim.x >> 5)) {
         const int4 lr = __ldg(p.fwd_long + k);
         const int r = lr.x;
         for (int tile = 0; tile < p.ntiles; ++tile) {

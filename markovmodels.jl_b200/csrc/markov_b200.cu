@@ -583,6 +583,10 @@ struct mk_batch {
     size_t trace_tsize = 0;
     bool ragged_cut = false;    // the current call stops at least one utterance tile early
     bool host_pending = false;  // a mk_pdfposteriors_host_begin call has not been waited for
+    // Threads per CTA of the shared-graph kernel: kSharedThreads (one CTA per SM owns the SM), or half of it so that the
+    // sweeps of TWO batches in flight share every SM (mk_batch_set_overlap): what one waits for at its grid barrier,
+    // the other computes.
+    int shared_threads = kSharedThreads;
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
     // One in-flight call per batch: the workspaces are shared by every entry point.  Each call records `ev_last` on
     // its stream when it has enqueued its work; a following call on ANOTHER stream (the *_host entry points run on
@@ -859,7 +863,7 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
                 TRY(emissions(p.n_lo, p.n_hi));
             }
             CK(cudaMemsetAsync(bt->barrier.p, 0, sizeof(unsigned), c.stream));
-            CK(cudaLaunchCooperativeKernel((void*)kern, dim3(g->n_sms), dim3(kSharedThreads), args, smem, c.stream));
+            CK(cudaLaunchCooperativeKernel((void*)kern, dim3(g->n_sms), dim3(bt->shared_threads), args, smem, c.stream));
             ++g_launches;
             if (seg && phase == 1 && mode == MODE_POST) {
                 // Ẑ ./ sums for the real frames of this segment, then hand them to the caller
@@ -1534,6 +1538,13 @@ int mk_pdfposteriors_host(mk_batch* b, const void* ll, int64_t sb, int64_t sd, i
 int mk_pdfposteriors_host_begin(mk_batch* b, const void* ll, int64_t sb, int64_t sd, int64_t sn, int64_t D,
                                 int64_t T, int expanded, const int32_t* seqlens, void* out_post, void* out_logz) {
     return posteriors_host(b, ll, sb, sd, sn, D, T, expanded, seqlens, out_post, out_logz, false);
+}
+int mk_batch_set_overlap(mk_batch* b, int enable) {
+    if (!b) return fail(MK_EINVAL, "null batch");
+    b->shared_threads = enable ? kSharedThreads / 2 : kSharedThreads;
+    const char* e = getenv("MK_OVERLAP_THREADS");  // (tuning)
+    if (enable && e && atoi(e) >= 64 && atoi(e) <= kSharedThreads && atoi(e) % 32 == 0) b->shared_threads = atoi(e);
+    return MK_OK;
 }
 int mk_batch_wait(mk_batch* b) {
     if (!b) return fail(MK_EINVAL, "null batch");

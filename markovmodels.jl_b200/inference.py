@@ -154,6 +154,10 @@ class BatchedFSM:
         _lib.check(_lib.lib().mk_batch_create(C.byref(h), arr, self.B))
         self._h = h
 
+    def set_overlap(self, enable=True):
+        """Share every SM with a second batch in flight (``mk_batch_set_overlap``): enable on both batches."""
+        _lib.check(_lib.lib().mk_batch_set_overlap(self._h, int(enable)))
+
     def wait(self):
         """Complete a ``pdfposteriors(..., wait=False)`` call on this batch (``mk_batch_wait``)."""
         _lib.check(_lib.lib().mk_batch_wait(self._h))

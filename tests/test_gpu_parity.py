@@ -573,6 +573,31 @@ def test_host_calls_overlap_across_batches(torch, mm, orc):
                      outs[2][1].numpy(), np.float32)
 
 
+def test_two_batches_share_the_sms(torch, mm, orc):
+    """mk_batch_set_overlap: the shared-graph sweeps of two batches run with half the threads per CTA, co-resident on every
+    SM, on two streams; same posteriors as the default launch."""
+    K = mm.LogSemiring[np.float32]
+    rng = np.random.default_rng(92)
+    B, T, D = 12, 40, 90
+    g = mm.graphs.denominator(K, n_tokens=900, n_pdf=D, seed=10)
+    bs = [gpu_batch(mm, [g] * B, D, "shared") for _ in range(2)]
+    Vs = [(rng.standard_normal((B, T, D)) * 2).astype(np.float32) for _ in range(2)]
+    lens = [rng.integers(T // 2, T + 1, B).astype(np.int32) for _ in range(2)]
+    for b in bs:
+        b.set_overlap(True)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = []
+    for k in range(2):
+        with torch.cuda.stream(streams[k]):
+            outs.append(mm.pdfposteriors(bs[k], dev(torch, Vs[k]), seqlengths=lens[k]))
+    torch.cuda.synchronize()
+    for k in range(2):
+        check_posteriors(mm, orc, [g] * B, D, Vs[k], lens[k], outs[k][0], outs[k][1], np.float32)
+    bs[0].set_overlap(False)
+    post, ttl = mm.pdfposteriors(bs[0], dev(torch, Vs[0]), seqlengths=lens[0])
+    np.testing.assert_allclose(ttl.cpu().numpy(), outs[0][1].cpu().numpy(), rtol=1e-6)
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("order", ["sorted", "shuffled"])
 def test_ragged_tiles_stop_early(torch, mm, orc, dtype, order):
