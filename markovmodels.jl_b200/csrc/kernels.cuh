@@ -13,7 +13,8 @@
 //    fetches them with one 16-byte load, a warp therefore gathers one contiguous 512 B
 //    segment per arc (L2-resident: two frames of state are 2*Ŝ*U*4 B ≈ 31 MB ≪ 126 MB).
 //    No cross-lane reduction is needed; the ⊕ over a row's arcs runs per lane.  Rows are
-//    split over warps by arc count.  One grid barrier per frame.
+//    split over warps by arc count.  One grid barrier per frame (the vectors are NOT resident in shared memory or
+//    cluster DSMEM: 2 x 15 MB per frame pair against 227 KB per SM / 3.6 MB per 16-CTA cluster).
 //    Replaces K1 (SpMV per frame), K2 (Ĉ·V̂ gather, Ĉᵀ scatter-reduce), K3 (α̂ ⊙ e₁), K4
 //    (per-frame broadcasts, γ, exp, sums) of SURVEY.md §2.2.
 //
@@ -21,11 +22,12 @@
 //    numerators: a few hundred states each, all distinct).  α/β vectors ping-pong in
 //    shared memory, arcs come through L1, one __syncthreads per frame.
 //
-// Semiring arithmetic (Semirings.jl): Log ⊕ = log-sum-exp evaluated as
-// max + log(Σ exp(x - max)) over a register-cached chunk of arcs (one ex2 per arc, one
-// rescale ex2 per further 8-arc chunk, one lg2 per row); Tropical ⊕ = max.  ⊗ = +.  -Inf is
-// the semiring zero and never produces NaN (the max of an all--Inf row is replaced by 0
-// before subtracting).
+// Semiring arithmetic (Semirings.jl).  Shared-graph kernel, Log: every stored vector exists as a normalised
+// log2 row and as its linear copy 2^(v + H); a row's ⊕ is Σ lin[neighbour] · W with linear arc weights — one FFMA (half
+// a packed fma.rn.f32x2) per arc and utterance, MUFU work per state only (lg2 of the sum, ex2 for the linear copy and for
+// γ) — and a row whose linear sum underflows is redone exactly from the log2 copies (two-pass max + Σ ex2).  Per-utterance
+// kernel and the exact path: max + log(Σ exp(x - max)).  Tropical ⊕ = max.  ⊗ = +.  -Inf is the semiring zero and never
+// produces NaN (the max of an all--Inf row is replaced by 0 before subtracting).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -1637,18 +1639,22 @@ __global__ void normalize_post_kernel(T* post, const T* zsum, int B, int D, int 
 template <typename T>
 __global__ void total_kernel(const T* zsum, const T* lz, T* logz, int B, int N1, const int* nlimit, double* stats,
                              const int* seqlens, int Tn) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per utterance: the lanes share the frames (a lone thread walked 151 dependent L2 loads: 36 us)
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= B) return;
-    T l = lz[b];
+    const T l = lz[b];
     T out;
     if (l == neg_inf<T>()) {
         out = l;
     } else {
-        T mn = zsum[b];
         const int nl = nlimit ? nlimit[b] : N1;
-        for (int n = 1; n < nl; ++n) mn = fmin(mn, zsum[size_t(n) * B + b]);
+        T mn = zsum[b];  // (frame 0 always exists)
+        for (int n = lane; n < nl; n += 32) mn = fmin(mn, zsum[size_t(n) * B + b]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
         out = mn > T(0) ? l + T(log(double(mn))) : neg_inf<T>();
     }
+    if (lane != 0) return;
     logz[b] = out;
     if (stats) {
         atomicAdd(stats, double(out));

@@ -246,8 +246,25 @@ __global__ void spmm_kernel(long long n_rows, const int32_t* __restrict__ rowptr
     if (i >= n_rows) return;
     const int beg = rowptr[i] - base, end = rowptr[i + 1] - base;
     for (long long j0 = (long long)blockIdx.y * CJ; j0 < n_cols_b; j0 += (long long)gridDim.y * CJ) {
-        Acc<T, SR> acc[CJ];
         const T* Bj = B + j0 * ldb;
+        if (end - beg == 1 && !accumulate && j0 + CJ <= n_cols_b) {
+            // one arc per row — the state-to-pdf maps Ĉ of the path (exactly one 1̄ per row,
+            // examples/prepare-lfmmi-graphs.jl:15-23): the ⊕ over a single term is the term, no exp / log
+            const T w = nzval[beg];
+            const T* src = Bj + (colval[beg] - base);
+            T x[CJ];
+#pragma unroll
+            for (int jj = 0; jj < CJ; ++jj) x[jj] = __ldg(src + jj * ldb);
+#pragma unroll
+            for (int jj = 0; jj < CJ; ++jj) {
+                T v;
+                if (SR == LSR_PROB) v = w * x[jj];
+                else { v = w + x[jj]; v = v > lin_neg_inf<T>() ? v : lin_neg_inf<T>(); }
+                C[(j0 + jj) * ldc + i] = v;
+            }
+            continue;
+        }
+        Acc<T, SR> acc[CJ];
         if (j0 + CJ <= n_cols_b) {
             for (int k = beg; k < end; ++k) {
                 const T w = nzval[k];

@@ -1006,7 +1006,7 @@ template <typename T, int SR> static int run(mk_batch* bt, Mode mode, const Call
             CK(cudaMemcpyAsync(bt->zlimit.p, bt->h_zlimit.data(), B * sizeof(int), cudaMemcpyHostToDevice, c.stream));
             zlimit = static_cast<const int*>(bt->zlimit.p);
         }
-        total_kernel<T><<<(B + 127) / 128, 128, 0, c.stream>>>(static_cast<const T*>(bt->zsum.p),
+        total_kernel<T><<<(B * 32 + 127) / 128, 128, 0, c.stream>>>(static_cast<const T*>(bt->zsum.p),
                                                              static_cast<const T*>(bt->lz.p),
                                                              static_cast<T*>(c.out1), B, N1, zlimit, c.stats,
                                                              c.expanded ? nullptr : d_seqlens, Tout);
