@@ -784,6 +784,8 @@ template <typename T> struct SharedParams {
     T* post; int B; int D; int Tn;
     const int* utt_b;  // [U4] global utterance index per group lane (-1 = padding)
     int post_vec4;     // 1: the 4 utterances of every lane are b0..b0+3, 16 B aligned
+    int post_ld;       // > 0: `post` is a staging array [Tn][D][post_ld] in LANE order (column = group lane u): any utterance
+                       // order keeps the 16-byte reductions; normalize_permuted_kernel moves it to the caller's (B, D, N) array
     T* zsum;           // [N1][B] per-frame normalisers (linear, relative to lz)
     T* lz;             // [B] forward total log-likelihood (natural log)
     double* lz2;       // [U4] the same in kernel units, handed from the forward to the backward launch
@@ -979,7 +981,7 @@ template <typename T, int SR> struct BwdFin {
         }
         beta_l = p.beta_out ? p.beta_out + size_t(n_) * p.S * p.U4 + uoff_ : nullptr;
         post_on = p.do_post && n_ < p.Tn;
-        post_l = post_on ? p.post + size_t(n_) * p.D * p.B : nullptr;
+        post_l = post_on ? p.post + size_t(n_) * p.D * (p.post_ld > 0 ? p.post_ld : p.B) : nullptr;
     }
     // items without arcs: rows of a merged run reuse the ⊕ just resolved (item.w bit0)
     __device__ __forceinline__ bool is_passive() const { return it.w & 1; }
@@ -1003,8 +1005,10 @@ template <typename T, int SR> struct BwdFin {
             }
             const int pdf = it.z;
             if (post_on && pdf < p.D) {
-                T* dst = post_l + size_t(pdf) * p.B;
-                if (p.post_vec4 && SR == SR_LOG) {
+                T* dst = post_l + size_t(pdf) * (p.post_ld > 0 ? p.post_ld : p.B);
+                if (p.post_ld > 0 && SR == SR_LOG) {
+                    red_add4(dst + uoff, pg);
+                } else if (p.post_vec4 && SR == SR_LOG) {
                     red_add4(dst + p.utt_b[uoff], pg);
                 } else {
 #pragma unroll
@@ -1625,6 +1629,33 @@ __global__ void normalize_post_kernel(T* post, const T* zsum, int B, int D, int 
                 row[b] = v;
                 sum += v;
             }
+        }
+    }
+    if (!occ) return;
+    double s = double(sum);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0 && s != 0.0) atomicAdd(occ + d, s);
+}
+// The same from a LANE-ordered staging array (SharedParams::post_ld): post[n][d][b] = stage[n][d][lane_of[b]] / zsum[n][b].
+// Used when the library sorted a ragged group's utterances by length (any permutation of the lanes).
+template <typename T>
+__global__ void normalize_permuted_kernel(const T* stage, int ld, const int* lane_of, T* post, const T* zsum, int B, int D,
+                                          int Tn, double* occ) {
+    const int lane = threadIdx.x & 31, d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (d >= D) return;
+    const int n0 = blockIdx.y * kNormFrames, n1 = min(Tn, n0 + kNormFrames);
+    T sum = T(0);
+    for (int n = n0; n < n1; ++n) {
+        const T* src = stage + (size_t(n) * D + d) * ld;
+        T* row = post + (size_t(n) * D + d) * B;
+        const T* z = zsum + size_t(n) * B;
+        for (int b = lane; b < B; b += 32) {
+            const int u = lane_of[b];
+            const T zz = z[b];
+            const T v = (u >= 0 && zz > T(0)) ? src[u] / zz : T(0);
+            row[b] = v;
+            sum += v;
         }
     }
     if (!occ) return;

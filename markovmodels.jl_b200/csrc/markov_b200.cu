@@ -560,6 +560,9 @@ struct Group {  // utterances sharing one graph, run by shared_fb_kernel
     DevBuf E, emax, emax_key, alpha, bt, flin, blin, part, gkey, coff, lz2, carry, tile_n1, trace;
     std::vector<unsigned char> h_trace;  // back-trace descriptors (bestpath), uploaded once
     size_t trace_tsize = 0;
+    DevBuf post_stage, lane_of;          // ragged groups sorted by length: lane-ordered posteriors, utterance -> lane
+    std::vector<int> h_lane_of;
+    bool staged = false;                 // the current call scatters into post_stage
     std::vector<int> h_tile_n1;  // ragged batches: frames each utterance tile needs (staging for tile_n1)
     std::vector<int> h_order;    // group lane u -> utterance b of the current call (utts, or its length-sorted quads)
     std::vector<int> h_utt_b;    // staging for d_utt_b when the order changes
@@ -607,7 +610,7 @@ struct mk_batch {
         for (auto& gr : groups) {
             cudaFree(gr.d_utt_b); cudaFree(gr.d_utt_off);
             gr.E.release(); gr.alpha.release(); gr.bt.release(); gr.flin.release(); gr.blin.release();
-            gr.part.release(); gr.gkey.release(); gr.coff.release(); gr.emax.release(); gr.emax_key.release(); gr.lz2.release(); gr.carry.release(); gr.tile_n1.release(); gr.trace.release();
+            gr.part.release(); gr.gkey.release(); gr.coff.release(); gr.emax.release(); gr.emax_key.release(); gr.lz2.release(); gr.carry.release(); gr.tile_n1.release(); gr.trace.release(); gr.post_stage.release(); gr.lane_of.release();
         }
         DevBuf* all[] = {&small_descs, &small_alpha, &small_ca, &zsum, &lz, &seqlens, &barrier, &trace,
                          &h_ll, &h_post, &h_logz, &h_path, &zlimit};
@@ -700,7 +703,23 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     const bool want_cut = mode == MODE_POST && c.seqlens && !c.expanded && ragged_cut_enabled();
     gr.h_order = gr.utts;
     bool permute = false;
-    if (want_cut && U4 > kTileUtts && gr.utts.size() % 4 == 0 && ragged_sort_enabled()) {
+    gr.staged = false;
+    // Single utterances sorted by length, longest first, when the whole batch is this one group: the posteriors are then
+    // scattered into a lane-ordered staging array (16-byte reductions whatever the order) and the normalisation pass
+    // writes them to the caller's utterance order (MK_RAGGED_SORT=quads keeps the quad sort below, =0 no sort at all).
+    const char* sort_env = getenv("MK_RAGGED_SORT");
+    const bool by_utt = want_cut && U4 > kTileUtts && ragged_sort_enabled() && bt->groups.size() == 1 && bt->small.empty() &&
+                        !(sort_env && sort_env[0] == 'q');
+    if (by_utt) {
+        std::vector<int> q(gr.utts.size());
+        for (size_t i = 0; i < q.size(); ++i) q[i] = int(i);
+        std::stable_sort(q.begin(), q.end(), [&](int a, int b) { return c.seqlens[gr.utts[a]] > c.seqlens[gr.utts[b]]; });
+        for (size_t i = 0; i < q.size() && !permute; ++i) permute = q[i] != int(i);
+        if (permute) {
+            for (size_t i = 0; i < q.size(); ++i) gr.h_order[i] = gr.utts[q[i]];
+            gr.staged = true;
+        }
+    } else if (want_cut && U4 > kTileUtts && gr.utts.size() % 4 == 0 && ragged_sort_enabled()) {
         const int nq = int(gr.utts.size() / 4);
         std::vector<int> q(nq), key(nq, 0);
         for (int i = 0; i < nq; ++i) {
@@ -720,6 +739,15 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
         gr.permuted = permute;
     }
 
+    if (gr.staged) {
+        gr.h_lane_of.assign(size_t(bt->B), -1);
+        for (size_t u = 0; u < gr.h_order.size(); ++u) gr.h_lane_of[gr.h_order[u]] = int(u);
+        TRY(gr.lane_of.ensure(size_t(bt->B) * sizeof(int)));
+        CK(cudaMemcpyAsync(gr.lane_of.p, gr.h_lane_of.data(), size_t(bt->B) * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+        const size_t stage_bytes = size_t(Tout) * Dout * U4 * sizeof(T);
+        TRY(gr.post_stage.ensure(stage_bytes));
+        CK(cudaMemsetAsync(gr.post_stage.p, 0, stage_bytes, c.stream));
+    }
     // frame segments of this call (one, unless the host pipeline cut it)
     std::vector<int> fb = seg ? seg->f : std::vector<int>{0, N1};
     const int K = int(fb.size()) - 1;
@@ -784,7 +812,7 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     p.flin = static_cast<T*>(gr.flin.p); p.blin = static_cast<T*>(gr.blin.p);
     p.beta_out = nullptr;
     p.post = nullptr; p.B = int(bt->B); p.D = Dout; p.Tn = Tout;
-    p.utt_b = gr.d_utt_b; p.post_vec4 = 0;
+    p.utt_b = gr.d_utt_b; p.post_vec4 = 0; p.post_ld = 0;
     p.zsum = static_cast<T*>(bt->zsum.p); p.lz = static_cast<T*>(bt->lz.p);
     p.barrier = static_cast<unsigned*>(bt->barrier.p);
     p.carry_C = static_cast<double*>(gr.carry.p);
@@ -827,6 +855,7 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
             p.do_fwd = p.do_bwd = p.do_post = 1;
             p.post = static_cast<T*>(c.out0);
             p.post_vec4 = (gr.vec4 && bt->B % 4 == 0 && (reinterpret_cast<uintptr_t>(c.out0) & 15) == 0) ? 1 : 0;
+            if (gr.staged) { p.post = static_cast<T*>(gr.post_stage.p); p.post_ld = U4; }
             break;
     }
     void* args[] = {&p};
@@ -870,10 +899,17 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
                 const int t0 = fb[k], t1 = std::min(fb[k + 1], Tout);
                 if (t1 > t0) {
                     dim3 ng((Dout + 7) / 8, (t1 - t0 + kNormFrames - 1) / kNormFrames);
-                    normalize_post_kernel<T><<<ng, 256, 0, c.stream>>>(
-                        static_cast<T*>(c.out0) + size_t(t0) * Dout * bt->B,
-                        static_cast<const T*>(bt->zsum.p) + size_t(t0) * bt->B, int(bt->B), Dout, t1 - t0,
-                        c.stats ? c.stats + 2 : nullptr);
+                    if (gr.staged)
+                        normalize_permuted_kernel<T><<<ng, 256, 0, c.stream>>>(
+                            static_cast<const T*>(gr.post_stage.p) + size_t(t0) * Dout * U4, U4,
+                            static_cast<const int*>(gr.lane_of.p), static_cast<T*>(c.out0) + size_t(t0) * Dout * bt->B,
+                            static_cast<const T*>(bt->zsum.p) + size_t(t0) * bt->B, int(bt->B), Dout, t1 - t0,
+                            c.stats ? c.stats + 2 : nullptr);
+                    else
+                        normalize_post_kernel<T><<<ng, 256, 0, c.stream>>>(
+                            static_cast<T*>(c.out0) + size_t(t0) * Dout * bt->B,
+                            static_cast<const T*>(bt->zsum.p) + size_t(t0) * bt->B, int(bt->B), Dout, t1 - t0,
+                            c.stats ? c.stats + 2 : nullptr);
                     CK(cudaGetLastError());
                     ++g_launches;
                 }
@@ -995,9 +1031,16 @@ template <typename T, int SR> static int run(mk_batch* bt, Mode mode, const Call
     if (mode == MODE_POST) {
         if (!seg) {  // (a segmented call normalises segment by segment, inside launch_shared)
             dim3 ng((Dout + 7) / 8, (Tout + kNormFrames - 1) / kNormFrames);
-            normalize_post_kernel<T><<<ng, 256, 0, c.stream>>>(static_cast<T*>(c.out0),
-                                                             static_cast<const T*>(bt->zsum.p), B, Dout, Tout,
-                                                             c.stats ? c.stats + 2 : nullptr);
+            if (bt->groups.size() == 1 && bt->groups[0].staged) {
+                Group& gr = bt->groups[0];
+                normalize_permuted_kernel<T><<<ng, 256, 0, c.stream>>>(
+                    static_cast<const T*>(gr.post_stage.p), gr.U4, static_cast<const int*>(gr.lane_of.p),
+                    static_cast<T*>(c.out0), static_cast<const T*>(bt->zsum.p), B, Dout, Tout, c.stats ? c.stats + 2 : nullptr);
+            } else {
+                normalize_post_kernel<T><<<ng, 256, 0, c.stream>>>(static_cast<T*>(c.out0),
+                                                                 static_cast<const T*>(bt->zsum.p), B, Dout, Tout,
+                                                                 c.stats ? c.stats + 2 : nullptr);
+            }
             CK(cudaGetLastError());
         }
         const int* zlimit = nullptr;
