@@ -773,9 +773,10 @@ template <typename T> struct SharedParams {
     const T* init_dense;                          // α̂ as a dense vector [S] (kernel units)
     const T* E;      // expanded, transposed emissions (kernel units, NOT normalised): [N1][Dh][U4]
     const T* emax;   // [N1][U4] per-frame emission maxima (kernel units), subtracted together with the shift
-    T* alpha;        // Log: [N1][Ŝ][U4] normalised a_n; Tropical: [N1][Sq][U4], the merged-run sources q_g after the states
+    T* alpha;        // [N1][Ŝ][U4] normalised a_n (log2 units / tropical values)
     T* bt;           // [2][S][U4]    b_{n+1} ⊗ e'_{n+1} ping-pong
-    T* flin;         // [2][Sq][U4]   Log: linear copies 2^(a_n + H_f) of the forward vector (ping-pong), the gather source
+    T* flin;         // [2][Sq][U4]   the forward gather source (ping-pong): Log linear copies 2^(a_n + H_f), Tropical a_n itself;
+                     //               rows Ŝ.. are the merged runs' virtual sources q_g
     T* blin;         // [2][S][U4]    Log: linear copies 2^(b_{n+1} ⊗ e'_{n+1} + H_b), the gather source
     T* beta_out;     // optional [N1][S][U4]  normalised b_n
     int* gkey;       // [2][N1][U4]   per-frame maxima (ordered keys): forward, backward
@@ -837,7 +838,7 @@ __device__ __forceinline__ void fwd_combine(const SharedParams<T>& p, int m, con
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int U4 = p.U4;
     const size_t frame = size_t(p.Sq) * U4;                          // linear copies: Ŝ + runs rows
-    const size_t frame_a = size_t(SR == SR_LOG ? p.S : p.Sq) * U4;  // α store
+    const size_t frame_a = size_t(p.S) * U4;  // α store
     const T* Em = p.E + size_t(m) * p.Dh * U4;
     const T* part = p.part + size_t(m & 1) * p.n_slots * U4;
     for (int k = warp; k < p.n_long; k += int(blockDim.x >> 5)) {
@@ -866,6 +867,7 @@ __device__ __forceinline__ void fwd_combine(const SharedParams<T>& p, int m, con
             }
             st4_cg(p.alpha + size_t(m) * frame_a + size_t(r) * U4 + uoff, val);
             if (SR == SR_LOG) st_lin(p.flin + size_t(m & 1) * frame + size_t(r) * U4 + uoff, val, p.fwd.H);
+            else st4_cg(p.flin + size_t(m & 1) * frame + size_t(r) * U4 + uoff, val);
         }
     }
 }
@@ -914,29 +916,22 @@ template <typename T, int SR> struct FwdFin {
         }
         if (it.w & 4) {
             const unsigned qoff = unsigned(p.S + (it.w >> 8)) * unsigned(p.U4 >> 2);
-            if (SR == SR_TROP) {
-                st4_cg(cur_l + size_t(qoff) * 4, qacc);
-                return;
-            }
-            st4_cg(lin_l + size_t(qoff) * 4, qacc);  // (no log2 row for q_g: the exact fallback expands runs)
+            st4_cg(lin_l + size_t(qoff) * 4, qacc);  // (no row for q_g in the α store: the exact fallback expands runs)
         }
     }
     // val: the row's normalised a_n (log2 / tropical)
     __device__ __forceinline__ void store(V4<T>& val) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) mx[j] = max_(mx[j], val.v[j]);
-        if (SR == SR_LOG) st4_stream(cur_l + size_t(unsigned(it.x)) * 4, val);  // (Tropical gathers from the store itself)
-        else st4_cg(cur_l + size_t(unsigned(it.x)) * 4, val);
-        if (SR == SR_LOG) {
-            V4<T> lin;
+        st4_stream(cur_l + size_t(unsigned(it.x)) * 4, val);  // the α store: Ŝ rows per frame, read back much later
+        // the gather source of the next frame: the linear copy (Log) / the value itself (Tropical), in the L2-resident
+        // ping-pong that also holds the merged runs' virtual sources
+        V4<T> lin;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) lin.v[j] = ex2_(val.v[j] + p.fwd.H);
-            // (rows of a merged run are only ever gathered through the run's virtual source)
-            if (!(it.w & 1)) st4_cg(lin_l + size_t(unsigned(it.x)) * 4, lin);
-            else emit_q(lin);
-        } else if (it.w & 1) {
-            emit_q(val);
-        }
+        for (int j = 0; j < 4; ++j) lin.v[j] = SR == SR_LOG ? ex2_(val.v[j] + p.fwd.H) : val.v[j];
+        // (rows of a merged run are only ever gathered through the run's virtual source)
+        if (!(it.w & 1)) st4_cg(lin_l + size_t(unsigned(it.x)) * 4, lin);
+        else emit_q(lin);
     }
     __device__ __forceinline__ void operator()(int item, const V4<T>& acc) {
         // item.w bit3: no initial state reaches this row — α = 0̄ in every frame; bit4: the row has no arcs
@@ -1123,7 +1118,7 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t frame = size_t(S) * U4;      // β-side vectors: Ŝ rows
     const size_t frame_q = size_t(p.Sq) * U4;  // forward vectors with the merged-run rows: Ŝ + runs
-    const size_t frame_a = SR == SR_LOG ? frame : frame_q;  // α store (Tropical gathers from it: q_g rows included)
+    const size_t frame_a = frame;              // α store: the states only (the gather source is the flin ping-pong)
     unsigned bar_target = 0;
 
     // This CTA's arcs stay in shared memory for the whole launch: the per-frame fence of the grid
@@ -1184,8 +1179,8 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
                 FwdFin<T, SR> fin(p, p.alpha + size_t(n > 0 ? n - 1 : 0) * frame_a, p.alpha + size_t(n) * frame_a,
                                   p.flin + size_t(n & 1) * frame_q, p.part + size_t(n & 1) * p.n_slots * U4,
                                   p.E + size_t(n) * p.Dh * U4, uoff, s_shift, p.emax + size_t(n) * U4);
-                // gather source: the previous frame's linear copies (Log) / the vector itself (Tropical)
-                const T* gsrc = (SR == SR_LOG ? p.flin + size_t((n - 1) & 1) * frame_q : fin.prev) + uoff;
+                // gather source: the previous frame's linear copies (Log) / values (Tropical), merged-run sources included
+                const T* gsrc = p.flin + size_t((n - 1) & 1) * frame_q + uoff;
                 for (;;) {
                     int wk = 0;
                     if (lane == 0) wk = atomicAdd(s_next + tile, 1);

@@ -680,14 +680,12 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     const size_t frame = size_t(S) * U4 * sizeof(T), frame_q = size_t(Sq) * U4 * sizeof(T);
     if (size_t(Sq) * U4 >= (size_t(1) << 31)) return fail(MK_ENOTSUP, "Ŝ*U exceeds 2^31 in one group");
     TRY(gr.E.ensure(size_t(N1) * Dh * U4 * sizeof(T)));
-    // α store: Log keeps the states only (the q_g exist as linear copies); Tropical gathers from the store itself
-    const size_t frame_a = SR == SR_LOG ? frame : frame_q;
+    // α store: the states only (the merged runs' sources q_g live in the forward gather ping-pong)
+    const size_t frame_a = frame;
     TRY(gr.alpha.ensure(size_t(N1) * frame_a));
     if (mode == MODE_POST || mode == MODE_BETA) TRY(gr.bt.ensure(2 * frame));
-    if (SR == SR_LOG) {  // linear copies of the two frames in flight: the gather sources
-        if (mode != MODE_BETA) TRY(gr.flin.ensure(2 * frame_q));
-        if (mode == MODE_POST || mode == MODE_BETA) TRY(gr.blin.ensure(2 * frame));
-    }
+    if (mode != MODE_BETA) TRY(gr.flin.ensure(2 * frame_q));  // forward gather source of the two frames in flight
+    if (SR == SR_LOG && (mode == MODE_POST || mode == MODE_BETA)) TRY(gr.blin.ensure(2 * frame));  // backward: linear copies
     TRY(gr.part.ensure(2 * size_t(std::max(g->n_slots, 1)) * U4 * sizeof(T)));
     TRY(gr.gkey.ensure(2 * size_t(N1) * U4 * sizeof(int)));
     TRY(gr.emax.ensure(size_t(N1) * U4 * sizeof(T)));
@@ -924,7 +922,7 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
         for (int z0 = 0; z0 < N1; z0 += 65535) {  // (gridDim.z is limited to 65535 frames per launch)
             dim3 ug((S + 31) / 32, (U4 + 31) / 32, std::min(N1 - z0, 65535)), ub(32, 8);
             unpack_states_kernel<T><<<ug, ub, 0, c.stream>>>(static_cast<const T*>(gr.alpha.p), S,
-                                                            (mode == MODE_BETA || SR == SR_LOG) ? S : Sq, U4, gr.d_utt_b,
+                                                            S, U4, gr.d_utt_b,
                                                             gr.d_utt_off, C, SR == SR_LOG ? 0.6931471805599453 : 1.0,
                                                             static_cast<T*>(c.out0), bt->total, z0);
             CK(cudaGetLastError());
@@ -1068,7 +1066,7 @@ template <typename T, int SR> static int run(mk_batch* bt, Mode mode, const Call
                 for (int k = 0; k < n; ++k) {
                     TraceDesc<T>& d = descs[k];
                     d.in_ptr = gr.g->d_in_ptr; d.in_arcs = static_cast<const Arc<T>*>(gr.g->d_in_arcs);
-                    d.base = (long long)k; d.sn = (long long)(gr.g->S + gr.g->n_runs) * gr.U4; d.ss = gr.U4;
+                    d.base = (long long)k; d.sn = (long long)gr.g->S * gr.U4; d.ss = gr.U4;
                     d.S = int(gr.g->S); d.b = gr.utts[k];
                 }
                 gr.h_trace.resize(descs.size() * sizeof(TraceDesc<T>));
