@@ -46,7 +46,9 @@ enum mk_status {
 };
 
 /* Semirings.jl types the path is instantiated with (src/MarkovModels.jl:12). */
-/* MK_PROB (ProbSemiring: ⊕ = +, ⊗ = *, 0̄ = 0, 1̄ = 1) is accepted by the operator-level entry points only. */
+/* MK_PROB (ProbSemiring: ⊕ = +, ⊗ = *, 0̄ = 0, 1̄ = 1): native at the operator level; a graph created with it is stored
+ * and run as its LogSemiring image (log.(weights)), emissions (probabilities) enter through log, α / β / totals leave
+ * through exp — same posteriors, the range of the log semiring inside. */
 enum mk_semiring { MK_LOG = 0, MK_TROPICAL = 1, MK_PROB = 2 };
 enum mk_dtype { MK_F32 = 0, MK_F64 = 1 };
 

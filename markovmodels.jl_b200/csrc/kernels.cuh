@@ -1365,6 +1365,13 @@ template <typename T> struct EmisParams {
 template <typename T>
 __device__ __forceinline__ T emission(const T* ll, long long sb, long long sd, long long sn, int D,
                                       int expanded, int L, int b, int d, int n) {
+    // `expanded`: bit0 = the caller passed D̂ x N̂ matrices; bit1 = ProbSemiring payloads (probabilities): the recursions run
+    // in the log semiring, a loaded value enters as its logarithm (0̄ = 0 -> -Inf, 1̄ = 1 -> 0: `expand` is unchanged)
+    if (expanded & 2) {
+        if (expanded & 1) return log_(ll[b * sb + d * sd + n * sn]);
+        if (d < D) return n < L ? log_(ll[b * sb + d * sd + n * sn]) : neg_inf<T>();
+        return n < L ? neg_inf<T>() : T(0);
+    }
     if (expanded) return ll[b * sb + d * sd + n * sn];
     if (d < D) return n < L ? ll[b * sb + d * sd + n * sn] : neg_inf<T>();
     return n < L ? neg_inf<T>() : T(0);
@@ -1521,7 +1528,7 @@ template <typename T, int SR> __global__ void __launch_bounds__(1024, 1) small_f
                 acc = acc + e - sh;
                 cur[s] = acc;
                 key = max(key, fkey(float(acc)));
-                A[size_t(n) * a_sn + s] = p.alpha_user ? T(double(acc) + C) : acc;
+                A[size_t(n) * a_sn + s] = p.alpha_user ? ((p.expanded & 2) ? T(exp(double(acc) + C)) : T(double(acc) + C)) : acc;
             }
             publish_key(s_keys, n & 1, key);
             __syncthreads();
@@ -1563,7 +1570,7 @@ template <typename T, int SR> __global__ void __launch_bounds__(1024, 1) small_f
             T beta = (n == p.N1 - 1) ? T(0)
                      : dead ? neg_inf<T>()
                             : small_row<T, SR>(u.out_arcs, first ? ob0 : u.out_ptr[i], first ? oe0 : u.out_ptr[i + 1], nxt) - sh;
-            if (Bo) Bo[size_t(n) * p.beta_sn + i] = T(double(beta) + C);
+            if (Bo) Bo[size_t(n) * p.beta_sn + i] = (p.expanded & 2) ? T(exp(double(beta) + C)) : T(double(beta) + C);
             if (p.do_post && !dead) {
                 T pg = exp_((first ? a0 : A[size_t(n) * a_sn + i]) + beta + g);
                 zs = lin_add<SR>(zs, pg);
@@ -1664,7 +1671,7 @@ __global__ void normalize_permuted_kernel(const T* stage, int ld, const int* lan
 // stats (optional, float64): stats[0] += Σ_b logz[b], stats[1] += Σ_b frames of b (seqlens[b], or Tn)
 template <typename T>
 __global__ void total_kernel(const T* zsum, const T* lz, T* logz, int B, int N1, const int* nlimit, double* stats,
-                             const int* seqlens, int Tn) {
+                             const int* seqlens, int Tn, int prob) {
     // one warp per utterance: the lanes share the frames (a lone thread walked 151 dependent L2 loads: 36 us)
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= B) return;
@@ -1681,7 +1688,7 @@ __global__ void total_kernel(const T* zsum, const T* lz, T* logz, int B, int N1,
         out = mn > T(0) ? l + T(log(double(mn))) : neg_inf<T>();
     }
     if (lane != 0) return;
-    logz[b] = out;
+    logz[b] = prob ? T(exp(double(out))) : out;  // (ProbSemiring: the total as a probability; the statistics keep the logarithm)
     if (stats) {
         atomicAdd(stats, double(out));
         atomicAdd(stats + 1, double(seqlens ? seqlens[b] : Tn));
@@ -1729,7 +1736,7 @@ __global__ void lfmmi_grad_kernel(const T* num, const T* den, int B, int D, int 
 template <typename T>
 __global__ void unpack_states_kernel(const T* src, int S, int S_src /* rows per source frame */, int U4, const int* utt_b,
                                      const long long* utt_off, const double* C /* [N1][U4] */, double unit, T* dst,
-                                     long long total, int n0) {
+                                     long long total, int n0, int prob) {
     __shared__ T tile[32][33];
     const int n = n0 + blockIdx.z, s0 = blockIdx.x * 32, u0 = blockIdx.y * 32;
     for (int k = threadIdx.y; k < 32; k += 8) {
@@ -1740,7 +1747,10 @@ __global__ void unpack_states_kernel(const T* src, int S, int S_src /* rows per 
     for (int k = threadIdx.y; k < 32; k += 8) {
         int u = u0 + k, s = s0 + threadIdx.x;
         if (s < S && u < U4 && utt_b[u] >= 0)
-            dst[utt_off[u] + s + total * n] = T((double(tile[threadIdx.x][k]) + C[size_t(n) * U4 + u]) * unit);
+        {
+            const double v = (double(tile[threadIdx.x][k]) + C[size_t(n) * U4 + u]) * unit;
+            dst[utt_off[u] + s + total * n] = prob ? T(exp(v)) : T(v);
+        }
     }
 }
 

@@ -131,6 +131,7 @@ struct DirDev {
 
 struct mk_graph {
     int semiring = 0, dtype = 0, device = 0, n_sms = 0;
+    bool prob = false;  // a ProbSemiring graph: stored and run as its LogSemiring image (log.(weights)); inputs / outputs converted
     int64_t S = 0, nnz = 0, Dh = 0;
     int max_in_deg = 0, max_out_deg = 0;
     // true weights, both orientations: per-utterance kernel, back-trace
@@ -343,7 +344,7 @@ static int build_graph(mk_graph* g, const int64_t* colptr, const int64_t* rowval
         if (s < 0 || s >= S) return fail(MK_EINVAL, "rowval[%lld] out of range", (long long)a);
         std::memset(&in_arcs[a], 0, sizeof(Arc<T>));
         in_arcs[a].idx = int(s);
-        in_arcs[a].w = nzval[a];
+        in_arcs[a].w = g->prob ? T(std::log(double(nzval[a]))) : nzval[a];
     }
     // Julia's CSC keeps row indices ascending inside a column; enforce it (defines the tie rule)
     for (int j = 0; j < S; ++j) {
@@ -383,7 +384,7 @@ static int build_graph(mk_graph* g, const int64_t* colptr, const int64_t* rowval
     for (int64_t k = 0; k < n_init; ++k) {
         int64_t s = init_idx[k] - base;
         if (s < 0 || s >= S) return fail(MK_EINVAL, "init_idx[%lld] out of range", (long long)k);
-        init[s] = init_w[k];
+        init[s] = g->prob ? T(std::log(double(init_w[k]))) : init_w[k];
     }
     // Row merging: runs of adjacent states with bit-identical out-arc lists (the A/B state pairs of
     // the chain topology: same successors, same weights).  Backward: β is computed once per run and
@@ -572,6 +573,7 @@ struct Group {  // utterances sharing one graph, run by shared_fb_kernel
 struct mk_batch {
     int64_t B = 0, total = 0;
     int semiring = 0, dtype = 0, device = 0, n_sms = 0;
+    bool prob = false;
     int64_t Dh = 0;
     std::vector<mk_graph*> graphs;
     std::vector<int64_t> off;
@@ -752,7 +754,7 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
 
     EmisParams<T> ep;
     ep.ll = static_cast<const T*>(c.ll); ep.sb = c.sb; ep.sd = c.sd; ep.sn = c.sn;
-    ep.D = int(c.D); ep.Tn = int(c.T); ep.expanded = c.expanded; ep.Dh = Dh; ep.N1 = N1;
+    ep.D = int(c.D); ep.Tn = int(c.T); ep.expanded = c.expanded | (bt->prob ? 2 : 0); ep.Dh = Dh; ep.N1 = N1;
     ep.seqlens = d_seqlens; ep.utt_b = gr.d_utt_b; ep.U4 = U4;
     ep.scale = SR == SR_LOG ? T(1.4426950408889634) : T(1);
     // expand + transpose + per-frame emission maxima of the frames [n0, n1)
@@ -924,7 +926,7 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
             unpack_states_kernel<T><<<ug, ub, 0, c.stream>>>(static_cast<const T*>(gr.alpha.p), S,
                                                             S, U4, gr.d_utt_b,
                                                             gr.d_utt_off, C, SR == SR_LOG ? 0.6931471805599453 : 1.0,
-                                                            static_cast<T*>(c.out0), bt->total, z0);
+                                                            static_cast<T*>(c.out0), bt->total, z0, bt->prob ? 1 : 0);
             CK(cudaGetLastError());
             ++g_launches;
         }
@@ -962,7 +964,7 @@ static int launch_small(mk_batch* bt, Mode mode, const CallArgs& c, int Dh, int 
     SmallParams<T> p;
     p.utts = static_cast<const UttDesc<T>*>(bt->small_descs.p);
     p.ll = static_cast<const T*>(c.ll); p.sb = c.sb; p.sd = c.sd; p.sn = c.sn;
-    p.D = Dout; p.Tn = Tout; p.expanded = c.expanded; p.Dh = Dh; p.N1 = N1;
+    p.D = Dout; p.Tn = Tout; p.expanded = c.expanded | (bt->prob ? 2 : 0); p.Dh = Dh; p.N1 = N1;
     p.seqlens = d_seqlens;
     p.alpha = static_cast<T*>(bt->small_alpha.p); p.alpha_sn = 0; p.alpha_user = 0;
     p.beta_out = nullptr; p.beta_sn = 0;
@@ -1050,7 +1052,7 @@ template <typename T, int SR> static int run(mk_batch* bt, Mode mode, const Call
         total_kernel<T><<<(B * 32 + 127) / 128, 128, 0, c.stream>>>(static_cast<const T*>(bt->zsum.p),
                                                              static_cast<const T*>(bt->lz.p),
                                                              static_cast<T*>(c.out1), B, N1, zlimit, c.stats,
-                                                             c.expanded ? nullptr : d_seqlens, Tout);
+                                                             c.expanded ? nullptr : d_seqlens, Tout, bt->prob ? 1 : 0);
         CK(cudaGetLastError());
         g_launches += 2;
     }
@@ -1302,10 +1304,7 @@ int mk_graph_create(mk_graph** out, int semiring, int dtype, int64_t n_states_ha
                     int64_t n_pdf_hat, int index_base, int device) {
     if (!out) return fail(MK_EINVAL, "null out");
     *out = nullptr;
-    if (semiring == MK_PROB)
-        return fail(MK_ENOTSUP, "ProbSemiring graphs are served by the operator level (mk_spmv / mk_spmm); the fused "
-                                "recursions take the same graph as LogSemiring (log.(weights))");
-    if (semiring != MK_LOG && semiring != MK_TROPICAL) return fail(MK_EINVAL, "unknown semiring %d", semiring);
+    if (semiring != MK_LOG && semiring != MK_TROPICAL && semiring != MK_PROB) return fail(MK_EINVAL, "unknown semiring %d", semiring);
     if (dtype != MK_F32 && dtype != MK_F64) return fail(MK_EINVAL, "unknown dtype %d", dtype);
     if (index_base != 0 && index_base != 1) return fail(MK_EINVAL, "index_base must be 0 or 1");
     if (n_states_hat < 2 || n_states_hat > (int64_t(1) << 30)) return fail(MK_EINVAL, "bad n_states_hat");
@@ -1324,7 +1323,10 @@ int mk_graph_create(mk_graph** out, int semiring, int dtype, int64_t n_states_ha
     if (!guard.ok) return fail(MK_ECUDA, "cannot select CUDA device %d", device);
     mk_graph* g = new (std::nothrow) mk_graph;
     if (!g) return fail(MK_ENOMEM, "out of host memory");
-    g->semiring = semiring; g->dtype = dtype; g->device = device;
+    // ProbSemiring: the graph is its LogSemiring image (x -> log x is a semiring isomorphism); emissions enter through
+    // log, α / β / totals leave through exp, posteriors are the same numbers
+    g->prob = semiring == MK_PROB;
+    g->semiring = g->prob ? int(MK_LOG) : semiring; g->dtype = dtype; g->device = device;
     g->S = n_states_hat; g->nnz = nnz_hat; g->Dh = n_pdf_hat;
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
@@ -1351,7 +1353,7 @@ int mk_graph_info(const mk_graph* g, int64_t* n_states_hat, int64_t* nnz_hat, in
     if (n_states_hat) *n_states_hat = g->S;
     if (nnz_hat) *nnz_hat = g->nnz;
     if (n_pdf_hat) *n_pdf_hat = g->Dh;
-    if (semiring) *semiring = g->semiring;
+    if (semiring) *semiring = g->prob ? int(MK_PROB) : g->semiring;
     if (dtype) *dtype = g->dtype;
     return MK_OK;
 }
@@ -1365,14 +1367,14 @@ int mk_batch_create(mk_batch** out, mk_graph* const* graphs, int64_t B) {
     mk_graph* g0 = graphs[0];
     for (int64_t b = 1; b < B; ++b) {
         mk_graph* g = graphs[b];
-        if (g->semiring != g0->semiring || g->dtype != g0->dtype || g->device != g0->device || g->Dh != g0->Dh)
+        if (g->semiring != g0->semiring || g->prob != g0->prob || g->dtype != g0->dtype || g->device != g0->device || g->Dh != g0->Dh)
             return fail(MK_EINVAL, "graphs[%lld] differs in semiring/dtype/device/n_pdf_hat", (long long)b);
     }
     DeviceGuard guard(g0->device);
     if (!guard.ok) return fail(MK_ECUDA, "cannot select CUDA device %d", g0->device);
     mk_batch* bt = new (std::nothrow) mk_batch;
     if (!bt) return fail(MK_ENOMEM, "out of host memory");
-    bt->B = B; bt->semiring = g0->semiring; bt->dtype = g0->dtype; bt->device = g0->device;
+    bt->B = B; bt->semiring = g0->semiring; bt->prob = g0->prob; bt->dtype = g0->dtype; bt->device = g0->device;
     bt->n_sms = g0->n_sms; bt->Dh = g0->Dh;
     bt->graphs.assign(graphs, graphs + B);
     bt->off.resize(B);

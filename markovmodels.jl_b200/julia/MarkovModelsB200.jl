@@ -18,7 +18,7 @@ const LIB = "libmarkov_b200"
 
 semiring_code(::Type{<:LogSemiring}) = Cint(0)
 semiring_code(::Type{<:TropicalSemiring}) = Cint(1)
-semiring_code(::Type{<:ProbSemiring}) = Cint(2)      # operator level only (mk_spmv / mk_spmm / mk_spvec_bcast)
+semiring_code(::Type{<:ProbSemiring}) = Cint(2)      # native at the operator level; graphs run as their LogSemiring image
 dtype_code(::Type{Float32}) = Cint(0)
 dtype_code(::Type{Float64}) = Cint(1)
 payload(::Type{<:Semiring{T}}) where T = T   # val(x)::T

@@ -573,6 +573,37 @@ def test_host_calls_overlap_across_batches(torch, mm, orc):
                      outs[2][1].numpy(), np.float32)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("force", ["small", "shared"])
+def test_prob_semiring_graphs_run_as_their_log_image(torch, mm, orc, dtype, force):
+    """FSM{ProbSemiring} through the fused recursions (the reference instantiates Prob for the same mul!, test/test_linalg.jl:89):
+    probabilities in (weights, emissions), probabilities out (α, β, totals); posteriors equal the LogSemiring run on the
+    logarithms, which the oracle checks."""
+    Kp, Kl = mm.ProbSemiring[dtype], mm.LogSemiring[dtype]
+    rng = np.random.default_rng(12)
+    B, T, D = 5, 12, 30
+    gl = mm.graphs.denominator(Kl, n_tokens=120, n_pdf=D, seed=3)
+    fl, pdf = gl
+    fp = mm.FSM(Kp, fl.nstates_hat, fl.init_idx, np.exp(fl.init_w.astype(np.float64)).astype(dtype), fl.colptr, fl.rowval,
+                np.exp(fl.nzval.astype(np.float64)).astype(dtype))
+    logV = (rng.standard_normal((B, T, D)) * 1.5).astype(dtype)
+    lens = rng.integers(T // 2, T + 1, B).astype(np.int32)
+    bl = gpu_batch(mm, [gl] * B, D, force)
+    bp = gpu_batch(mm, [(fp, pdf)] * B, D, force)
+    post_l, ttl_l = mm.pdfposteriors(bl, dev(torch, logV), seqlengths=lens)
+    post_p, ttl_p = mm.pdfposteriors(bp, dev(torch, np.exp(logV)), seqlengths=lens)
+    rt = 2e-4 if dtype == np.float32 else 1e-9
+    np.testing.assert_allclose(post_p.cpu().numpy(), post_l.cpu().numpy(), rtol=rt, atol=1e-7)
+    np.testing.assert_allclose(ttl_p.cpu().numpy(), np.exp(ttl_l.cpu().numpy().astype(np.float64)), rtol=rt)
+    check_posteriors(mm, orc, [gl] * B, D, logV, lens, post_p, np.log(ttl_p.cpu().numpy().astype(np.float64)).astype(dtype), dtype)
+    A_l = mm.αrecursion(bl, dev(torch, logV), seqlengths=lens).cpu().numpy().astype(np.float64)
+    A_p = mm.αrecursion(bp, dev(torch, np.exp(logV)), seqlengths=lens).cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(A_p, np.exp(A_l), rtol=rt, atol=0)
+    B_l = mm.βrecursion(bl, dev(torch, logV), seqlengths=lens).cpu().numpy().astype(np.float64)
+    B_p = mm.βrecursion(bp, dev(torch, np.exp(logV)), seqlengths=lens).cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(B_p, np.exp(B_l), rtol=rt, atol=0)
+
+
 def test_two_batches_share_the_sms(torch, mm, orc):
     """mk_batch_set_overlap: the shared-graph sweeps of two batches run with half the threads per CTA, co-resident on every
     SM, on two streams; same posteriors as the default launch."""
