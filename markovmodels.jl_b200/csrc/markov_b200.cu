@@ -769,8 +769,14 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
         if (SR == SR_LOG) CK(cudaMemsetAsync(keys, 0x80, size_t(nf) * U4 * sizeof(int), c.stream));
         for (int z0 = 0; z0 < nf; z0 += 65535) {  // (gridDim.z is limited to 65535 frames per launch)
             e.n0 = n0 + z0;
-            dim3 eg((Dh + 31) / 32, (U4 + 31) / 32, std::min(nf - z0, 65535)), eb(32, 8);
-            expand_transpose_kernel<T><<<eg, eb, 0, c.stream>>>(e);
+            if (getenv("MK_NARROW_TRANSPOSE")) {  // (the round-1 32 x 32 tiles, for A/B timing)
+                dim3 eg((Dh + 31) / 32, (U4 + 31) / 32, std::min(nf - z0, 65535)), eb(32, 8);
+                expand_transpose_kernel<T><<<eg, eb, 0, c.stream>>>(e);
+            } else {
+                constexpr int DT = WideTile<T>::d;
+                dim3 eg((Dh + DT - 1) / DT, (U4 + 127) / 128, std::min(nf - z0, 65535));
+                expand_transpose_wide_kernel<T><<<eg, 256, 0, c.stream>>>(e);
+            }
             CK(cudaGetLastError());
             ++g_launches;
         }
