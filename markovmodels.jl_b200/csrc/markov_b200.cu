@@ -769,7 +769,9 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
         if (SR == SR_LOG) CK(cudaMemsetAsync(keys, 0x80, size_t(nf) * U4 * sizeof(int), c.stream));
         for (int z0 = 0; z0 < nf; z0 += 65535) {  // (gridDim.z is limited to 65535 frames per launch)
             e.n0 = n0 + z0;
-            if (getenv("MK_NARROW_TRANSPOSE")) {  // (the round-1 32 x 32 tiles, for A/B timing)
+            // (32 x 32 tiles when two batches share the SMs: the small blocks slip in beside the other batch's sweep, the
+            // wide ones wait for it — 7.15 against 7.65 ms per batch; MK_NARROW_TRANSPOSE forces them, for A/B timing)
+            if (getenv("MK_NARROW_TRANSPOSE") || bt->shared_threads != kSharedThreads) {
                 dim3 eg((Dh + 31) / 32, (U4 + 31) / 32, std::min(nf - z0, 65535)), eb(32, 8);
                 expand_transpose_kernel<T><<<eg, eb, 0, c.stream>>>(e);
             } else {
