@@ -34,9 +34,9 @@ UNIT = "frames/s"
 B_PER_GPU, T_FRAMES, N_PDF, N_TOKENS, SEED = 128, 150, 3000, 15000, 303
 HBM_FALLBACK_GBS = 6650.0
 # dram__bytes_read.sum + dram__bytes_write.sum of the two shared_fb_kernel launches of ONE pdfposteriors call on
-# this workload, from the ncu counters summarised in profiles/r01_shared_fb_kernel_ncu.md (end-of-round build with
-# the L2 eviction hints: forward 0.220 + 2.289 GB, backward 2.756 + 1.376 GB); null for any other shape
-NCU_DRAM_BYTES_PER_LAUNCH = 6.641e9
+# this workload, from the ncu capture summarised in profiles/r02_shared_fb_kernel_ncu.md (round-2 end-of-round build:
+# forward 0.219 + 2.289 GB, backward 2.767 + 1.679 GB); null for any other shape
+NCU_DRAM_BYTES_PER_LAUNCH = 6.954e9
 
 
 def workload_config(n_gpus, b_per_gpu, frames):
@@ -394,7 +394,7 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (B, T) == (B_PER_GPU, T_FRAMES) else None,
-                     "traffic_unit": "bytes per launch pair (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_shared_fb_kernel_ncu.md)",
+                     "traffic_unit": "bytes per launch pair (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r02_shared_fb_kernel_ncu.md)",
                      "algorithmic_bytes_per_launch": bytes_per_unit * units,
                      "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})",
                      "kernel": "shared_fb_kernel<float, Log> (forward sweep + backward sweep: two cooperative "
