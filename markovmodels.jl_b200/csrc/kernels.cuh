@@ -791,6 +791,9 @@ template <typename T> struct SharedParams {
     T* lz;             // [B] forward total log-likelihood (natural log)
     double* lz2;       // [U4] the same in kernel units, handed from the forward to the backward launch
     unsigned* barrier;
+    // calibration (mk_graph_create): per-CTA cycles between leaving a grid barrier and arriving at the next, summed over
+    // the launch — [2][grid], forward then backward — or null
+    unsigned long long* cta_cycles;
     int do_fwd, do_bwd, do_post;
     // frame segment of this launch: the forward sweep runs frames [n_lo, n_hi) upwards, the backward sweep the same
     // range downwards.  A sweep cut into several launches (host-buffer pipeline: copies overlap the kernels) carries
@@ -1142,6 +1145,8 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
         s_lz[u] = 0.0; s_g[u] = T(0); s_z[u] = T(0); s_key[u] = kKeyMin;
     }
     grid_sync(p.barrier, bar_target);
+    long long t_mark = 0, t_work = 0;  // (thread 0, calibration launches only)
+    if (p.cta_cycles && threadIdx.x == 0) t_mark = clock64();
 
     // ---------------------------------------------------------------- forward (αrecursion)
     if (PHASE == 0) {
@@ -1220,8 +1225,11 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
                 if (k != kKeyMin) atomicMax(p.gkey + size_t(n) * U4 + u, k);
                 s_key[u] = kKeyMin;
             }
+            if (p.cta_cycles && threadIdx.x == 0) t_work += clock64() - t_mark;
             grid_sync(p.barrier, bar_target);
+            if (p.cta_cycles && threadIdx.x == 0) t_mark = clock64();
         }
+        if (p.cta_cycles && threadIdx.x == 0) p.cta_cycles[blockIdx.x] = (unsigned long long)t_work;
         if (p.n_hi < p.N1) {  // the sweep continues in the next launch
             if (blockIdx.x == 0)
                 for (int u = threadIdx.x; u < U4; u += blockDim.x) { p.carry_C[u] = s_C[u]; p.carry_shift[u] = s_shift[u]; }
@@ -1338,8 +1346,11 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
                 s_z[u] = T(0);
             }
         }
+        if (p.cta_cycles && threadIdx.x == 0) t_work += clock64() - t_mark;
         grid_sync(p.barrier, bar_target);
+        if (p.cta_cycles && threadIdx.x == 0) t_mark = clock64();
     }
+    if (p.cta_cycles && threadIdx.x == 0) p.cta_cycles[gridDim.x + blockIdx.x] = (unsigned long long)t_work;
     if (p.n_lo > 0 && blockIdx.x == 0)  // the sweep continues in the next launch
         for (int u = threadIdx.x; u < U4; u += blockDim.x) p.carry_C[u] = s_C[u];
 }

@@ -132,6 +132,8 @@ struct DirDev {
 struct mk_graph {
     int semiring = 0, dtype = 0, device = 0, n_sms = 0;
     bool prob = false;  // a ProbSemiring graph: stored and run as its LogSemiring image (log.(weights)); inputs / outputs converted
+    bool calibrated = false;                 // the plans' CTA split follows measured per-CTA speeds
+    unsigned long long* d_cta_cycles = nullptr;  // set while the calibration call runs: [2][n_sms]
     int64_t S = 0, nnz = 0, Dh = 0;
     int max_in_deg = 0, max_out_deg = 0;
     // true weights, both orientations: per-utterance kernel, back-trace
@@ -192,7 +194,7 @@ template <typename T>
 static void build_plan(const std::vector<int>& ptr, const std::vector<Arc<T>>& arcs, const std::vector<int>& pdf,
                        int S, int n_ctas, bool split, const std::vector<int>& gflags, const std::vector<char>& tied,
                        bool reuse, bool linear, double H, DirHost<T>& d, std::vector<int4>& long_rows,
-                       std::vector<Arc<T>>& long_arcs, int& n_slots) {
+                       std::vector<Arc<T>>& long_arcs, int& n_slots, const std::vector<double>* share = nullptr) {
     // Log semiring: the padded (streamed) arcs hold LINEAR weights 2^(w - R - H) that multiply the linear
     // copies 2^(v + H) of the vector; pads are 0.  Tropical: w itself, pads 0̄.
     const T ninf = linear ? T(0) : -std::numeric_limits<T>::infinity();
@@ -237,8 +239,12 @@ static void build_plan(const std::vector<int>& ptr, const std::vector<Arc<T>>& a
     cta_items[0] = 0;
     double acc = 0;
     int i = 0;
+    // `share` (calibration, mk_graph_create): CTA k's part of the cost — the measured relative speed of its SM on this
+    // graph — instead of 1 / n_ctas
+    std::vector<double> cum(n_ctas + 1, 0.0);
+    for (int k = 0; k < n_ctas; ++k) cum[k + 1] = cum[k] + (share ? (*share)[k] : 1.0 / n_ctas);
     for (int k = 1; k < n_ctas; ++k) {
-        const double target = total * k / n_ctas;
+        const double target = total * cum[k] / cum[n_ctas];
         while (i < n_items) {
             double c = cost(i);
             if (acc + 0.5 * c > target) break;
@@ -319,6 +325,10 @@ template <typename T> static double max_row_logsum(const std::vector<int>& ptr, 
     }
     return best;
 }
+
+// Runs a short synthetic pdfposteriors on the freshly built graph and returns the work cycles every CTA spent per sweep
+// (defined after the dispatch code below).
+static int calibrate_graph(mk_graph* g, std::vector<double>& fwd_cycles, std::vector<double>& bwd_cycles);
 
 template <typename T>
 static int build_graph(mk_graph* g, const int64_t* colptr, const int64_t* rowval, const void* nzval_,
@@ -545,6 +555,51 @@ static int build_graph(mk_graph* g, const int64_t* colptr, const int64_t* rowval
     TRY(upload(fwd_long_arcs, &g->d_fwd_long_arcs));
     g->bytes = 2 * (S + 1) * sizeof(int) + 4 * nnz * sizeof(Arc<T>) + S * (sizeof(int) + 2 * sizeof(T)) +
                (fwd.pidx.size() + bwd.pidx.size()) * (sizeof(int) + sizeof(T));
+    // Calibration: the cost model (arcs + 12 per item) and the SMs are not uniform — on cfg 3 the CTAs on one block of SM
+    // ids take 8 % longer per frame than the mean, and every frame waits for the slowest.  One short synthetic call on the
+    // new graph measures each CTA's work cycles per sweep; the plans are then rebuilt with every CTA's share of the cost
+    // proportional to its measured speed (clipped to +-25 %), three times over (MK_CALIBRATE=n: n rounds, 0 disables); graphs that
+    // never take the shared-graph kernel (fewer than 2 048 states) are not calibrated.
+    const char* cal = getenv("MK_CALIBRATE");
+    if (!(cal && cal[0] == '0') && S >= 2048) {
+        const int rounds = (cal && atoi(cal) >= 1) ? std::min(atoi(cal), 12) : 3;
+        std::vector<double> sf(g->n_sms, 1.0), sb(g->n_sms, 1.0);  // shares so far (relative)
+        for (int round = 0; round < rounds; ++round) {
+            std::vector<double> tf, tb;
+            if (calibrate_graph(g, tf, tb) != MK_OK || int(tf.size()) != g->n_sms || int(tb.size()) != g->n_sms) {
+                cudaGetLastError();  // (a failed calibration leaves the current plan in place)
+                break;
+            }
+            // a CTA that took t with share s runs at speed s / t: the next share is proportional to it
+            auto update = [&](std::vector<double>& sh, const std::vector<double>& t) {
+                double mean_v = 0;
+                std::vector<double> v(t.size(), 0.0);
+                for (size_t k = 0; k < t.size(); ++k) { v[k] = t[k] > 0 ? sh[k] / t[k] : 0.0; mean_v += v[k]; }
+                mean_v /= double(t.size());
+                if (!(mean_v > 0)) return;
+                for (size_t k = 0; k < t.size(); ++k) sh[k] = v[k] > 0 ? std::min(1.25, std::max(0.75, v[k] / mean_v)) : 1.0;
+            };
+            update(sf, tf);
+            update(sb, tb);
+            DirHost<T> fwd2, bwd2;
+            std::vector<int4> fwd_long2, no_long2;
+            std::vector<Arc<T>> fwd_long_arcs2, no_arcs2;
+            int n_slots2 = 0, no_slots2 = 0;
+            build_plan<T>(in_ptr_m, in_s, pdf, S, g->n_sms, true, gf_fwd, tied, false, linear, g->fwd.H, fwd2, fwd_long2,
+                          fwd_long_arcs2, n_slots2, &sf);
+            build_plan<T>(out_ptr, out_s, pdf, S, g->n_sms, false, gf_bwd, tied, true, linear, g->bwd.H, bwd2, no_long2,
+                          no_arcs2, no_slots2, &sb);
+            if (n_slots2 != g->n_slots || fwd_long2.size() != fwd_long.size()) break;  // (the items do not depend on the split)
+            CK(cudaDeviceSynchronize());
+            const double Rf = g->fwd.R, Hf = g->fwd.H, Rb = g->bwd.R, Hb = g->bwd.H;
+            g->fwd.release(); g->bwd.release();
+            g->fwd = DirDev(); g->bwd = DirDev();
+            g->fwd.R = Rf; g->fwd.H = Hf; g->bwd.R = Rb; g->bwd.H = Hb;
+            TRY(upload_plan<T>(fwd2, in_s, g->fwd));
+            TRY(upload_plan<T>(bwd2, out_s, g->bwd));
+            g->calibrated = true;
+        }
+    }
     return MK_OK;
 }
 
@@ -823,6 +878,7 @@ static int launch_shared(mk_batch* bt, Group& gr, Mode mode, const CallArgs& c, 
     p.utt_b = gr.d_utt_b; p.post_vec4 = 0; p.post_ld = 0;
     p.zsum = static_cast<T*>(bt->zsum.p); p.lz = static_cast<T*>(bt->lz.p);
     p.barrier = static_cast<unsigned*>(bt->barrier.p);
+    p.cta_cycles = g->d_cta_cycles;
     p.carry_C = static_cast<double*>(gr.carry.p);
     p.carry_shift = reinterpret_cast<T*>(static_cast<double*>(gr.carry.p) + U4);
     p.n_lo = 0; p.n_hi = N1;
@@ -1147,6 +1203,47 @@ static int dispatch(mk_batch* bt, Mode mode, const CallArgs& c) {
         }
     }
     return rc;
+}
+
+static int calibrate_graph(mk_graph* g, std::vector<double>& fwd_cycles, std::vector<double>& bwd_cycles) {
+    // 128 utterances x 24 frames of all-zero log-likelihoods (the work of a frame does not depend on the values) through
+    // the public entry points; the second call is the measured one (the first fills the caches and sizes the workspaces)
+    const int B = 128, T = 24;
+    const int64_t D = g->Dh - 1;
+    const size_t ts = g->dtype == MK_F32 ? 4 : 8;
+    std::vector<mk_graph*> graphs(B, g);
+    mk_batch* bt = nullptr;
+    int rc = mk_batch_create(&bt, graphs.data(), B);
+    if (rc != MK_OK) return rc;
+    void *ll = nullptr, *post = nullptr, *logz = nullptr;
+    unsigned long long* cyc = nullptr;
+    auto cleanup = [&]() {
+        g->d_cta_cycles = nullptr;
+        cudaFree(ll); cudaFree(post); cudaFree(logz); cudaFree(cyc);
+        mk_batch_destroy(bt);
+    };
+    const size_t n_ll = size_t(B) * T * D;
+    if (bt->groups.size() != 1 || cudaMalloc(&ll, n_ll * ts) != cudaSuccess || cudaMalloc(&post, n_ll * ts) != cudaSuccess ||
+        cudaMalloc(&logz, B * ts) != cudaSuccess || cudaMalloc(&cyc, 2 * sizeof(unsigned long long) * g->n_sms) != cudaSuccess) {
+        cleanup();
+        cudaGetLastError();
+        return MK_ENOMEM;
+    }
+    cudaMemset(ll, 0, n_ll * ts);
+    cudaMemset(cyc, 0, 2 * sizeof(unsigned long long) * g->n_sms);
+    for (int rep = 0; rep < 2 && rc == MK_OK; ++rep) {
+        g->d_cta_cycles = rep == 1 ? cyc : nullptr;
+        rc = mk_pdfposteriors(bt, ll, T * D, 1, D, D, T, 0, nullptr, post, logz, nullptr);
+    }
+    if (rc == MK_OK && cudaDeviceSynchronize() != cudaSuccess) rc = MK_ECUDA;
+    std::vector<unsigned long long> h(2 * size_t(g->n_sms));
+    if (rc == MK_OK && cudaMemcpy(h.data(), cyc, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = MK_ECUDA;
+    cleanup();
+    if (rc != MK_OK) return rc;
+    fwd_cycles.assign(h.begin(), h.begin() + g->n_sms);
+    bwd_cycles.assign(h.begin() + g->n_sms, h.end());
+    return MK_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
