@@ -237,12 +237,12 @@ __device__ __forceinline__ void cta_sync_unaligned() {
 #define MK_ABL(p, bit) false
 #endif
 #ifdef MK_PROFILE_BARRIER
+__shared__ long long t_last;  // thread 0: when the CTA left the last grid barrier
 __device__ unsigned long long g_prof[148 * 4];
 __device__ unsigned long long g_redo;  // exact-fallback events  // per CTA: cycles before arriving, cycles waiting, ...
 #endif
 __device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& target) {
 #ifdef MK_PROFILE_BARRIER
-    static __shared__ long long t_last;
     long long t0 = clock64();
 #endif
     __syncthreads();
@@ -264,7 +264,7 @@ __device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& target) {
         long long t2 = clock64();
         if (target > gridDim.x) {  // skip the first barrier
             g_prof[blockIdx.x * 4 + 0] += (unsigned long long)(t0 - t_last);  // thread 0: work since last barrier
-            g_prof[blockIdx.x * 4 + 1] += (unsigned long long)(t1 - t0);      // thread 0 waiting for its CTA
+            // (slot 1: scalar phase, barrier exit -> chunk loop start, added by the kernel)
             g_prof[blockIdx.x * 4 + 2] += (unsigned long long)(t2 - t1);      // CTA waiting for the grid
         }
         t_last = t2;
@@ -1100,7 +1100,7 @@ __host__ __device__ inline size_t arc_cache_bytes(int cap, int items, int chunks
     return size_t(cap) * (4 + (tsize == 4 ? 8 : tsize)) + ((size_t(items) * 24 + 15) & ~size_t(15)) + size_t(chunks) * 16;
 }
 __host__ __device__ inline size_t shared_scalars_bytes(int U4, size_t tsize) {
-    return (size_t(U4) * (2 * sizeof(double) + 3 * tsize + 2 * sizeof(int)) + size_t((U4 + 127) / 128) * sizeof(int) + 16 + 15) &
+    return (size_t(U4) * (2 * sizeof(double) + 3 * tsize + 3 * sizeof(int)) + size_t((U4 + 127) / 128) * sizeof(int) + 16 + 15) &
            ~size_t(15);
 }
 
@@ -1118,6 +1118,9 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
     int* s_key = reinterpret_cast<int*>(s_z + U4);        // [U4] running maxima
     int* s_exact = s_key + U4;                            // [U4] exactness flags of the frame (resolve_sum, exact_flags())
     int* s_next = s_exact + U4;                           // [ntiles] dynamic chunk counters, one per utterance tile
+    int* s_len = s_next + (U4 + kTileUtts - 1) / kTileUtts;  // [U4] sequence lengths: read once (the per-frame scalar phase is
+                                                          // serial, and utt_b -> seqlens were two dependent L2 round trips in it:
+                                                          // the grid barrier's acquire empties L1 every frame)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t frame = size_t(S) * U4;      // β-side vectors: Ŝ rows
     const size_t frame_q = size_t(p.Sq) * U4;  // forward vectors with the merged-run rows: Ŝ + runs
@@ -1143,6 +1146,8 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
         s_C[u] = first_segment ? 0.0 : p.carry_C[u];
         s_shift[u] = (first_segment || PHASE == 1) ? T(0) : p.carry_shift[u];
         s_lz[u] = 0.0; s_g[u] = T(0); s_z[u] = T(0); s_key[u] = kKeyMin;
+        const int b = p.utt_b[u];
+        s_len[u] = (b >= 0 && p.seqlens) ? __ldg(p.seqlens + b) : p.Tn;
     }
     grid_sync(p.barrier, bar_target);
     long long t_mark = 0, t_work = 0;  // (thread 0, calibration launches only)
@@ -1159,14 +1164,16 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
             for (int u = threadIdx.x; u < U4; u += blockDim.x) {
                 if (n >= tile_limit(p, u / kTileUtts)) { s_key[u] = kKeyMin; continue; }  // Ca, shift stay at the tile's last frame
                 {   // is the gather source α_{n-1} confined to the seed states?  (only meaningful under `expand`)
-                    const int b = p.utt_b[u];
-                    const int L = (b >= 0 && p.seqlens) ? __ldg(p.seqlens + b) : p.Tn;
+                    const int L = s_len[u];
                     s_exact[u] = (n == 1 ? 32 : 0) | ((p.bwd_dead_ok && n - 1 >= L) ? 64 : 0);
                 }
+                int key = kKeyMin;
+                if (n >= 1) key = __ldcg(p.gkey + size_t(n - 1) * U4 + u);
+                const T em = __ldg(p.emax + size_t(n) * U4 + u);  // (requested together with the key: one L2 round trip)
                 T sh = T(0);
-                if (n >= 1) sh = shift_from_key<SR, T>(max(__ldcg(p.gkey + size_t(n - 1) * U4 + u), s_key[u]));
+                if (n >= 1) sh = shift_from_key<SR, T>(max(key, s_key[u]));
                 s_shift[u] = sh;
-                s_C[u] += double(sh) + double(__ldg(p.emax + size_t(n) * U4 + u));
+                s_C[u] += double(sh) + double(em);
                 s_key[u] = kKeyMin;
                 if (blockIdx.x == 0) p.Coff[size_t(n) * U4 + u] = s_C[u];
             }
@@ -1176,6 +1183,7 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
             // The finaliser (lane pointers, per-utterance scalars, running maxima) is set up once per tile.
 #ifdef MK_PROFILE_BARRIER
             const long long t_busy0 = clock64();
+            if (threadIdx.x == 0 && bar_target > gridDim.x) g_prof[blockIdx.x * 4 + 1] += (unsigned long long)(t_busy0 - t_last);
 #endif
             for (int tile = 0; tile < p.ntiles; ++tile) {
                 if (n >= tile_limit(p, tile)) continue;  // ragged batch: this tile's utterances are all finished
@@ -1267,26 +1275,35 @@ __global__ void __launch_bounds__(kSharedThreads, 1) shared_fb_kernel(const __gr
             const int lim = tile_limit(p, u / kTileUtts);
             if (n >= lim) continue;  // this tile's backward sweep starts at frame lim - 1
             {   // is the gather source b_{n+1} ⊗ e_{n+1} confined to the phony final state?
-                const int b = p.utt_b[u];
-                const int L = (b >= 0 && p.seqlens) ? __ldg(p.seqlens + b) : p.Tn;
+                const int L = s_len[u];
                 s_exact[u] = (p.bwd_dead_ok && n + 1 >= L) ? 32 : 0;
             }
+            // (the three global loads of the phase are requested together: one L2 round trip, not three)
+            int key = kKeyMin;
+            T em = T(0);
+            double ca = 0.0;
+            if (n < lim - 1) {
+                key = __ldcg(gkey_b + size_t(n + 1) * U4 + u);
+                em = __ldg(p.emax + size_t(n + 1) * U4 + u);
+            }
+            if (p.do_post) ca = __ldcg(p.Coff + size_t(n) * U4 + u);
             T sh = T(0);
             if (n < lim - 1) {
-                sh = shift_from_key<SR, T>(__ldcg(gkey_b + size_t(n + 1) * U4 + u));
-                s_C[u] += double(sh) + double(__ldg(p.emax + size_t(n + 1) * U4 + u));
+                sh = shift_from_key<SR, T>(key);
+                s_C[u] += double(sh) + double(em);
             }
             s_shift[u] = sh;
             if (blockIdx.x == 0 && p.beta_out) Cb[size_t(n) * U4 + u] = s_C[u];
             if (p.do_post) {
                 double lz = s_lz[u];
-                s_g[u] = (lz == double(neg_inf<T>())) ? T(0) : T(__ldcg(p.Coff + size_t(n) * U4 + u) + s_C[u] - lz);
+                s_g[u] = (lz == double(neg_inf<T>())) ? T(0) : T(ca + s_C[u] - lz);
             }
         }
         for (int t = threadIdx.x; t < p.ntiles; t += blockDim.x) s_next[t] = c0;
         __syncthreads();
 #ifdef MK_PROFILE_BARRIER
         const long long t_busy0 = clock64();
+        if (threadIdx.x == 0 && bar_target > gridDim.x) g_prof[blockIdx.x * 4 + 1] += (unsigned long long)(t_busy0 - t_last);
 #endif
         for (int tile = 0; tile < p.ntiles; ++tile) {  // (as in the forward sweep)
             const int lim = tile_limit(p, tile);

@@ -25,7 +25,7 @@ a = np.array(buf[:148 * 4], np.float64).reshape(148, 4)
 print('exact-fallback events per call:', buf[148 * 4], 'of', 2 * (T + 1) * fsm.nstates_hat, 'row evaluations')
 nb = 2 * (T + 1)
 print("per barrier interval, cycles (mean over CTAs / min / max):")
-for k, name in enumerate(["thread0 work since last barrier", "thread0 waits for its CTA", "CTA waits for the grid"]):
+for k, name in enumerate(["thread0 work since last barrier", "scalar phase (barrier exit -> chunk loop)", "CTA waits for the grid"]):
     x = a[:, k] / nb
     print(f"  {name:34s} {x.mean():9.0f} {x.min():9.0f} {x.max():9.0f}")
 order = np.argsort(-a[:, 0])
