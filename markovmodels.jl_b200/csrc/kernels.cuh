@@ -342,7 +342,7 @@ __device__ __forceinline__ V4<T> row_reduce(const Arc<T>* __restrict__ arcs, int
 // α store keeps no log2 row for the virtual sources q_g (only their linear copies exist), so the rare exact
 // path expands them.  Plain two-pass loops: this code runs for a handful of rows per call.
 template <typename T>
-__device__ __noinline__ void row_reduce_runs(const Arc<T>* __restrict__ arcs, int beg, int end, const T* vec, int U4, int uoff,
+__device__ __forceinline__ void row_reduce_runs(const Arc<T>* __restrict__ arcs, int beg, int end, const T* vec, int U4, int uoff,
                                              const int2* __restrict__ runs, int S, T* out4) {
     T m[4], s[4];
 #pragma unroll
@@ -418,7 +418,7 @@ template <typename T> __device__ __forceinline__ T min4(const V4<T>& x) {
     return fmin(fmin(x.v[0], x.v[1]), fmin(x.v[2], x.v[3]));
 }
 template <typename T, int SR>
-__device__ __noinline__ void redo_row(const DirPlan<T>* pl, int item, const T* vec, int U4, int uoff, const T* acc4,
+__device__ __forceinline__ void redo_row(const DirPlan<T>* pl, int item, const T* vec, int U4, int uoff, const T* acc4,
                                       unsigned live, T* val4) {
 #ifdef MK_PROFILE_BARRIER
     if ((threadIdx.x & 31) == 0) atomicAdd(&g_redo, 1ull);
@@ -454,7 +454,9 @@ __device__ __forceinline__ int* exact_flags(int U4, size_t tsize) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     return reinterpret_cast<int*>(smem_raw + size_t(U4) * (2 * sizeof(double) + 3 * tsize + sizeof(int)));
 }
-// The rare part of resolve_sum, out of line: which utterances really need the exact path?  Not those whose emission is
+// The rare part of resolve_sum (inlined: as out-of-line calls, entered by the few live lanes of a partial utterance tile, it left
+// compute-sanitizer's synccheck reporting divergent barriers — lanes return from such a call one by one — and cost 0.5 %): which
+// utterances really need the exact path?  Not those whose emission is
 // 0̄, and not those whose all-zero sum is exact by construction: the per-frame, per-utterance flags in shared memory
 // (exact_flags) say whether the gather source of this frame lives on the seed states only — bit5: the frame after α̂
 // (forward) / the frame before an utterance's phony frames (backward); bit6: the frames after an utterance's first
@@ -462,7 +464,7 @@ __device__ __forceinline__ int* exact_flags(int U4, size_t tsize) {
 // batch the finished utterances would otherwise send the 146 segments of the phony final state's row through the
 // serial exact path in every frame (measured: 5x per frame).
 template <typename T, int SR>
-__device__ __noinline__ V4<T> resolve_slow(V4<T> acc, V4<T> val, unsigned live, int item_w, const DirPlan<T>* pl, int item,
+__device__ __forceinline__ V4<T> resolve_slow(V4<T> acc, V4<T> val, unsigned live, int item_w, const DirPlan<T>* pl, int item,
                                            const T* vec, int U4, int uoff) {
     const int4 xf = *reinterpret_cast<const int4*>(exact_flags(U4, sizeof(T)) + uoff);
     const int xw[4] = {xf.x, xf.y, xf.z, xf.w};
