@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace mk {
 
@@ -90,7 +91,7 @@ template <typename T> struct Acc<T, LSR_PROB> {
 };
 
 // c[r] = ⊕_k nzval[k] ⊗ b[colval[k]] — LANES lanes per row (the reference spends a whole warp per row,
-// src/linalg.jl:213-233; rows of the path's graphs hold ~17 arcs, so the host picks 4/8/32 from nnz / rows).
+// src/linalg.jl:213-233; rows of the path's graphs hold ~17 arcs, so the host picks 2/4/32 from nnz / rows).
 // A row is taken in chunks of LANES x R arcs: every lane first requests its R (colval, nzval) pairs and the R
 // gathers from b — all in flight together — and only then folds them.  Log semiring: the chunk's maximum is made
 // group-uniform with LANES-wide shuffles, every lane adds exp(v - M) of its own arcs to a lane-local sum (one exp per
@@ -212,14 +213,31 @@ template <typename T, int SR>
 __global__ void spmv_long_kernel(const int* __restrict__ worklist, int worklist_cap, const int32_t* __restrict__ rowptr,
                                  const int32_t* __restrict__ colval, const T* __restrict__ nzval, int base,
                                  const T* __restrict__ b, T* __restrict__ c) {
-    __shared__ T sm[8], ss[8];
+    __shared__ T sm[32], ss[32];
     const int count = min(worklist[0], worklist_cap);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = blockIdx.x; i < count; i += gridDim.x) {
         const int r = worklist[1 + i];
         const int beg = rowptr[r] - base, end = rowptr[r + 1] - base;
         Acc<T, SR> acc;
-        for (int k = beg + threadIdx.x; k < end; k += blockDim.x) acc.add_prod(nzval[k], b[colval[k] - base]);
+        // (8 arcs and their gathers in flight per thread: one arc at a time measured 44 us for the 128 final-state rows of
+        // cfg 3 — 9 300 arcs each, 36 dependent round trips per thread)
+        constexpr int Q = 8;
+        for (int k0 = beg + threadIdx.x; k0 < end; k0 += blockDim.x * Q) {
+            int col[Q];
+            T w[Q], x[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const int k = k0 + q * blockDim.x;
+                if (k < end) { col[q] = colval[k] - base; w[q] = nzval[k]; }
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q)
+                if (k0 + q * blockDim.x < end) x[q] = b[col[q]];
+#pragma unroll
+            for (int q = 0; q < Q; ++q)
+                if (k0 + q * blockDim.x < end) acc.add_prod(w[q], x[q]);
+        }
         acc.template reduce<32>();
         if (lane == 0) acc.spill(sm[warp], ss[warp]);
         __syncthreads();
@@ -294,6 +312,240 @@ __global__ void spmm_kernel(long long n_rows, const int32_t* __restrict__ rowptr
 #else
             *dst = acc[jj].value();
 #endif
+        }
+    }
+}
+
+// ---- SpMM through a shared-memory window of B ---------------------------------------------------------------------
+// spmm_kernel's gathers fetch 4 bytes of every 32-byte sector they touch: at cfg 3 (Ĉ·V̂: 3.84 M rows x 151 columns) that is
+// 18.5 GB through the L2 -> L1 path for 2.6 GB of algorithmic traffic, and the 1.1 ms it takes is exactly that path's bandwidth
+// (148 SMs x 64 B/clk).  The matrices of the path are block-diagonal (one block per utterance, src/fsmops.jl:28-36), so the
+// columns a block of consecutive rows touches form a narrow window: spmm_window_kernel finds it per block of `rb_rows` rows, and
+// spmm_staged_kernel copies that window of CJ columns of B into shared memory — coalesced, every sector used in full — as
+// [column of A][CJ] so that an arc's CJ operands are one 16-byte shared-memory load.  A block whose window does not fit
+// (a matrix without that structure) reads B from global memory exactly like spmm_kernel; no host decision, no synchronisation.
+__global__ void spmm_window_kernel(long long n_rows, int rb_rows, const int32_t* __restrict__ rowptr,
+                                   const int32_t* __restrict__ colval, int base, int* __restrict__ win) {
+    __shared__ int slo[32], shi[32];
+    const long long r0 = (long long)blockIdx.x * rb_rows;
+    const long long r1 = r0 + rb_rows < n_rows ? r0 + rb_rows : n_rows;
+    const int beg = rowptr[r0] - base, end = rowptr[r1] - base;
+    int lo = 0x7fffffff, hi = -1;
+    for (int k = beg + threadIdx.x; k < end; k += blockDim.x) {
+        const int c = colval[k] - base;
+        lo = min(lo, c);
+        hi = max(hi, c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) { slo[threadIdx.x >> 5] = lo; shi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < int(blockDim.x >> 5); ++w) { lo = min(lo, slo[w]); hi = max(hi, shi[w]); }
+        win[2 * blockIdx.x] = lo;
+        win[2 * blockIdx.x + 1] = hi;
+    }
+}
+
+// CJ operands of one arc: from the staged window (16-byte loads) or straight from B.
+template <typename T, int CJ, bool STAGED>
+__device__ __forceinline__ void spmm_operands(T (&x)[CJ], const T* __restrict__ sB, const T* __restrict__ Bj, long long ldb,
+                                              int col, int lo, int ncj, T zero) {
+    if (STAGED) {
+        constexpr int PER = 16 / int(sizeof(T));
+        const uint4* src = reinterpret_cast<const uint4*>(sB + size_t(col - lo) * CJ);
+#pragma unroll
+        for (int q = 0; q < CJ / PER; ++q) {
+            const uint4 v = src[q];
+            T t[PER];
+            memcpy(t, &v, 16);
+#pragma unroll
+            for (int e = 0; e < PER; ++e) x[q * PER + e] = t[e];
+        }
+    } else {
+        const T* src = Bj + col;
+#pragma unroll
+        for (int jj = 0; jj < CJ; ++jj) x[jj] = jj < ncj ? __ldg(src + jj * ldb) : zero;
+    }
+}
+
+// One row with any number of arcs (or β = 1).  C0: this row block's part of the first column of the chunk; l: row in block.
+// (Out of line: its accumulators would otherwise share the register budget of the one-arc path.)
+template <typename T, int SR, int CJ, bool STAGED>
+__device__ __noinline__ void spmm_one_row(int l, int beg, int end, const int32_t* __restrict__ colval,
+                                          const T* __restrict__ nzval, int base, const T* __restrict__ sB, int lo,
+                                          const T* __restrict__ Bj, long long ldb, T* __restrict__ C0, long long ldc, int ncj,
+                                          int accumulate) {
+    const T zero = SR == LSR_PROB ? T(0) : lin_neg_inf<T>();
+    Acc<T, SR> acc[CJ];
+    T x[CJ];
+    for (int k = beg; k < end; ++k) {
+        const T w = nzval[k];
+        spmm_operands<T, CJ, STAGED>(x, sB, Bj, ldb, colval[k] - base, lo, ncj, zero);
+#pragma unroll
+        for (int jj = 0; jj < CJ; ++jj) acc[jj].add_prod(w, x[jj]);
+    }
+#pragma unroll
+    for (int jj = 0; jj < CJ; ++jj) {
+        if (jj >= ncj) break;
+        T* dst = C0 + jj * ldc + l;
+        if (accumulate) acc[jj].add_value(*dst);
+        __stcs(dst, acc[jj].value());
+    }
+}
+
+// U rows of one thread (l0, l0 + step, ...; all inside the block).  A row is a chain of dependent loads (row pointer -> arc ->
+// operand -> store): the U row pointers, then the U arcs, are requested together; the operands come from shared memory and are
+// consumed row by row (holding all U x CJ of them would not fit 64 registers — measured: spills through L1, 1.13 ms at cfg 3).
+template <typename T, int SR, int CJ, int U, bool STAGED, bool FULL>
+__device__ __forceinline__ void spmm_row_batch(int l0, int step, const int32_t* __restrict__ rp,
+                                               const int32_t* __restrict__ colval, const T* __restrict__ nzval, int base,
+                                               const T* __restrict__ sB, int lo, const T* __restrict__ Bj, long long ldb,
+                                               T* const (&Cr)[CJ], long long ldc, int ncj, int accumulate) {
+    const T zero = SR == LSR_PROB ? T(0) : lin_neg_inf<T>();
+    int beg[U], end[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { beg[u] = rp[l0 + u * step] - base; end[u] = rp[l0 + u * step + 1] - base; }
+    bool single = !accumulate;
+#pragma unroll
+    for (int u = 0; u < U; ++u) single = single && end[u] - beg[u] == 1;
+    if (single) {  // one arc per row (Ĉ): the ⊕ over a single term is the term
+        int col[U];
+        T w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { col[u] = colval[beg[u]] - base; w[u] = nzval[beg[u]]; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            T x[CJ];
+            spmm_operands<T, CJ, STAGED>(x, sB, Bj, ldb, col[u], lo, ncj, zero);
+#pragma unroll
+            for (int jj = 0; jj < CJ; ++jj) {
+                if (!FULL && jj >= ncj) break;
+                T v;
+                if (SR == LSR_PROB) v = w[u] * x[jj];
+                else { v = w[u] + x[jj]; v = v > lin_neg_inf<T>() ? v : lin_neg_inf<T>(); }
+                __stcs(Cr[jj] + (l0 + u * step), v);
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        spmm_one_row<T, SR, CJ, STAGED>(l0 + u * step, beg[u], end[u], colval, nzval, base, sB, lo, Bj, ldb, Cr[0], ldc, ncj,
+                                        accumulate);
+}
+
+// Row pointers of U rows of one thread; `single` = every one of them holds exactly one arc.
+template <int U>
+__device__ __forceinline__ void spmm_row_ptrs(const int32_t* __restrict__ rp, int l0, int step, int base, int (&beg)[U],
+                                              bool& single) {
+    int len[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int b0 = rp[l0 + u * step], b1 = rp[l0 + u * step + 1];
+        beg[u] = b0 - base;
+        len[u] = b1 - b0;
+    }
+    single = true;
+#pragma unroll
+    for (int u = 0; u < U; ++u) single = single && len[u] == 1;
+}
+
+// The rows of one block: 32-bit offsets into the block; C is written with streaming stores so that the arcs and B stay in L2 for
+// the CTAs of the same row block that work on the other column chunks.  Software-pipelined by one batch: the row pointers of the
+// next U rows are requested while the arcs of this batch are in flight (one L2 round trip per batch instead of two).
+template <typename T, int SR, int CJ, int U, bool STAGED, bool FULL>
+__device__ __forceinline__ void spmm_rows(int nrow, const int32_t* __restrict__ rp, const int32_t* __restrict__ colval,
+                                          const T* __restrict__ nzval, int base, const T* __restrict__ sB, int lo,
+                                          const T* __restrict__ Bj, long long ldb, T* const (&Cr)[CJ], long long ldc,
+                                          int ncj, int accumulate) {
+    const T zero = SR == LSR_PROB ? T(0) : lin_neg_inf<T>();
+    const int step = int(blockDim.x);
+    int l0 = int(threadIdx.x);
+    if (!accumulate) {
+        // one arc per row (Ĉ): the ⊕ over a single term is the term.  (No call in this loop: the out-of-line general row would
+        // force everything that lives across it into local memory.)
+        bool go = l0 + (U - 1) * step < nrow;
+        int beg[U];
+        if (go) spmm_row_ptrs<U>(rp, l0, step, base, beg, go);
+        while (go) {
+            int col[U];
+            T w[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) { col[u] = colval[beg[u]] - base; w[u] = nzval[beg[u]]; }
+            const int ln = l0 + step * U;
+            go = ln + (U - 1) * step < nrow;
+            if (go) spmm_row_ptrs<U>(rp, ln, step, base, beg, go);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                T x[CJ];
+                spmm_operands<T, CJ, STAGED>(x, sB, Bj, ldb, col[u], lo, ncj, zero);
+#pragma unroll
+                for (int jj = 0; jj < CJ; ++jj) {
+                    if (!FULL && jj >= ncj) break;
+                    T v;
+                    if (SR == LSR_PROB) v = w[u] * x[jj];
+                    else { v = w[u] + x[jj]; v = v > lin_neg_inf<T>() ? v : lin_neg_inf<T>(); }
+                    __stcs(Cr[jj] + (l0 + u * step), v);
+                }
+            }
+            l0 = ln;
+        }
+    }
+    // whatever is left — from the first batch with a row of another length on, or everything when β = 1
+    for (; l0 + (U - 1) * step < nrow; l0 += step * U)
+        spmm_row_batch<T, SR, CJ, U, STAGED, FULL>(l0, step, rp, colval, nzval, base, sB, lo, Bj, ldb, Cr, ldc, ncj, accumulate);
+    for (; l0 < nrow; l0 += step)
+        spmm_row_batch<T, SR, CJ, 1, STAGED, FULL>(l0, step, rp, colval, nzval, base, sB, lo, Bj, ldb, Cr, ldc, ncj, accumulate);
+}
+
+// grid = (min(ceil(n_cols_b / CJ), 65535), row blocks): the CTAs of one row block — one per column chunk — run side by side and
+// share its arcs and its window of B through L2.  Dynamic shared memory = max_window * CJ * sizeof(T).
+template <typename T, int SR, int CJ, int THREADS, int U>
+__global__ void __launch_bounds__(THREADS, 2)
+spmm_staged_kernel(long long n_rows, int rb_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colval,
+                   const T* __restrict__ nzval, int base, const T* __restrict__ B, long long ldb, T* __restrict__ C,
+                   long long ldc, long long n_cols_b, int accumulate, const int* __restrict__ win, int max_window) {
+    extern __shared__ __align__(16) unsigned char spmm_smem[];
+    T* sB = reinterpret_cast<T*>(spmm_smem);
+    const long long r0 = (long long)blockIdx.y * rb_rows;
+    const int nrow = int(r0 + rb_rows < n_rows ? rb_rows : n_rows - r0);
+    const int lo = win[2 * blockIdx.y], hi = win[2 * blockIdx.y + 1];
+    const int W = hi >= lo ? hi - lo + 1 : 0;
+    const bool staged = W <= max_window;  // (block-uniform)
+    const T zero = SR == LSR_PROB ? T(0) : lin_neg_inf<T>();
+    const int32_t* rp = rowptr + r0;
+    for (long long j0 = (long long)blockIdx.x * CJ; j0 < n_cols_b; j0 += (long long)gridDim.x * CJ) {
+        const int ncj = int(n_cols_b - j0 < CJ ? n_cols_b - j0 : CJ);
+        const T* Bj = B + j0 * ldb;
+        T* Cr[CJ];
+#pragma unroll
+        for (int jj = 0; jj < CJ; ++jj) Cr[jj] = C + (j0 + (jj < ncj ? jj : 0)) * ldc + r0;
+        if (staged) {
+            __syncthreads();  // the readers of the previous window are done
+            constexpr int PER = 16 / int(sizeof(T));
+            const T* Bw = Bj + lo;
+#pragma unroll 2
+            for (int c = threadIdx.x; c < W; c += THREADS) {
+                T x[CJ];
+#pragma unroll
+                for (int jj = 0; jj < CJ; ++jj) x[jj] = jj < ncj ? __ldg(Bw + jj * ldb + c) : zero;
+                uint4* dst = reinterpret_cast<uint4*>(sB + size_t(c) * CJ);
+#pragma unroll
+                for (int q = 0; q < CJ / PER; ++q) {
+                    uint4 v;
+                    memcpy(&v, &x[q * PER], 16);
+                    dst[q] = v;
+                }
+            }
+            __syncthreads();
+            if (ncj == CJ) spmm_rows<T, SR, CJ, U, true, true>(nrow, rp, colval, nzval, base, sB, lo, Bj, ldb, Cr, ldc, ncj, accumulate);
+            else spmm_rows<T, SR, CJ, U, true, false>(nrow, rp, colval, nzval, base, sB, lo, Bj, ldb, Cr, ldc, ncj, accumulate);
+        } else {
+            spmm_rows<T, SR, CJ, U, false, false>(nrow, rp, colval, nzval, base, sB, lo, Bj, ldb, Cr, ldc, ncj, accumulate);
         }
     }
 }

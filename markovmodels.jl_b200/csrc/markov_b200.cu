@@ -1309,27 +1309,28 @@ template <typename T, int SR>
 static int spmv_launch(int64_t n_rows, int64_t nnz, const int32_t* rowptr, const int32_t* colval, const void* nzval,
                        int base, const void* b, void* c, int sms, cudaStream_t st) {
     // lanes per row and arcs per lane and chunk from the mean row length: Ĉ-like matrices (1 arc per row) 4 x 2; the
-    // path's graphs (~17 arcs per row) 4 x 8 — 8 rows per warp with up to 32 arcs each in flight (8 lanes x 4 arcs
-    // measured 0.37 ms against 0.30 ms on the block-diagonal T̂ᵀ of cfg 3); dense-ish rows (ω as a 1-row matrix) a warp.
+    // path's graphs (~17 arcs per row) 2 x 12 — 16 rows per warp with up to 24 arcs each in flight (measured on the
+    // block-diagonal T̂ᵀ of cfg 3: 8 lanes x 4 arcs 0.37 ms, 4 x 8 0.268, 2 x 16 0.261, 2 x 12 0.259, 1 x 32 0.34);
+    // dense-ish rows (ω as a 1-row matrix) a warp.
     const double mean = double(nnz) / double(std::max<int64_t>(n_rows, 1));
-    const int lanes = mean <= 24 ? 4 : 32;
-    const int per_lane = mean <= 6 ? 2 : (mean <= 24 ? 8 : 4);
+    const T* v = static_cast<const T*>(nzval); const T* bb = static_cast<const T*>(b); T* cc = static_cast<T*>(c);
+    const int lanes = mean <= 6 ? 4 : (mean <= 24 ? 2 : 32);
+    const int per_lane = mean <= 6 ? 2 : (mean <= 24 ? 12 : 4);
     const int threads = 256;
     const int64_t want = (n_rows * lanes + threads - 1) / threads;
     const int blocks = int(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(sms) * 32)));  // grid-stride beyond
-    const T* v = static_cast<const T*>(nzval); const T* bb = static_cast<const T*>(b); T* cc = static_cast<T*>(c);
-    // rows more than 16 x longer than a lane group's chunk go to a work list and get a CTA each (stream-ordered scratch)
-    const int long_row = lanes * per_lane * 16;
+    // rows far longer than a lane group's chunk go to a work list and get a CTA each (stream-ordered scratch)
+    const int long_row = lanes == 32 ? 2048 : 512;
     const int cap = int(std::min<int64_t>(n_rows, kSpmvWorklistCap));
     int* wl = nnz > long_row ? spmv_worklist(st, kSpmvWorklistCap) : nullptr;  // (none: the long rows are done in place)
     if (wl) CK(cudaMemsetAsync(wl, 0, sizeof(int), st));
-    if (lanes == 4 && per_lane == 2) spmv_kernel<T, SR, 4, 2><<<blocks, threads, 0, st>>>(n_rows, rowptr, colval, v, base, bb, cc, long_row, wl, cap);
-    else if (lanes == 4) spmv_kernel<T, SR, 4, 8><<<blocks, threads, 0, st>>>(n_rows, rowptr, colval, v, base, bb, cc, long_row, wl, cap);
+    if (lanes == 4) spmv_kernel<T, SR, 4, 2><<<blocks, threads, 0, st>>>(n_rows, rowptr, colval, v, base, bb, cc, long_row, wl, cap);
+    else if (lanes == 2) spmv_kernel<T, SR, 2, 12><<<blocks, threads, 0, st>>>(n_rows, rowptr, colval, v, base, bb, cc, long_row, wl, cap);
     else spmv_kernel<T, SR, 32, 4><<<blocks, threads, 0, st>>>(n_rows, rowptr, colval, v, base, bb, cc, long_row, wl, cap);
     CK(cudaGetLastError());
     ++g_launches;
     if (wl) {
-        spmv_long_kernel<T, SR><<<sms, 256, 0, st>>>(wl, cap, rowptr, colval, v, base, bb, cc);
+        spmv_long_kernel<T, SR><<<sms, 512, 0, st>>>(wl, cap, rowptr, colval, v, base, bb, cc);
         CK(cudaGetLastError());
         ++g_launches;
     }
@@ -1343,6 +1344,34 @@ static int spmm_launch(int64_t n_rows, const int32_t* rowptr, const int32_t* col
 #define MK_SPMM_CJ 8
 #endif
     constexpr int CJ = MK_SPMM_CJ;  // columns per thread (tools/ab_variants.py; Ĉ·V̂ at cfg 3)
+    // Large products go through the shared-memory window of B (linalg.cuh, spmm_staged_kernel): blocks of rb_rows rows x 4
+    // columns, the column window of every row block found by a pre-pass on the same stream.  MK_SPMM_STAGED=0 keeps the
+    // direct kernel; MK_SPMM_RB overrides the rows per block.
+    static const int staged_on = [] { const char* e = getenv("MK_SPMM_STAGED"); return e ? atoi(e) : 1; }();
+    static const int rb_env = [] { const char* e = getenv("MK_SPMM_RB"); return e ? atoi(e) : 0; }();
+    if (staged_on && n_rows >= (1 << 17) && cols >= 4) {
+        constexpr int SCJ = 4;
+        constexpr int kWindowBytes = 110 * 1024;  // two CTAs per SM
+        const int rb_rows = rb_env > 0 ? rb_env : 16384;
+        const int64_t nblocks = (n_rows + rb_rows - 1) / rb_rows;
+        int* win = nblocks <= 32768 ? spmv_worklist(st, kSpmvWorklistCap) : nullptr;
+        if (win) {
+            spmm_window_kernel<<<unsigned(nblocks), 512, 0, st>>>(n_rows, rb_rows, rowptr, colval, base, win);
+            CK(cudaGetLastError());
+            dim3 sgrid(unsigned(std::min<int64_t>((cols + SCJ - 1) / SCJ, 65535)), unsigned(nblocks));
+            // 512 threads x 8 rows in flight per thread, two CTAs per SM (measured at cfg 3: 512 x 4 0.71 ms, 256 x 16 0.74 ms,
+            // 256 x 8 0.79 ms, this 0.67 ms; spmm_kernel 1.11 ms)
+            constexpr int THREADS = 512, U = 8;
+            CK(cudaFuncSetAttribute(spmm_staged_kernel<T, SR, SCJ, THREADS, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kWindowBytes));  // (per device; cheap)
+            spmm_staged_kernel<T, SR, SCJ, THREADS, U><<<sgrid, THREADS, kWindowBytes, st>>>(
+                n_rows, rb_rows, rowptr, colval, static_cast<const T*>(nzval), base, static_cast<const T*>(B), ldb,
+                static_cast<T*>(C), ldc, cols, accumulate, win, kWindowBytes / int(SCJ * sizeof(T)));
+            CK(cudaGetLastError());
+            g_launches += 2;
+            return MK_OK;
+        }
+    }
     dim3 grid(unsigned((n_rows + 255) / 256), unsigned(std::min<int64_t>((cols + CJ - 1) / CJ, 65535)));
     spmm_kernel<T, SR, CJ><<<grid, 256, 0, st>>>(n_rows, rowptr, colval, static_cast<const T*>(nzval), base,
                                                  static_cast<const T*>(B), ldb, static_cast<T*>(C), ldc, cols, accumulate);

@@ -118,6 +118,49 @@ def test_mul_random_graph_sizes(torch, mm, orc, sr, dtype):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("sr", SEMIRINGS)
+def test_mul_matrix_block_diagonal_large(torch, mm, orc, sr, dtype):
+    """Ĉ·V̂ at scale (src/inference.jl:150): products with >= 2^17 rows stage the column window of every block of rows
+    in shared memory.  Block-diagonal part (narrow windows: staged; in Float64 some windows are too wide and read B
+    directly), a tail of rows with columns all over the matrix (never staged), one-arc and many-arc rows, empty rows,
+    0̄ entries, 7 columns (a full chunk of 4 and a partial one), padded leading dimensions, β = 0 and β = 1."""
+    K = _K(mm, sr, dtype)
+    rng = np.random.default_rng(11)
+    blk_rows, blk_cols, nblk, tail = 7000, 900, 20, 12000
+    m, n = blk_rows * nblk + tail, blk_cols * nblk
+    per_row = rng.integers(0, 4, m)
+    per_row[rng.random(m) < 0.6] = 1
+    I = np.repeat(np.arange(1, m + 1), per_row)  # noqa: E741
+    blk = np.minimum((I - 1) // blk_rows, nblk - 1)
+    J = blk * blk_cols + rng.integers(0, blk_cols, I.size) + 1
+    in_tail = I > blk_rows * nblk
+    J[in_tail] = rng.integers(1, n + 1, int(in_tail.sum()))
+    _, first = np.unique(np.stack([I, J]), axis=1, return_index=True)
+    I, J = I[first], J[first]  # noqa: E741
+    if K.code == 2:
+        V, Bm = rng.random(I.size), rng.random((n, 7))
+        V[::11] = 0.0
+    else:
+        V, Bm = rng.standard_normal(I.size) * 3, rng.standard_normal((n, 7)) * 30
+        V[::11] = -np.inf
+        Bm[::13, :] = -np.inf
+    V, Bm = V.astype(dtype), Bm.astype(dtype)
+    A = mm.CuSparseMatrixCSR(K, I, J, V, m, n)
+    bigB = mm.linalg.colmajor(K, n + 5, 7, fill=float(K.zero))
+    bigB[:n, :] = torch.from_numpy(Bm).cuda()
+    big = mm.linalg.colmajor(K, m + 3, 7, fill=777.0)
+    C = big[:m, :]
+    mm.mul_(C, A, bigB[:n, :])
+    want = _oracle_mul(orc, K, I, J, V, m, n, Bm)
+    tol = dict(rtol=1e-4 if dtype == np.float32 else 1e-11, atol=1e-30)
+    np.testing.assert_allclose(C.cpu().numpy(), want, **tol)
+    np.testing.assert_array_equal(big[m:, :].cpu().numpy(), np.full((3, 7), 777.0))  # padding rows untouched
+    mm.mul_(C, A, bigB[:n, :], True, True)
+    np.testing.assert_allclose(C.cpu().numpy(), K.add_ufunc(want, want), **tol)
+
+
+@pytest.mark.gpu
 def test_mul_log_full_range(torch, mm):
     """⊕ of the Log semiring never exponentiates an un-shifted value: payloads around ±1e4 (exp overflows /
     underflows in both precisions) still give max + log(count)."""
