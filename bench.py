@@ -204,7 +204,13 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (libmarkov_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
     binding = "unbound"
-    if world > 1 and os.environ.get("MK_BENCH_BIND", "1") != "0":
+    try:
+        affinity0 = os.sched_getaffinity(0)
+    except AttributeError:
+        affinity0 = None
+    # (also at N = 1: where the pinned buffers of the e2e leg land decides its PCIe rate — the same call measured
+    # 7.8 and 8.5 ms per step on two runs of an unbound process; the CPU baseline gets the full core set back below)
+    if os.environ.get("MK_BENCH_BIND", "1") != "0":
         binding = bind_rank_to_cores(torch, local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     dist = None
     if world > 1:
@@ -288,27 +294,33 @@ def run_ours(args):
         step_e2e()
     torch.cuda.synchronize()
     single_t = torch.tensor([time.perf_counter() - t0], device="cuda")
-    # The same steps double-buffered: two batch objects (one graph) alternate, step k+1's host-to-device copy and
-    # forward sweep overlap step k's device-to-host copy (PCIe is full duplex).  Every step still copies its inputs
-    # in from pinned memory and its posteriors and log-likelihoods out, and the host reads each result.
-    bf2 = [bfsm, mm.batch(*[cfsm] * B)]
-    post_h2 = torch.empty((T, D, B), pin_memory=True)
-    ttl_h2 = torch.empty((B,), pin_memory=True)
-    outs = [(post_np, ttl_np), (post_h2.numpy(), ttl_h2.numpy())]
+    # The same steps with three calls in flight: three batch objects (one graph) take turns, so that step k+1's and
+    # k+2's host-to-device copies overlap step k's sweeps and step k-1's device-to-host copy (PCIe is full duplex; with
+    # two objects the copies of one batch — 2 x 4.2 ms — no longer fit beside the other's 7.4 ms of sweeps).  Every step
+    # still copies its inputs in from pinned memory and its posteriors and log-likelihoods out, and the host reads
+    # each result.
+    DEPTH = 3
+    bf2 = [bfsm] + [mm.batch(*[cfsm] * B) for _ in range(DEPTH - 1)]
+    outs = [(post_np, ttl_np)]
+    keep_pinned = []
+    for _ in range(DEPTH - 1):
+        ph, th = torch.empty((T, D, B), pin_memory=True), torch.empty((B,), pin_memory=True)
+        keep_pinned.append((ph, th))
+        outs.append((ph.numpy(), th.numpy()))
     checks = []
 
     def run_pipelined(n):
         for k in range(n):
-            j = k & 1
-            if k >= 2:
+            j = k % DEPTH
+            if k >= DEPTH:
                 bf2[j].wait()
                 checks.append(float(outs[j][1].sum()))
             mm.pdfposteriors(bf2[j], Vh_np, out=outs[j], wait=False)
-        for k in range(max(0, n - 2), n):
-            bf2[k & 1].wait()
-            checks.append(float(outs[k & 1][1].sum()))
+        for k in range(max(0, n - DEPTH), n):
+            bf2[k % DEPTH].wait()
+            checks.append(float(outs[k % DEPTH][1].sum()))
 
-    run_pipelined(3)
+    run_pipelined(2 * DEPTH)
     sync_all()
     t0 = time.perf_counter()
     run_pipelined(args.steps)
@@ -319,11 +331,11 @@ def run_ours(args):
         dist.all_reduce(single_t, op=dist.ReduceOp.MAX)
     e2e_s, single_s = float(e2e_t), float(single_t)
     torch.testing.assert_close(torch.from_numpy(outs[1][1]).cuda(), ttl, rtol=1e-5, atol=1e-3)
-    # the same two batches with DEVICE-resident inputs, one stream each (what the overlap buys without PCIe in the way)
+    # two of these batches with DEVICE-resident inputs, one stream each (what overlap buys without PCIe in the way)
     # (SM sharing on: each batch's sweeps run with half the threads per CTA, so the two cooperative kernels are
-    # co-resident and one fills the other's grid-barrier waits; it does not pay inside the host pipeline above, whose
-    # sweeps are cut into short segments: 8.39 against 8.24 ms per step)
-    for bb in bf2:
+    # co-resident and one fills the other's grid-barrier waits; it did not pay inside the host pipeline above:
+    # 8.39 against 8.24 ms per step when measured with two calls in flight)
+    for bb in bf2[:2]:
         bb.set_overlap(True)
     dev_out = [(post, ttl), (torch.empty_like(post), torch.empty_like(ttl))]
     side = [torch.cuda.Stream(), torch.cuda.Stream()]
@@ -343,7 +355,7 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(two_t, op=dist.ReduceOp.MAX)
     two_s = float(two_t)
-    for bb in bf2:
+    for bb in bf2[:2]:
         bb.set_overlap(False)
     h2d = Vh.numel() * 4
     d2h = (post_h.numel() + ttl_h.numel()) * 4
@@ -381,8 +393,9 @@ def run_ours(args):
         "config": workload_config(world, B, T),
         "e2e": {"value": frames_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
-                "how": "host buffers through mk_pdfposteriors_host_begin / mk_batch_wait, two batches in flight "
-                       "(double-buffered): every step copies its inputs in and its results out inside the timed region",
+                "how": "host buffers through mk_pdfposteriors_host_begin / mk_batch_wait, three batches in flight: "
+                       "every step copies its inputs in and its results out inside the timed region",
+                "calls_in_flight": DEPTH,
                 "single_call": {"value": frames_total * args.steps / single_s, "unit": UNIT,
                                 "ms_per_step": 1e3 * single_s / args.steps,
                                 "how": "one blocking mk_pdfposteriors_host call per step (latency of a lone call)"}},
@@ -418,6 +431,11 @@ def run_ours(args):
     }
     if world == 1 and not args.skip_cpu_baseline:
         import oracle
+        if affinity0 is not None:
+            try:
+                os.sched_setaffinity(0, affinity0)
+            except OSError:
+                pass
         threads = oracle.num_threads()
         n_utts, frames = threads, T
         v = cpu_sample(fsm, pdfids, n_utts, frames, threads)

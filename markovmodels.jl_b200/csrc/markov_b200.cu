@@ -1755,10 +1755,11 @@ static int posteriors_host(mk_batch* b, const void* ll, int64_t sb, int64_t sd, 
     // cut into frame segments; the copy stream brings slice k+1 in while the forward sweep runs slice k, and
     // takes the posteriors of segment k out while the backward sweep runs segment k-1.  MK_NO_PIPELINE=1 disables.
     // Segments: a lone blocking call wants many (the un-overlapped first copy in and last copy out shrink: 8 segments
-    // 9.78 ms, 12 9.59 ms on the 128 x 150 x 3000 call); calls that overlap each other want few (fewer launches, the
-    // neighbour call hides head and tail: 2 segments 8.36 ms, 4 8.27 ms, 12 8.53 ms per step, double-buffered)
-    int K = int(std::min<int64_t>(wait ? 12 : 4, T / 8));
-    if (getenv("MK_SEGMENTS") && atoi(getenv("MK_SEGMENTS")) >= 1) K = std::min(K, atoi(getenv("MK_SEGMENTS")));  // (tuning)
+    // 9.78 ms, 12 9.59 ms on the 128 x 150 x 3000 call).  Calls that overlap each other (begin / wait) want none: the
+    // neighbour calls hide the copies, segments only add launches and event waits — per step at cfg 3, two batches in
+    // flight: 1 segment 8.30 ms, 2 7.96, 4 8.15; three in flight: 1 segment 7.77, 2 8.38, 4 8.39 (tools/e2e_depth_probe.py).
+    int K = int(std::min<int64_t>(wait ? 12 : 1, T / 8));
+    if (getenv("MK_SEGMENTS") && atoi(getenv("MK_SEGMENTS")) >= 1) K = int(std::min<int64_t>(std::min<int64_t>(atoi(getenv("MK_SEGMENTS")), int64_t(mk_batch::kMaxSegments)), T / 8));  // (tuning)
     const bool pipe = b->groups.size() == 1 && b->small.empty() && !expanded && sd == 1 && sn == D && sb == T * D &&
                       K >= 2 && !(getenv("MK_NO_PIPELINE") && atoi(getenv("MK_NO_PIPELINE")));
     if (pipe) {

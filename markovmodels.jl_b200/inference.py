@@ -366,7 +366,8 @@ def pdfposteriors(x, V, Ĉs=None, seqlengths=None, out=None, stats=None, wait=Tr
     of ``D + 2`` entries that receives the data-parallel step statistics ``[Σ logZ, #frames,
     occupancy[D]]`` (``mk_pdfposteriors_stats``; see :mod:`sharding`).  ``wait=False`` (host input with
     ``out=`` PINNED buffers only): enqueue the copies and kernels and return; ``x.wait()`` completes the call
-    (``mk_pdfposteriors_host_begin`` / ``mk_batch_wait`` — double buffering with two ``batch`` objects)."""
+    (``mk_pdfposteriors_host_begin`` / ``mk_batch_wait`` — keep three ``batch`` objects in flight: the copies of
+    one call then fit beside the sweeps of the other two)."""
     B = len(V) if isinstance(V, (list, tuple)) else V.shape[0]
     b = _as_batch(x, Ĉs, B)
     e = _emissions(V, b.K, b.n_pdf_hat)
