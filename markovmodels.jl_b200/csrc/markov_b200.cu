@@ -17,6 +17,7 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <memory>
+#include <atomic>
 #include <mutex>
 #include <functional>
 #include <limits>
@@ -1562,9 +1563,11 @@ int mk_batch_create(mk_batch** out, mk_graph* const* graphs, int64_t B) {
     return MK_OK;
 }
 
+static void set_host_pending(mk_batch* b, bool pending);
 int mk_batch_destroy(mk_batch* b) {
     if (!b) return MK_OK;
     DeviceGuard guard(b->device);
+    set_host_pending(b, false);  // (the destructor drains the batch's streams)
     delete b;
     return MK_OK;
 }
@@ -1723,13 +1726,22 @@ int mk_batch_set_overlap(mk_batch* b, int enable) {
     if (enable && e && atoi(e) >= 64 && atoi(e) <= kSharedThreads && atoi(e) % 32 == 0) b->shared_threads = atoi(e);
     return MK_OK;
 }
+// Host-buffer calls begun and not yet waited for, per device: a call that starts with none in flight has no neighbour to
+// hide its copies behind.
+static std::atomic<int> g_host_inflight[64];
+static void set_host_pending(mk_batch* b, bool pending) {
+    if (b->host_pending == pending) return;
+    b->host_pending = pending;
+    if (b->device >= 0 && b->device < 64) g_host_inflight[b->device] += pending ? 1 : -1;
+}
+
 int mk_batch_wait(mk_batch* b) {
     if (!b) return fail(MK_EINVAL, "null batch");
     DeviceGuard guard(b->device);
     if (!guard.ok) return fail(MK_ECUDA, "cannot select CUDA device %d", b->device);
     if (b->own_stream) CK(cudaStreamSynchronize(b->own_stream));
     if (b->copy_stream) CK(cudaStreamSynchronize(b->copy_stream));
-    b->host_pending = false;
+    set_host_pending(b, false);
     return MK_OK;
 }
 
@@ -1742,7 +1754,8 @@ static int posteriors_host(mk_batch* b, const void* ll, int64_t sb, int64_t sd, 
     if (!guard.ok) return fail(MK_ECUDA, "cannot select CUDA device %d", b->device);
     // one call per batch at a time: the staging buffers and workspaces belong to the batch (several batches overlap)
     if (b->host_pending) TRY(mk_batch_wait(b));
-    b->host_pending = !wait;
+    const bool alone = b->device < 0 || b->device >= 64 || g_host_inflight[b->device].load() == 0;
+    set_host_pending(b, !wait);
     const size_t ts = tsize(b->dtype);
     const int64_t Dout = expanded ? D - 1 : D, Tout = expanded ? T - 1 : T;
     const size_t in_bytes = size_t(extent(b->B, D, T, sb, sd, sn)) * ts;
@@ -1757,8 +1770,9 @@ static int posteriors_host(mk_batch* b, const void* ll, int64_t sb, int64_t sd, 
     // Segments: a lone blocking call wants many (the un-overlapped first copy in and last copy out shrink: 8 segments
     // 9.78 ms, 12 9.59 ms on the 128 x 150 x 3000 call).  Calls that overlap each other (begin / wait) want none: the
     // neighbour calls hide the copies, segments only add launches and event waits — per step at cfg 3, two batches in
-    // flight: 1 segment 8.30 ms, 2 7.96, 4 8.15; three in flight: 1 segment 7.77, 2 8.38, 4 8.39 (tools/e2e_depth_probe.py).
-    int K = int(std::min<int64_t>(wait ? 12 : 1, T / 8));
+    // flight: 1 segment 8.46 ms, 2 8.07, 4 8.16; three in flight: 1 segment 7.77, 2 8.2, 4 8.5 (tools/e2e_depth_probe.py).
+    // The first call of such a sequence (none in flight when it begins) has no neighbour yet: 4 segments.
+    int K = int(std::min<int64_t>(wait ? 12 : (alone ? 4 : 1), T / 8));
     if (getenv("MK_SEGMENTS") && atoi(getenv("MK_SEGMENTS")) >= 1) K = int(std::min<int64_t>(std::min<int64_t>(atoi(getenv("MK_SEGMENTS")), int64_t(mk_batch::kMaxSegments)), T / 8));  // (tuning)
     const bool pipe = b->groups.size() == 1 && b->small.empty() && !expanded && sd == 1 && sn == D && sb == T * D &&
                       K >= 2 && !(getenv("MK_NO_PIPELINE") && atoi(getenv("MK_NO_PIPELINE")));
