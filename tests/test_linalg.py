@@ -120,6 +120,47 @@ def test_mul_random_graph_sizes(torch, mm, orc, sr, dtype):
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("sr", SEMIRINGS)
+def test_mul_vector_block_diagonal_large(torch, mm, orc, sr, dtype):
+    """blockdiag(T̂ᵀ ...) ⊗ b at scale (one frame of the reference's αrecursion, src/inference.jl:69-72): matrices of >= 2^16
+    graph-like rows go through the kernel that keeps a window of b in shared memory.  14 blocks of 5 000 x 5 000 (a row block
+    of the kernel sees one or two of them; in Float64 the window holds only 15 360 entries), ~17 arcs per row, every 97th row
+    with arcs all over the matrix (outside any window), one long row per block (the phony final state's), an empty row,
+    0̄ entries."""
+    K = _K(mm, sr, dtype)
+    rng = np.random.default_rng(13)
+    blk, nblk = 5000, 14
+    m = n = blk * nblk
+    per_row = rng.integers(8, 27, m)
+    I = np.repeat(np.arange(1, m + 1), per_row)  # noqa: E741
+    J = ((I - 1) // blk) * blk + rng.integers(0, blk, I.size) + 1
+    far = (I % 97) == 0
+    J[far] = rng.integers(1, n + 1, int(far.sum()))
+    keep = I != 3  # an empty row
+    I, J = I[keep], J[keep]  # noqa: E741
+    for k in range(nblk):  # the long rows: 1 200 arcs from the block's first columns
+        I = np.concatenate([I, np.full(1200, (k + 1) * blk)])  # noqa: E741
+        J = np.concatenate([J, k * blk + np.arange(1, 1201)])
+    _, first = np.unique(np.stack([I, J]), axis=1, return_index=True)
+    I, J = I[first], J[first]  # noqa: E741
+    if K.code == 2:
+        V, b = rng.random(I.size), rng.random(n)
+        V[::11] = 0.0
+    else:
+        V, b = rng.standard_normal(I.size) * 3, rng.standard_normal(n) * 30
+        V[::11] = -np.inf
+        b[::13] = -np.inf
+    V, b = V.astype(dtype), b.astype(dtype)
+    A = mm.CuSparseMatrixCSR(K, I, J, V, m, n)
+    got = mm.mul_(torch.full((m,), 777.0, dtype=torch.from_numpy(b).dtype, device="cuda"), A,
+                  torch.from_numpy(b).cuda()).cpu().numpy()
+    want = _oracle_mul(orc, K, I, J, V, m, n, b)
+    np.testing.assert_allclose(got, want, rtol=1e-4 if dtype == np.float32 else 1e-11, atol=1e-30)
+    assert got[2] == K.zero
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("sr", SEMIRINGS)
 def test_mul_matrix_block_diagonal_large(torch, mm, orc, sr, dtype):
     """Ĉ·V̂ at scale (src/inference.jl:150): products with >= 2^17 rows stage the column window of every block of rows
     in shared memory.  Block-diagonal part (narrow windows: staged; in Float64 some windows are too wide and read B
