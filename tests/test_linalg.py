@@ -202,6 +202,40 @@ def test_mul_matrix_block_diagonal_large(torch, mm, orc, sr, dtype):
 
 
 @pytest.mark.gpu
+def test_mul_zero_based_indices_large(torch, mm):
+    """The C ABI takes CUSPARSE-style 0-based arrays as well (`index_base = 0`): the batch-sized kernels (row-block windows of
+    mk_spmm, lane groups + long-row list of mk_spmv) must give the same bits as with CUDA.jl's 1-based arrays."""
+    from markov_b200 import _lib
+    K = mm.LogSemiring[np.float32]
+    rng = np.random.default_rng(17)
+    blk, nblk = 6000, 24
+    m, n = blk * nblk, 500 * nblk
+    per_row = rng.integers(1, 4, m)
+    I = np.repeat(np.arange(1, m + 1), per_row)  # noqa: E741
+    J = ((I - 1) // blk) * 500 + rng.integers(0, 500, I.size) + 1
+    _, first = np.unique(np.stack([I, J]), axis=1, return_index=True)
+    I, J = I[first], J[first]  # noqa: E741
+    V = (rng.standard_normal(I.size) * 3).astype(np.float32)
+    A = mm.CuSparseMatrixCSR(K, I, J, V, m, n)
+    B = mm.linalg.to_colmajor(K, (rng.standard_normal((n, 6)) * 5).astype(np.float32))
+    b = B[:, 0].contiguous()
+    C1 = mm.mul_(mm.linalg.colmajor(K, m, 6), A, B)
+    c1 = mm.mul_(torch.empty(m, device="cuda"), A, b)
+    rp0, cv0 = (A.rowPtr - 1).contiguous(), (A.colVal - 1).contiguous()
+    C0 = mm.linalg.colmajor(K, m, 6)
+    c0 = torch.empty(m, device="cuda")
+    l = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(l.mk_spmm(K.code, K.dtype_code, m, n, A.nnz, rp0.data_ptr(), cv0.data_ptr(), A.nzVal.data_ptr(), 0, B.data_ptr(),
+                         n, 6, B.stride(1), C0.data_ptr(), m, 6, C0.stride(1), 0, st))
+    _lib.check(l.mk_spmv(K.code, K.dtype_code, m, n, A.nnz, rp0.data_ptr(), cv0.data_ptr(), A.nzVal.data_ptr(), 0, b.data_ptr(),
+                         n, c0.data_ptr(), m, st))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(C0.cpu().numpy(), C1.cpu().numpy())
+    np.testing.assert_array_equal(c0.cpu().numpy(), c1.cpu().numpy())
+
+
+@pytest.mark.gpu
 def test_mul_log_full_range(torch, mm):
     """⊕ of the Log semiring never exponentiates an un-shifted value: payloads around ±1e4 (exp overflows /
     underflows in both precisions) still give max + log(count)."""
