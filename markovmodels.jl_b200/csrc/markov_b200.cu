@@ -1355,7 +1355,7 @@ static int spmm_launch(int64_t n_rows, const int32_t* rowptr, const int32_t* col
         constexpr int kWindowBytes = 110 * 1024;  // two CTAs per SM
         const int rb_rows = rb_env > 0 ? rb_env : 16384;
         const int64_t nblocks = (n_rows + rb_rows - 1) / rb_rows;
-        int* win = nblocks <= 32768 ? spmv_worklist(st, kSpmvWorklistCap) : nullptr;
+        int* win = 3 * nblocks <= kSpmvWorklistCap ? spmv_worklist(st, kSpmvWorklistCap) : nullptr;  // {lo, hi, one-arc rows} per block
         if (win) {
             spmm_window_kernel<<<unsigned(nblocks), 512, 0, st>>>(n_rows, rb_rows, rowptr, colval, base, win);
             CK(cudaGetLastError());

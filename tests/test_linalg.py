@@ -202,6 +202,38 @@ def test_mul_matrix_block_diagonal_large(torch, mm, orc, sr, dtype):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("sr", SEMIRINGS)
+def test_mul_matrix_one_arc_rows_large(torch, mm, sr, dtype):
+    """Ĉ·V̂ (src/inference.jl:150; Ĉ has exactly one entry per row, examples/prepare-lfmmi-graphs.jl:15-23) at batch size: the
+    Float32 kernel takes four adjacent rows per thread and writes 16 bytes per column.  The ⊕ over one term is the term, so the
+    result is exact: C[i, j] = A[i, c_i] ⊗ B[c_i, j].  Row counts divisible by four and not (tail rows, unaligned columns),
+    9 columns (two full chunks and a partial one), 0̄ weights and operands."""
+    K = _K(mm, sr, dtype)
+    rng = np.random.default_rng(19)
+    blk_rows, blk_cols = 9000, 700
+    for m in (144000, 144003):
+        nblk = (m + blk_rows - 1) // blk_rows
+        n = nblk * blk_cols
+        I = np.arange(1, m + 1)  # noqa: E741
+        J = ((I - 1) // blk_rows) * blk_cols + rng.integers(0, blk_cols, m) + 1
+        if K.code == 2:
+            V, Bm = rng.random(m), rng.random((n, 9))
+            V[::17] = 0.0
+            want = V[:, None] * Bm[J - 1, :]
+        else:
+            V, Bm = rng.standard_normal(m) * 3, rng.standard_normal((n, 9)) * 30
+            V[::17] = -np.inf
+            Bm[::13, :] = -np.inf
+            want = V[:, None] + Bm[J - 1, :]
+        V, Bm = V.astype(dtype), Bm.astype(dtype)
+        want = (V[:, None] * Bm[J - 1, :]) if K.code == 2 else (V[:, None] + Bm[J - 1, :])
+        A = mm.CuSparseMatrixCSR(K, I, J, V, m, n)
+        C = mm.mul_(mm.linalg.colmajor(K, m, 9, fill=777.0), A, mm.linalg.to_colmajor(K, Bm))
+        np.testing.assert_array_equal(C.cpu().numpy(), want.astype(dtype))
+
+
+@pytest.mark.gpu
 def test_mul_zero_based_indices_large(torch, mm):
     """The C ABI takes CUSPARSE-style 0-based arrays as well (`index_base = 0`): the batch-sized kernels (row-block windows of
     mk_spmm, lane groups + long-row list of mk_spmv) must give the same bits as with CUDA.jl's 1-based arrays."""
