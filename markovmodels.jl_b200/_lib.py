@@ -54,7 +54,7 @@ def build(force=False, verbose=False):
     from concurrent.futures import ThreadPoolExecutor
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     flags = [f for f in NVCC_FLAGS if f != "-shared"]
-    for knob in ("MK_PASS_QUADS", "MK_THREADS", "MK_PROFILE_BARRIER", "MK_ABLATE", "MK_SPMM_CJ", "MK_SPMM_STCS", "MK_L2_HINTS"):  # kernel tuning knobs (defaults in kernels.cuh)
+    for knob in ("MK_PASS_QUADS", "MK_THREADS", "MK_PROFILE_BARRIER", "MK_ABLATE", "MK_SPMM_CJ", "MK_SPMM_STCS", "MK_L2_HINTS", "MK_TR_BATCH"):  # kernel tuning knobs (defaults in kernels.cuh)
         if os.environ.get(knob):
             flags.insert(0, f"-D{knob}={os.environ[knob]}")
     if verbose:

@@ -1455,21 +1455,51 @@ template <typename T> __global__ void __launch_bounds__(256) expand_transpose_wi
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = p.n0 + blockIdx.z;
     const int d0 = blockIdx.x * DT, u0 = blockIdx.y * 128;
-#pragma unroll 4
-    for (int ul = warp; ul < 128; ul += 8) {
-        const int u = u0 + ul;
-        int b = -1, L = 0;
+    // The warp's 16 utterances: index and length first (lanes 0-15 fetch one each: two dependent loads once per warp instead of
+    // once per utterance), then the emissions in batches of kTrBatch utterances — every load of a batch is requested before any
+    // value is used (the straightforward loop had 2-4 loads in flight per lane: the compiler does not hoist loads over
+    // emission()'s branches).
+#ifndef MK_TR_BATCH
+#define MK_TR_BATCH 8
+#endif
+    constexpr int kTrBatch = MK_TR_BATCH, kPerLane = DT / 32;
+    int my_b = -1, my_L = 0;
+    if (lane < 16) {
+        const int u = u0 + warp + 8 * lane;
         if (u < p.U4) {
-            b = p.utt_b[u];
-            if (b >= 0) L = p.seqlens ? p.seqlens[b] : p.Tn;
+            my_b = p.utt_b[u];
+            if (my_b >= 0) my_L = p.seqlens ? p.seqlens[my_b] : p.Tn;
+        }
+    }
+#pragma unroll
+    for (int k0 = 0; k0 < 16; k0 += kTrBatch) {
+        T v[kTrBatch][kPerLane];
+        unsigned loaded = 0;
+#pragma unroll
+        for (int k = 0; k < kTrBatch; ++k) {
+            const int b = __shfl_sync(0xffffffffu, my_b, k0 + k), L = __shfl_sync(0xffffffffu, my_L, k0 + k);
+#pragma unroll
+            for (int j = 0; j < kPerLane; ++j) {
+                const int d = d0 + lane + 32 * j;
+                // `expand` (src/inference.jl:54-60) without the load where the value is a constant; see emission()
+                T cst = neg_inf<T>();
+                bool need = b >= 0 && d < p.Dh;
+                if (need && !(p.expanded & 1)) {
+                    if (d < p.D) need = n < L;
+                    else { need = false; cst = n < L ? neg_inf<T>() : T(0); }
+                }
+                v[k][j] = need ? __ldg(p.ll + b * p.sb + d * p.sd + n * p.sn) : cst;
+                loaded |= need ? 1u << (k * kPerLane + j) : 0u;
+            }
         }
 #pragma unroll
-        for (int dl = lane; dl < DT; dl += 32) {
-            const int d = d0 + dl;
-            T v = neg_inf<T>();
-            if (b >= 0 && d < p.Dh) v = emission<T>(p.ll, p.sb, p.sd, p.sn, p.D, p.expanded, L, b, d, n);
-            tile[dl][ul] = v * p.scale;
-        }
+        for (int k = 0; k < kTrBatch; ++k)
+#pragma unroll
+            for (int j = 0; j < kPerLane; ++j) {
+                T x = v[k][j];
+                if ((p.expanded & 2) && ((loaded >> (k * kPerLane + j)) & 1u)) x = log_(x);  // ProbSemiring payloads
+                tile[lane + 32 * j][warp + 8 * (k0 + k)] = x * p.scale;
+            }
     }
     __syncthreads();
     T m[4];
