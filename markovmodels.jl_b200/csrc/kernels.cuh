@@ -1412,17 +1412,35 @@ template <typename T> __global__ void expand_transpose_kernel(EmisParams<T> p) {
     __shared__ T tile[32][33];
     const int n = p.n0 + blockIdx.z;
     const int d0 = blockIdx.x * 32, u0 = blockIdx.y * 32;
-    for (int k = threadIdx.y; k < 32; k += 8) {
-        int u = u0 + k, d = d0 + threadIdx.x;
-        T v = neg_inf<T>();
-        if (u < p.U4 && d < p.Dh) {
-            int b = p.utt_b[u];
-            if (b >= 0) {
-                int L = p.seqlens ? p.seqlens[b] : p.Tn;
-                v = emission<T>(p.ll, p.sb, p.sd, p.sn, p.D, p.expanded, L, b, d, n);
-            }
+    {   // the thread's four (utterance, pdf) elements: indices, lengths and values each requested together
+        const int d = d0 + threadIdx.x;
+        int b4[4], L4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int u = u0 + threadIdx.y + 8 * i;
+            b4[i] = (u < p.U4 && d < p.Dh) ? p.utt_b[u] : -1;
         }
-        tile[k][threadIdx.x] = v * p.scale;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) L4[i] = (b4[i] >= 0 && p.seqlens) ? p.seqlens[b4[i]] : p.Tn;
+        T v4[4];
+        unsigned loaded = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            T cst = neg_inf<T>();
+            bool need = b4[i] >= 0;
+            if (need && !(p.expanded & 1)) {
+                if (d < p.D) need = n < L4[i];
+                else { need = false; cst = n < L4[i] ? neg_inf<T>() : T(0); }
+            }
+            v4[i] = need ? __ldg(p.ll + b4[i] * p.sb + d * p.sd + n * p.sn) : cst;
+            loaded |= need ? 1u << i : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            T x = v4[i];
+            if ((p.expanded & 2) && ((loaded >> i) & 1u)) x = log_(x);  // ProbSemiring payloads
+            tile[threadIdx.y + 8 * i][threadIdx.x] = x * p.scale;
+        }
     }
     __syncthreads();
     T m = neg_inf<T>();
